@@ -1,0 +1,116 @@
+/* jvmc_b200.h -- C ABI of the B200-native jVMC hot path (libjvmc_b200.so).
+ *
+ * The reference (markusschmitt/vmc_jax, jVMC 1.5.8) is pure Python on JAX and has no FFI of its
+ * own; every entry point below replaces one jit/pmap'd Python function of the per-step VMC path
+ * and is what an XLA-FFI / ctypes / torch binding for that function would bind.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless named host*; complex128 arrays are passed as
+ *     `double*` with interleaved (re, im) pairs; configurations are int32 in {0,..,lDim-1};
+ *   - `stream` is a cudaStream_t; functions enqueue work and return, they never allocate device
+ *     memory and never synchronise (exception: jvmc_eigh waits if cuSOLVER needs a host buffer);
+ *   - return value: 0 = ok, <0 = error code (jvmc_error_string).
+ *   - "tables" is the buffer filled by jvmc_rbm_tables: T[N*M] | lc[N] | tb2[M] | lcb[1] (complex128).
+ *   - Khatri-Rao "site" index r: r = 0 is the bias pseudo-site (sigma = +1) when hasBias, followed by
+ *     the N lattice sites; complex parameter index c = r*M + j  (Flax leaf order: bias, kernel).
+ */
+#ifndef JVMC_B200_H
+#define JVMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JVMC_OK 0
+#define JVMC_ERR_ARG (-1)
+#define JVMC_ERR_CUDA (-2)
+#define JVMC_ERR_UNSUPPORTED (-3)
+#define JVMC_ERR_SOLVER (-4)
+
+int jvmc_version(void);
+const char* jvmc_error_string(int code);
+
+/* NQS.__call__/_eval for CpxRBM/RBM: jVMC/vqs.py:223-251, jVMC/nets/rbm.py:30-38,82-88,
+ * jVMC/nets/activation_functions.py:19-22; also the sampler's final re-evaluation
+ * jVMC/sampler.py:293-296.  s[B,N] -> logpsi[B] (complex), tau[B,M] = tanh(theta) (complex, may be NULL). */
+int jvmc_rbm_logpsi(const int32_t* s, long long B, int N, int M, const double* W, const double* bias,
+                    double* logpsi, double* tau, void* stream);
+
+/* Per-parameter flip-ratio tables tanh(2W), log prod_j cosh(2W_ij), tanh(2b), log prod_j cosh(2 b_j). */
+long long jvmc_rbm_tables_elems(int N, int M);
+int jvmc_rbm_tables(int N, int M, const double* W, const double* bias, double* tables, void* stream);
+
+/* MCSampler._get_samples/_sweep + proposers: jVMC/sampler.py:15-19,30-39,42-64,301-356.
+ * proposer: 0 spin_flip, 1 spin_flip_Z2, 2 spin_flip_zeroMag.  states[C,N] in/out; out[numSamplesPerChain*C, N]
+ * time-major / chain-minor (sampler.py:323); counters[2] += (proposed, accepted).  Philox stream:
+ * (seed; step0 + step, chain0 + chain). */
+int jvmc_rbm_mcmc(int32_t* states, long long C, int N, int M, const double* W, const double* bias,
+                  const double* tables, unsigned long long seed, unsigned long long step0, long long chain0,
+                  int proposer, double mu, int sweepSteps, long long thermSteps, int numSamplesPerChain,
+                  int refreshEvery, int32_t* out, unsigned long long* counters, void* stream);
+
+/* Operator.get_s_primes: jVMC/operator/base.py:91-160 + BranchFreeOperator._get_s_primes
+ * jVMC/operator/branch_free.py:443-487.  Phase 1: all matrix elements mAll[B,numOps] (diagonal strings merged),
+ * choice[B,numOps] (nonzero ops ascending, then numOps-1), count[B], maxCount[1].  Phase 2 (after the caller
+ * read Kmax = *maxCount): sp[B*Kmax,N], matEl[B,Kmax] with the reference's padding. */
+int jvmc_bfo_matels(const int32_t* s, long long B, int N, int numOps, int len, int lDim, const int32_t* idx,
+                    const int32_t* map, const double* matEls, const int32_t* fermi, const uint8_t* isDiag,
+                    int numDiag, const double* pref, double* mAll, int32_t* choice, int32_t* count,
+                    int32_t* maxCount, void* stream);
+int jvmc_bfo_emit(const int32_t* s, long long B, int N, int numOps, int len, int lDim, const int32_t* idx,
+                  const int32_t* map, const double* matEls, const int32_t* fermi, const uint8_t* isDiag,
+                  const double* mAll, const int32_t* choice, const int32_t* count, int Kmax, int32_t* sp,
+                  double* matEl, void* stream);
+
+/* Operator._get_O_loc: jVMC/operator/base.py:162-164. */
+int jvmc_oloc_reduce(const double* matEl, const double* logPsiS, const double* logPsiSP, long long B, int K,
+                     double* out, void* stream);
+
+/* Operator.get_O_loc fast path (base.py:166-192) for (Cpx)RBM + branch-free strings flipping <= 2 sites,
+ * lDim = 2, no fermionic strings.  errFlag (device int) is set to 1 if a string flips more sites. */
+int jvmc_rbm_eloc_bfo(const int32_t* s, const double* tau, long long B, int N, int M, const double* tables,
+                      int numOps, int len, int lDim, const int32_t* idx, const int32_t* map, const double* matEls,
+                      const int32_t* fermi, const uint8_t* isDiag, int numDiag, const double* pref, double* out,
+                      int* errFlag, void* stream);
+
+/* NQS.gradients: jVMC/vqs.py:46-69,256-287.  layout 0: holomorphic [b, i b, W, i W]; 1: real params [b, W]. */
+int jvmc_rbm_grad(const int32_t* s, const double* tau, long long B, int N, int M, int hasBias, int layout,
+                  double* out, void* stream);
+
+/* out[r,j] = sum_n wgt_n sigma_{n,r} (conjTau ? conj tau_nj : tau_nj): SampledObs mean / covar(grads,Eloc) /
+ * MinSR -O^dagger x without forming O (jVMC/stats.py:50-58,204,245; jVMC/util/minsr.py:65).
+ * workspace: jvmc_rbm_moments_chunks(B) * R * M complex128. */
+int jvmc_rbm_moments_chunks(long long B);
+int jvmc_rbm_moments(const int32_t* s, const double* tau, const double* wgt, long long B, int N, int M,
+                     int hasBias, int conjTau, double* workspace, double* out, void* stream);
+
+/* sigT[R][ceil(B/32)] bit-packed transposed spins (bias pseudo-site row first). */
+int jvmc_pack_sigma(const int32_t* s, long long B, int N, int hasBias, unsigned int* sigT, void* stream);
+
+/* SampledObs.covar() of the gradients = S (jVMC/stats.py:235-245, jVMC/util/tdvp.py:142), Khatri-Rao form:
+ * A[(r,j),(r',l)] = alpha sum_n sigma_nr sigma_nr' conj(Y_nj) Y_nl - kappa conj(mu_rj) mu_r'l, A row-major
+ * [R*M, R*M] complex128, fully populated.  tile: 0 auto | 64 | 80. */
+int jvmc_rbm_gram_S(const double* Y, long long B, int M, int R, const unsigned int* sigT, const double* mu,
+                    double alpha, double kappa, double* A, int tile, void* stream);
+
+/* S = q(S0) (+ diagonal shift) in the reference's flat layout from A: jVMC/util/tdvp.py:140-146.
+ * mode 0: Re -> double[P,P]; mode 1: i*Im -> complex128[P,P]; column-major. */
+int jvmc_expand_S(const double* A, int M, int N, int hasBias, int mode, double shift, double* out, void* stream);
+
+/* jnp.linalg.eigh (jVMC/util/tdvp.py:153-171): cuSOLVER Xsyevd, lower, vectors; column-major in/out. */
+int jvmc_eigh_workspace(int n, int isComplex, long long* hostDeviceBytes, long long* hostHostBytes);
+int jvmc_eigh(int n, int isComplex, double* A, double* w, void* work, long long deviceBytes, int* info,
+              void* stream);
+
+/* Regularised pseudo-inverse loop of TDVP.solve (jVMC/util/tdvp.py:193-209) on the device.
+ * VtF, F complex128[n]; snr may be NULL (ExactSampler semantics); scal[0]=residual, scal[1]=cutoff. */
+int jvmc_tdvp_regularize(int n, const double* ev, const double* VtF, const double* snr, const double* F,
+                         double pinvTol, double pinvCutoff, double snrTol, double* pinvEv, double* scal,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

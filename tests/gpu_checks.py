@@ -1,0 +1,313 @@
+"""Kernel-level parity checks: CUDA path (through the C ABI) vs the CPU oracle on identical seeded inputs.
+Used by tests/test_gpu_kernels.py (-m gpu) and by __graft_entry__.smoke()."""
+import numpy as np
+import torch
+
+from oracle import rbm as orbm, bfo as obfo, stats as ostats, solve as osolve, sampling as osamp
+from vmc_jax_b200 import kernels as K
+
+DEV = "cuda:0"
+RTOL = 1e-10   # north_star: logpsi, E_loc, F and S within 1e-10 relative (fp64)
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    den = max(np.max(np.abs(b)), 1e-300)
+    return float(np.max(np.abs(a - b)) / den) if a.size else 0.0
+
+
+def rand_configs(B, N, seed):
+    return np.random.default_rng(seed).integers(0, 2, (B, N)).astype(np.int32)
+
+
+# ---------------------------------------------------------------- logpsi / tau / tables
+def check_logpsi(N=20, M=40, B=333, bias=True, seed=1, real=False):
+    W, b = orbm.init_o1(N, M, bias, seed, real=real)
+    s = rand_configs(B, N, seed + 1)
+    Wc = np.asarray(W, np.complex128)
+    bc = None if b is None else np.asarray(b, np.complex128)
+    lp, tau = K.rbm_logpsi(dev(s), dev(Wc), None if bc is None else dev(bc))
+    ref = orbm.real_rbm_logpsi(s, W, b) if real else orbm.cpx_rbm_logpsi(s, Wc, bc)
+    e1 = np.max(np.abs(host(lp) - ref) / np.maximum(np.abs(ref), 1e-3))
+    e2 = relerr(host(tau), orbm.tau(s, Wc, bc))
+    assert e1 < RTOL and e2 < RTOL, (e1, e2)
+    return e1, e2
+
+
+def check_tables(N=12, M=24, bias=True, seed=3):
+    W, b = orbm.init_o1(N, M, bias, seed)
+    t = host(K.rbm_tables(dev(W), None if b is None else dev(b)))
+    T = t[:N * M].reshape(N, M)
+    lc = t[N * M:N * M + N]
+    tb2 = t[N * M + N:N * M + N + M]
+    lcb = t[-1]
+    assert relerr(T, np.tanh(2 * W)) < RTOL
+    assert relerr(np.exp(lc), np.prod(np.cosh(2 * W), axis=1)) < RTOL
+    if bias:
+        assert relerr(tb2, np.tanh(2 * b)) < RTOL
+        assert relerr(np.exp(lcb), np.prod(np.cosh(2 * b))) < RTOL
+    else:
+        assert np.all(tb2 == 0) and lcb == 0
+
+
+# ---------------------------------------------------------------- operators
+def op_tables_to_device(tab):
+    isDiag = np.zeros(tab.numOps, np.uint8)
+    isDiag[tab.diag] = 1
+    return K.OpTables(tab.idx, tab.map, tab.matEls, tab.fermi, isDiag, DEV)
+
+
+def operator_zoo(N):
+    """Operators covering the reference's test cases (tests/operator_test.py) and BASELINE configs."""
+    zoo = {}
+    zoo["tfim1d"] = obfo.tfim_strings((N,), -0.7, -1.0)
+    zoo["tfim_field"] = [x for l in range(N) for x in
+                         [(-1., [obfo.Sz(l), obfo.Sz((l + 1) % N)]), (-0.7, [obfo.Sx(l)]), (0.1, [obfo.Sz(l)])]]
+    zoo["sx_sysz"] = [x for i in range(N) for x in
+                      [(2., [obfo.Sx(i)]), (2., [obfo.Sy(i), obfo.Sz((i + 1) % N)])]]
+    zoo["splus"] = [(2., [obfo.Sp(i)]) for i in range(3)]
+    zoo["heis"] = [x for l in range(N) for x in
+                   [(1., [obfo.Sx(l), obfo.Sx((l + 1) % N)]), (1., [obfo.Sy(l), obfo.Sy((l + 1) % N)]),
+                    (1., [obfo.Sz(l), obfo.Sz((l + 1) % N)])]]
+    zoo["single_diag"] = [(0.5, [obfo.Sz(0)]), (1.5, [obfo.Sx(1)])]
+    zoo["same_site"] = [(1.0, [obfo.Sz(2), obfo.Sx(2)]), (0.25, [obfo.Sx(1), obfo.Sx(1)]), (1.0, [obfo.Sm(0)])]
+    return zoo
+
+
+def hubbard_strings(L=4):
+    t, mu, V, fl = -1.0, -2.0, 4.0, 2
+    n = fl * L
+    up, do = 0, n - 1
+    S = []
+    for i in range(L):
+        S.append((V, [obfo.number(up + i), obfo.number(do - i)]))
+        S.append((mu, [obfo.number(up + i)]))
+        S.append((mu, [obfo.number(do - i)]))
+        if i == L - 1:
+            continue
+        S.append((t, [obfo.creation(up + i + 1), obfo.annihilation(up + i)]))
+        S.append((t, [obfo.creation(up + i), obfo.annihilation(up + i + 1)]))
+        S.append((t, [obfo.creation(do - i - 1), obfo.annihilation(do - i)]))
+        S.append((t, [obfo.creation(do - i), obfo.annihilation(do - i - 1)]))
+    return S
+
+
+def check_s_primes(strings, N, B=97, seed=5, args=()):
+    """Bit-exact s' / matEl / counts against the oracle (north_star)."""
+    tab = obfo.Tables(strings)
+    s = rand_configs(B, N, seed)
+    sp_ref, m_ref, cnt_ref = obfo.get_s_primes(tab, s, *args)
+    dt = op_tables_to_device(tab)
+    sp, m, cnt = K.bfo_s_primes(dev(s), dt, dev(tab.eval_prefactors(*args)))
+    assert np.array_equal(host(cnt), cnt_ref)
+    assert host(sp).shape == sp_ref.shape and np.array_equal(host(sp), sp_ref)
+    assert np.array_equal(host(m), m_ref), np.max(np.abs(host(m) - m_ref))
+
+
+def check_eloc(strings, N=10, M=20, B=203, bias=False, seed=7, args=()):
+    """Fused RBM E_loc and the generic (s' -> logpsi -> reduce) path vs the reference's algorithm."""
+    tab = obfo.Tables(strings)
+    W, b = orbm.init_o1(N, M, bias, seed)
+    s = rand_configs(B, N, seed + 1)
+    f = lambda x: orbm.cpx_rbm_logpsi(x, W, b)
+    ref = obfo.get_O_loc(tab, s, f, *args)
+    dW, db, ds = dev(W), (None if b is None else dev(b)), dev(s)
+    lp, tau = K.rbm_logpsi(ds, dW, db)
+    dt = op_tables_to_device(tab)
+    pref = dev(tab.eval_prefactors(*args))
+    # generic path
+    sp, m, cnt = K.bfo_s_primes(ds, dt, pref)
+    lpsp, _ = K.rbm_logpsi(sp, dW, db, want_tau=False)
+    e_gen = host(K.oloc_reduce(m, lp, lpsp))
+    # fused path
+    tables = K.rbm_tables(dW, db)
+    e_fused, err = K.rbm_eloc(ds, tau, tables, dt, pref)
+    assert int(err.item()) == 0
+    r1, r2 = relerr(e_gen, ref), relerr(host(e_fused), ref)
+    assert r1 < RTOL and r2 < RTOL, (r1, r2)
+    return r1, r2
+
+
+# ---------------------------------------------------------------- gradients / moments / Gram
+def kr_gradients(s, W, b):
+    """Oracle gradients in Khatri-Rao complex order c = r*M + j (bias pseudo-site first)."""
+    G = orbm.gradients_holomorphic(s, W, b)
+    N, M = W.shape
+    if b is None:
+        return G[:, :N * M]
+    return np.concatenate([G[:, :M], G[:, 2 * M:2 * M + N * M]], axis=1)
+
+
+def check_grad(N=6, M=5, B=17, bias=True, seed=9):
+    W, b = orbm.init_o1(N, M, bias, seed)
+    s = rand_configs(B, N, seed + 1)
+    ds = dev(s)
+    _, tau = K.rbm_logpsi(ds, dev(W), None if b is None else dev(b))
+    g = host(K.rbm_grad(ds, tau, bias, 0))
+    assert relerr(g, orbm.gradients_holomorphic(s, W, b)) < RTOL
+    Wr, br = orbm.init_o1(N, M, bias, seed, real=True)
+    _, taur = K.rbm_logpsi(ds, dev(Wr.astype(np.complex128)), None if br is None else dev(br.astype(np.complex128)))
+    gr = host(K.rbm_grad(ds, taur, bias, 1))
+    assert relerr(gr, orbm.gradients_real(s, Wr, br)) < RTOL
+
+
+def check_moments_gram(N=7, M=24, B=211, bias=True, seed=11, uniform=True, tile=0):
+    """mu, F-kernel and the centred Gram A = <conj(O) O>_c vs the oracle's SampledObs.covar."""
+    W, b = orbm.init_o1(N, M, bias, seed)
+    s = rand_configs(B, N, seed + 1)
+    rng = np.random.default_rng(seed + 2)
+    p = np.ones(B) / B if uniform else rng.uniform(0.5, 1.5, B)
+    p = p / p.sum()
+    E = rng.normal(size=B) + 1j * rng.normal(size=B)
+    O = kr_gradients(s, W, b)
+    obsO, obsE = ostats.SampledObs(O, p), ostats.SampledObs(E, p)
+    A_ref = obsO.covar()
+    F_ref = obsO.covar(obsE).ravel()
+    ds = dev(s)
+    _, tau = K.rbm_logpsi(ds, dev(W), None if b is None else dev(b))
+    dp = dev(p)
+    mu = K.rbm_moments(ds, tau, dp.to(torch.complex128), bias, 0)
+    assert relerr(host(mu).ravel(), obsO.mean()) < RTOL
+    Ebar = np.sum(p * E)
+    Fk = K.rbm_moments(ds, tau, dev(p * (E - Ebar)), bias, 1)
+    assert relerr(host(Fk).ravel(), F_ref) < RTOL
+    sigT = K.pack_sigma(ds, bias)
+    if uniform:
+        A = K.rbm_gram_S(tau, sigT, mu, p[0], 1.0, tile=tile)
+    else:
+        Y = tau * torch.sqrt(dp)[:, None]
+        A = K.rbm_gram_S(Y, sigT, mu, 1.0, 1.0, tile=tile)
+    A = host(A)
+    # scale: the uncentred second moment (A is a difference of two such terms)
+    scale = max(np.max(np.abs(A_ref)), np.max(np.abs(obsO.mean())) ** 2)
+    r = float(np.max(np.abs(A - A_ref)) / scale)
+    assert r < RTOL, r
+    assert np.array_equal(A, A.conj().T)   # exactly Hermitian by construction
+    return r
+
+
+# ---------------------------------------------------------------- solve
+def check_tdvp_solve(N=4, M=3, bias=True, makeReal='real', rhsPrefactor=1.0, shift=2.0, seed=13):
+    """S expansion + eigh + regulariser vs oracle TDVP.solve on the exact basis (no SNR cut, unique update)."""
+    W, b = orbm.init_o1(N, M, bias, seed)
+    basis = osamp.basis_states(N)
+    lp = orbm.cpx_rbm_logpsi(basis, W, b)
+    p, _ = osamp.exact_probabilities(lp)
+    ham = obfo.Tables(obfo.tfim_strings((N,), -0.9, -1.0))
+    E = obfo.get_O_loc(ham, basis, lambda x: orbm.cpx_rbm_logpsi(x, W, b), logPsiS=lp)
+    td = osolve.TDVP(snrTol=1, pinvTol=0.0, pinvCutoff=1e-8, rhsPrefactor=rhsPrefactor, diagonalShift=shift,
+                     makeReal=makeReal, exact_sampler=True)
+    upd_ref, res_ref, cut_ref = osolve.tdvp_rhs(W, b, basis, p, E, td, 2 ** N, orbm.gradients_holomorphic)
+    # device
+    ds, dp = dev(basis), dev(p)
+    _, tau = K.rbm_logpsi(ds, dev(W), None if b is None else dev(b))
+    mu = K.rbm_moments(ds, tau, dp.to(torch.complex128), bias, 0)
+    Ebar = np.sum(p * E)
+    Fc = K.rbm_moments(ds, tau, dev(p * (E - Ebar)), bias, 1).reshape(-1)
+    sigT = K.pack_sigma(ds, bias)
+    A = K.rbm_gram_S(tau * torch.sqrt(dp)[:, None], sigT, mu, 1.0, 1.0)
+    mode = 0 if makeReal == 'real' else 1
+    St = K.expand_S(A, M, N, bias, mode, shift)
+    S_ref = td.S
+    assert relerr(host(St).T, S_ref) < RTOL
+    # F0 = -x [Fc, -i Fc] per leaf (flat layout), F = q(F0)
+    Mb = M if bias else 0
+    parts = []
+    for lo, hi in ([(0, Mb)] if bias else []) + [(Mb, Mb + N * M)]:
+        parts += [Fc[lo:hi], -1j * Fc[lo:hi]]
+    F0 = (-rhsPrefactor) * torch.cat(parts)
+    assert relerr(host(F0), td.F0) < RTOL
+    F = F0.real.to(torch.complex128) if mode == 0 else (1j * F0.imag)
+    ev, Vt, info = K.eigh_inplace(St)
+    assert int(info.item()) == 0
+    assert relerr(host(ev), td.ev) < 1e-9
+    VtF = torch.mv(Vt.conj().to(torch.complex128), F)
+    pinvEv, scal = K.tdvp_regularize(ev, VtF, None, F, 0.0, 1e-8, 1.0)
+    upd = torch.mv(Vt.to(torch.complex128).T, pinvEv * VtF).real
+    r = relerr(host(upd), upd_ref)
+    assert r < 1e-6, r
+    assert abs(scal[1].item() - cut_ref) < 1e-15
+    assert abs(scal[0].item() - res_ref) < 1e-8 * max(1.0, res_ref)
+    return r
+
+
+# ---------------------------------------------------------------- sampler
+def chi2_pvalue(counts, pex):
+    from scipy.stats import chi2
+    n = counts.sum()
+    exp = pex * n
+    keep = exp >= 5
+    c = np.concatenate([counts[keep], [counts[~keep].sum()]]) if (~keep).any() else counts[keep]
+    e = np.concatenate([exp[keep], [exp[~keep].sum()]]) if (~keep).any() else exp[keep]
+    ok = e > 0
+    stat = np.sum((c[ok] - e[ok]) ** 2 / e[ok])
+    return float(chi2.sf(stat, ok.sum() - 1)), stat
+
+
+def run_sampler(W, b, C, numSamples, proposer="spin_flip", mu=2.0, seed=4321, K_sweep=None, therm=20, init=None,
+                refreshEvery=1):
+    N, M = W.shape
+    K_sweep = N if K_sweep is None else K_sweep
+    dW, db = dev(W), (None if b is None else dev(b))
+    tables = K.rbm_tables(dW, db)
+    states = torch.zeros((C, N), dtype=torch.int32, device=DEV)
+    if init is not None:
+        states[:] = dev(np.asarray(init, np.int32))
+    counters = torch.zeros(2, dtype=torch.int64, device=DEV)
+    spc = (numSamples + C - 1) // C
+    cfg = K.rbm_mcmc(states, dW, db, tables, seed, 0, 0, proposer, mu, K_sweep, therm * K_sweep, spc, counters,
+                     refreshEvery)
+    torch.cuda.synchronize()
+    return host(cfg), host(counters), host(states)
+
+
+def check_sampler_chi2(N=4, M=2, weights=None, proposer="spin_flip", mu=2.0, C=592, numSamples=1_000_000,
+                       bias=False, seed=4321, sector=False, refreshEvery=1):
+    """Sampled distribution vs ExactSampler probabilities, chi-squared p-value > 1e-3 (north_star)."""
+    if weights is None:
+        W, b = orbm.init_o1(N, M, bias, 17)
+    else:
+        W, b = orbm.unflatten_params(np.asarray(weights), N, M, bias)
+    basis = osamp.basis_states(N)
+    lp = orbm.cpx_rbm_logpsi(basis, W, b)
+    pex = np.exp(mu * np.real(lp))
+    init = None
+    if sector:
+        mask = basis.sum(1) == N // 2
+        pex = np.where(mask, pex, 0.0)
+        init = np.array([1] * (N // 2) + [0] * (N - N // 2), np.int32)
+    pex /= pex.sum()
+    # 8N Metropolis steps between emitted samples: autocorrelation is negligible, so the plain
+    # chi-squared statistic applies
+    cfg, counters, _ = run_sampler(W, b, C, numSamples, proposer, mu, seed, K_sweep=8 * N, init=init,
+                                   refreshEvery=refreshEvery)
+    ints = (cfg.astype(np.int64) * (2 ** np.arange(N))[None, :]).sum(1)
+    counts = np.bincount(ints, minlength=2 ** N).astype(np.float64)
+    if sector:
+        assert counts[pex == 0].sum() == 0
+    pval, stat = chi2_pvalue(counts, pex)
+    # chains are autocorrelated between emitted samples only weakly (K=N steps per sweep); allow p > 1e-3
+    assert pval > 1e-3, (pval, stat)
+    assert counters[0] > 0 and 0 < counters[1] <= counters[0]
+    return pval
+
+
+def smoke_check():
+    assert torch.cuda.is_available(), "smoke() needs a CUDA device"
+    check_logpsi(N=8, M=16, B=64)
+    check_s_primes(obfo.tfim_strings((8,), -0.7), 8, B=32)
+    check_eloc(obfo.tfim_strings((8,), -0.7), N=8, M=16, B=64)
+    check_moments_gram(N=5, M=16, B=100)
+    check_tdvp_solve()
+    check_sampler_chi2(N=4, M=2, numSamples=200_000, C=148)

@@ -1,0 +1,152 @@
+"""-m gpu: parity of every CUDA kernel (called through the C ABI) against the CPU oracle.
+Tolerances: bit-exact for s'/matEl/counts; 1e-10 relative (fp64) for logpsi, tau, E_loc, F, S
+(BASELINE.json north_star); chi-squared p > 1e-3 for sampled distributions."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import bfo as obfo  # noqa: E402
+import gpu_checks as G  # noqa: E402
+
+with open(os.path.join(os.path.dirname(__file__), "golden", "reference_goldens.json")) as f:
+    REFG = json.load(f)
+
+
+@pytest.mark.parametrize("N,M,B,bias,real", [(20, 40, 333, False, False), (20, 40, 8, True, False),
+                                              (100, 400, 1001, False, False), (40, 80, 77, True, False),
+                                              (6, 3, 1, True, False), (12, 7, 50, True, True),
+                                              (400, 160, 64, False, False)])
+def test_logpsi_tau(N, M, B, bias, real):
+    G.check_logpsi(N, M, B, bias, seed=N + M, real=real)
+
+
+def test_logpsi_empty_batch():
+    import torch
+    from vmc_jax_b200 import kernels as K
+    W = G.dev(np.ones((4, 2), np.complex128))
+    lp, tau = K.rbm_logpsi(torch.zeros((0, 4), dtype=torch.int32, device=G.DEV), W)
+    assert lp.shape == (0,) and tau.shape == (0, 2)
+
+
+@pytest.mark.parametrize("bias", [False, True])
+def test_tables(bias):
+    G.check_tables(bias=bias)
+
+
+@pytest.mark.parametrize("name", ["tfim1d", "tfim_field", "sx_sysz", "splus", "heis", "single_diag", "same_site"])
+def test_s_primes_bit_exact(name):
+    N = 8
+    G.check_s_primes(G.operator_zoo(N)[name], N)
+
+
+def test_s_primes_2d_tfim_and_ragged():
+    G.check_s_primes(obfo.tfim_strings((4, 4), 3.04), 16, B=33)
+    G.check_s_primes(obfo.tfim_strings((10, 10), 3.04), 100, B=5)
+    G.check_s_primes(obfo.tfim_strings((6,), 1.0), 6, B=1)
+
+
+def test_s_primes_time_dependent_prefactor():
+    strings = [(lambda t: 2.0 * t, [obfo.Sp(i)]) for i in range(3)]
+    for t in [0.5, 2, 13.9]:
+        G.check_s_primes(strings, 4, B=24, args=(t,))
+
+
+def test_s_primes_fermionic_bit_exact():
+    G.check_s_primes(G.hubbard_strings(4), 8, B=256)
+
+
+def test_s_primes_all_zero_rows():
+    # S+ on all-ones configurations: no nonzero entry at all -> Kmax = 0
+    import torch
+    from vmc_jax_b200 import kernels as K
+    tab = obfo.Tables([(2., [obfo.Sp(i)]) for i in range(3)])
+    s = np.ones((5, 4), np.int32)
+    sp, m, cnt = K.bfo_s_primes(G.dev(s), G.op_tables_to_device(tab), G.dev(tab.eval_prefactors()))
+    assert sp.shape == (0, 4) and m.shape == (5, 0) and int(cnt.sum()) == 0
+
+
+@pytest.mark.parametrize("name", ["tfim1d", "tfim_field", "sx_sysz", "heis", "single_diag", "same_site"])
+@pytest.mark.parametrize("bias", [False, True])
+def test_eloc_fused_and_generic(name, bias):
+    N = 10
+    G.check_eloc(G.operator_zoo(N)[name], N=N, M=20, bias=bias)
+
+
+def test_eloc_2d_tfim_config2_shape():
+    G.check_eloc(obfo.tfim_strings((10, 10), 3.04), N=100, M=400, B=64)
+
+
+def test_grad_layouts():
+    G.check_grad(bias=True)
+    G.check_grad(bias=False)
+    G.check_grad(N=20, M=40, B=9, bias=False)
+
+
+@pytest.mark.parametrize("N,M,B,bias,uniform,tile", [
+    (7, 24, 211, True, True, 0), (7, 24, 211, False, False, 0), (5, 80, 100, False, True, 0),
+    (3, 40, 37, True, False, 0), (4, 100, 64, False, True, 0), (6, 160, 50, True, True, 0),
+    (5, 80, 100, False, True, 64), (20, 40, 450, False, True, 0), (2, 70, 1, False, True, 0)])
+def test_moments_and_gram(N, M, B, bias, uniform, tile):
+    G.check_moments_gram(N, M, B, bias, uniform=uniform, tile=tile)
+
+
+@pytest.mark.parametrize("makeReal,x,shift,bias", [('real', 1.0, 2.0, False), ('real', 1.0, 0.0, True),
+                                                  ('imag', 1.j, 0.0, False), ('imag', 1.j, 0.0, True)])
+def test_tdvp_solve(makeReal, x, shift, bias):
+    G.check_tdvp_solve(makeReal=makeReal, rhsPrefactor=x, shift=shift, bias=bias)
+
+
+def test_sampler_reference_weights():
+    """reference tests/sampler_test.py:32-75 (bare CpxRBM, fixed 16-float weight vector)."""
+    G.check_sampler_chi2(N=4, M=2, weights=REFG["rbm_weights"], numSamples=1_000_000)
+
+
+@pytest.mark.parametrize("N,M", [(4, 8), (8, 16), (12, 24)])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_sampler_chi2_spin_flip(N, M, seed):
+    G.check_sampler_chi2(N=N, M=M, numSamples=1_000_000, seed=seed)
+
+
+def test_sampler_chi2_16_sites():
+    G.check_sampler_chi2(N=16, M=32, numSamples=2_000_000, C=1184)
+
+
+@pytest.mark.parametrize("bias", [False, True])
+def test_sampler_chi2_z2(bias):
+    G.check_sampler_chi2(N=8, M=16, proposer="spin_flip_Z2", bias=bias, numSamples=1_000_000)
+
+
+@pytest.mark.parametrize("bias", [False, True])
+def test_sampler_chi2_zero_mag(bias):
+    G.check_sampler_chi2(N=8, M=16, proposer="spin_flip_zeroMag", bias=bias, sector=True, numSamples=1_000_000)
+
+
+def test_sampler_mu1_and_rare_refresh():
+    G.check_sampler_chi2(N=8, M=16, mu=1.0, numSamples=1_000_000)
+    G.check_sampler_chi2(N=8, M=16, numSamples=1_000_000, refreshEvery=64)
+
+
+def test_sampler_stream_independent_of_chain_partition():
+    """Philox is keyed by global chain id: two half-size launches reproduce one full launch (multi-GPU sharding)."""
+    import torch
+    from oracle import rbm as orbm
+    from vmc_jax_b200 import kernels as K
+    N, M, C = 8, 16, 64
+    W, b = orbm.init_o1(N, M, False, 3)
+    dW = G.dev(W)
+    tables = K.rbm_tables(dW, None)
+
+    def run(chain0, nchains):
+        st = torch.zeros((nchains, N), dtype=torch.int32, device=G.DEV)
+        cnt = torch.zeros(2, dtype=torch.int64, device=G.DEV)
+        out = K.rbm_mcmc(st, dW, None, tables, 99, 0, chain0, "spin_flip", 2.0, N, 5 * N, 7, cnt)
+        return G.host(out).reshape(7, nchains, N), G.host(cnt)
+    full, cf = run(0, C)
+    a, ca = run(0, C // 2)
+    bb, cb = run(C // 2, C // 2)
+    assert np.array_equal(full, np.concatenate([a, bb], axis=1))
+    assert np.array_equal(cf, ca + cb)

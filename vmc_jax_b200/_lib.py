@@ -1,0 +1,105 @@
+"""ctypes binding of libjvmc_b200.so (the C ABI declared in include/jvmc_b200.h).
+
+There is no CPU fallback: if the library is missing, or no CUDA device is present when a kernel is
+requested, the call raises."""
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjvmc_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "jvmc_b200.h")
+
+_lib = None
+
+c_ll = ctypes.c_longlong
+c_ull = ctypes.c_ulonglong
+c_int = ctypes.c_int
+c_dbl = ctypes.c_double
+c_ptr = ctypes.c_void_p
+
+_SIGS = {
+    "jvmc_version": (c_int, []),
+    "jvmc_error_string": (ctypes.c_char_p, [c_int]),
+    "jvmc_rbm_logpsi": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "jvmc_rbm_tables_elems": (c_ll, [c_int, c_int]),
+    "jvmc_rbm_tables": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "jvmc_rbm_mcmc": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ull, c_ull, c_ll, c_int, c_dbl,
+                              c_int, c_ll, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "jvmc_bfo_matels": (c_int, [c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int,
+                                c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "jvmc_bfo_emit": (c_int, [c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                              c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
+    "jvmc_oloc_reduce": (c_int, [c_ptr, c_ptr, c_ptr, c_ll, c_int, c_ptr, c_ptr]),
+    "jvmc_rbm_eloc_bfo": (c_int, [c_ptr, c_ptr, c_ll, c_int, c_int, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr,
+                                  c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "jvmc_rbm_grad": (c_int, [c_ptr, c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
+    "jvmc_rbm_moments_chunks": (c_int, [c_ll]),
+    "jvmc_rbm_moments": (c_int, [c_ptr, c_ptr, c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "jvmc_pack_sigma": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr]),
+    "jvmc_rbm_gram_S": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_int, c_ptr]),
+    "jvmc_expand_S": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr]),
+    "jvmc_eigh_workspace": (c_int, [c_int, c_int, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll)]),
+    "jvmc_eigh": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ll, c_ptr, c_ptr]),
+    "jvmc_tdvp_regularize": (c_int, [c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr]),
+}
+
+
+def declared_symbols():
+    """Names of every function declared in include/jvmc_b200.h."""
+    with open(HEADER) as f:
+        txt = f.read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(jvmc_[a-zA-Z0-9_]+)\s*\(", txt)))
+
+
+def load():
+    """Load the shared library and bind every declared symbol (raises if one is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libjvmc_b200.so not found at %s: build it with `python __graft_entry__.py` "
+            "(there is no CPU fallback for the VMC hot path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name in declared_symbols():
+        fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+        if name not in _SIGS:
+            raise RuntimeError("no ctypes signature registered for " + name)
+        fn.restype, fn.argtypes = _SIGS[name]
+    _lib = lib
+    return lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("vmc_jax_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def ptr(t):
+    """Device pointer of a (contiguous) tensor, or None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "kernel arguments must be contiguous"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().jvmc_error_string(rc).decode()
+        raise RuntimeError("libjvmc_b200 %s failed: %s (code %d)" % (what, msg, rc))
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point on the current stream (appended as last argument)."""
+    require_cuda()
+    lib = load()
+    rc = getattr(lib, name)(*args, stream())
+    check(rc, name)

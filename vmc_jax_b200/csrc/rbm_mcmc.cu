@@ -1,0 +1,286 @@
+// jvmc_rbm_mcmc -- parallel-chain Metropolis sampler for (Cpx)RBM wave functions.
+//
+// Replaces MCSampler._get_samples / _sweep.perform_mc_update (reference jVMC/sampler.py:301-356)
+// and the proposers propose_spin_flip / _Z2 / _zeroMag (jVMC/sampler.py:15-19,30-39,42-64).
+//
+// One warp per Markov chain.  The chain keeps tau_j = tanh(theta_j) (theta = sigma W + b) in shared
+// memory and the configuration as a bit mask in registers (lane l owns sites 32l..32l+31).  A
+// proposal that flips sites a (and b) changes theta by Delta = -2 sigma_a W_a (- 2 sigma_b W_b) and
+//    psi(s')/psi(s) = prod_a cosh-prod(a) * prod_j [ d_j + tau_j n_j ],
+//    one flip : n = t_a, d = 1;   two flips: n = t_a + t_b, d = 1 + t_a t_b,  t_a = -sigma_a tanh(2W_aj)
+// (tanh/cosh addition theorems), so a proposal costs M complex multiply-adds instead of a full
+// N*M forward pass; tanh(2W) and log prod_j cosh(2W_ij) are per-parameter tables (jvmc_rbm_tables).
+// Accepted moves update tau rationally, tau' = (tau d + n)/(d + tau n); tau is re-derived from
+// theta = sigma W + b every `refreshEvery` sweeps to stop round-off drift.
+// Global Z2 flip (prob. 1/5 in the _Z2/_zeroMag proposers): theta -> -theta + 2b.
+//
+// RNG: Philox4x32-10 keyed by the seed, counter = (Metropolis step, global chain id, purpose):
+// results are independent of how chains are distributed over GPUs.  The reference's threefry
+// stream is not reproduced (parity is distributional).
+#include "common.cuh"
+
+namespace {
+
+constexpr int MC_WPC = 4;  // warps (= chains) per CTA
+
+struct McmcArgs {
+  int32_t* states;
+  long long C;
+  int N, M;
+  const cplx* W;
+  const cplx* bias;
+  const cplx* T;
+  const cplx* lc;
+  const cplx* tb2;
+  const cplx* lcb;
+  unsigned long long seed, step0;
+  long long chain0;
+  int proposer;
+  double mu;
+  int K;
+  long long thermSteps;
+  int numSamples;
+  int refreshEvery;
+  int32_t* out;
+  unsigned long long* counters;
+};
+
+__device__ __forceinline__ int nth_set_bit(uint32_t w, int n) {  // n >= 1, position of n-th set bit
+  for (int k = 1; k < n; ++k) w &= w - 1;
+  return __ffs(w) - 1;
+}
+
+// site index of the r-th (1-based) set bit of the warp-distributed mask; -1 if fewer than r bits set
+__device__ __forceinline__ int warp_select(uint32_t word, int r, int lane) {
+  int cnt = __popc(word);
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  int exc = inc - cnt;
+  bool mine = (r > exc) && (r <= inc);
+  int pos = mine ? (lane * 32 + nth_set_bit(word, r - exc)) : -1;
+  unsigned who = __ballot_sync(0xffffffffu, mine);
+  if (who == 0) return -1;
+  return __shfl_sync(0xffffffffu, pos, __ffs(who) - 1);
+}
+
+__global__ void __launch_bounds__(MC_WPC * 32)
+rbm_mcmc_kernel(McmcArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long chain = (long long)blockIdx.x * MC_WPC + warp;
+  if (chain >= a.C) return;  // whole warp exits together
+  const int N = a.N, M = a.M;
+  cplx* tau = reinterpret_cast<cplx*>(smem_raw) + (size_t)warp * M;
+  uint32_t* sbits = reinterpret_cast<uint32_t*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)MC_WPC * M) + warp * 32;
+  const bool hasBias = a.bias != nullptr;
+  const unsigned long long gchain = (unsigned long long)(a.chain0 + chain);
+  const Philox rng(a.seed);
+
+  // load configuration bits
+  uint32_t valid = 0, bits = 0;
+  {
+    int base = lane * 32;
+    for (int k = 0; k < 32; ++k) {
+      int i = base + k;
+      if (i < N) {
+        valid |= 1u << k;
+        if (a.states[chain * N + i] != 0) bits |= 1u << k;
+      }
+    }
+  }
+
+  auto refresh = [&]() {
+    sbits[lane] = bits;
+    __syncwarp();
+    for (int j0 = 0; j0 < M; j0 += 32) {
+      int j = j0 + lane;
+      if (j < M) {
+        cplx acc = hasBias ? a.bias[j] : cmk(0.0, 0.0);
+        for (int i = 0; i < N; ++i) {
+          double sg = ((sbits[i >> 5] >> (i & 31)) & 1u) ? 1.0 : -1.0;
+          cplx w = a.W[(size_t)i * M + j];
+          acc.x = fma(sg, w.x, acc.x);
+          acc.y = fma(sg, w.y, acc.y);
+        }
+        cplx l, t;
+        lncosh_tanh(acc, l, t);
+        tau[j] = t;
+      }
+    }
+    __syncwarp();
+  };
+
+  unsigned long long nAcc = 0, nProp = 0;
+  const long long total = a.thermSteps + (long long)a.numSamples * a.K;
+  long long nextEmit = a.thermSteps + a.K;
+  int emitted = 0;
+  int sweepCtr = 0;
+  refresh();
+
+  for (long long st = 0; st < total; ++st) {
+    const unsigned long long gs = a.step0 + (unsigned long long)st;
+    uint4 r = rng((uint32_t)gs, (uint32_t)(gs >> 32), (uint32_t)gchain, (uint32_t)(gchain >> 32) << 8);
+    int sa = -1, sb = -1;  // flipped sites
+    bool g = false;
+    if (a.proposer == 2) {
+      int half = N / 2;
+      int ru = 1 + (int)__umulhi(r.x, (uint32_t)half);
+      int rd = 1 + (int)__umulhi(r.y, (uint32_t)half);
+      sa = warp_select(bits, ru, lane);
+      sb = warp_select((~bits) & valid, rd, lane);
+      if (sa < 0) { sa = sb; sb = -1; }
+      uint4 r2 = rng((uint32_t)gs, (uint32_t)(gs >> 32), (uint32_t)gchain, ((uint32_t)(gchain >> 32) << 8) | 1u);
+      g = __umulhi(r2.x, 5u) == 0u;
+    } else {
+      sa = (int)__umulhi(r.x, (uint32_t)N);
+      g = (a.proposer == 1) && (__umulhi(r.y, 5u) == 0u);
+    }
+    const bool gb = g && hasBias;
+    double sga = 0.0, sgb = 0.0;  // -sigma of the flipped sites
+    double lre = 0.0;
+    const cplx* Ta = a.T;
+    const cplx* Tb = a.T;
+    if (sa >= 0) {
+      uint32_t w = __shfl_sync(0xffffffffu, bits, sa >> 5);
+      sga = ((w >> (sa & 31)) & 1u) ? -1.0 : 1.0;
+      Ta = a.T + (size_t)sa * M;
+      lre += a.lc[sa].x;
+    }
+    if (sb >= 0) {
+      uint32_t w = __shfl_sync(0xffffffffu, bits, sb >> 5);
+      sgb = ((w >> (sb & 31)) & 1u) ? -1.0 : 1.0;
+      Tb = a.T + (size_t)sb * M;
+      lre += a.lc[sb].x;
+    }
+    if (gb) lre += a.lcb[0].x;
+
+    double prod = 1.0;
+    if (sb < 0 && !gb) {
+      // hot path: single flip, f = 1 + tau * t_a
+      if (sa >= 0) {
+        for (int j = lane; j < M; j += 32) {
+          cplx t = Ta[j];
+          cplx tj = tau[j];
+          double fr = fma(sga, fma(tj.x, t.x, -tj.y * t.y), 1.0);
+          double fi = sga * fma(tj.x, t.y, tj.y * t.x);
+          prod *= fma(fr, fr, fi * fi);
+        }
+      }
+    } else {
+      for (int j = lane; j < M; j += 32) {
+        cplx ta = cscale(Ta[j], sga);
+        cplx n = ta, d = cmk(1.0, 0.0);
+        if (sb >= 0) {
+          cplx tb = cscale(Tb[j], sgb);
+          n = cadd(ta, tb);
+          d = cadd(d, cmul(ta, tb));
+        }
+        cplx tj = tau[j];
+        cplx f = cadd(d, cmul(tj, n));
+        if (gb) {
+          cplx t1 = cdiv(cadd(cmul(tj, d), n), f);
+          cplx f2 = csub(cmk(1.0, 0.0), cmul(t1, a.tb2[j]));
+          f = cmul(f, f2);
+        }
+        prod *= cabs2(f);
+      }
+    }
+    prod = warp_prod(prod);
+    double P;
+    if (a.mu == 2.0) P = exp(2.0 * lre) * prod;
+    else P = exp(a.mu * (lre + 0.5 * log(prod)));
+    const double u = u01_from_bits(r.z, r.w);
+    const bool accept = u < P;
+    nProp += 1;
+    if (accept) {
+      nAcc += 1;
+      for (int j = lane; j < M; j += 32) {
+        cplx tj = tau[j];
+        cplx tn = tj;
+        if (sa >= 0) {
+          cplx ta = cscale(Ta[j], sga);
+          cplx n = ta, d = cmk(1.0, 0.0);
+          if (sb >= 0) {
+            cplx tb = cscale(Tb[j], sgb);
+            n = cadd(ta, tb);
+            d = cadd(d, cmul(ta, tb));
+          }
+          tn = cdiv(cadd(cmul(tj, d), n), cadd(d, cmul(tj, n)));
+        }
+        if (g) {
+          if (hasBias) {
+            cplx b2 = a.tb2[j];
+            tn = cdiv(csub(b2, tn), csub(cmk(1.0, 0.0), cmul(b2, tn)));
+          } else {
+            tn = cmk(-tn.x, -tn.y);
+          }
+        }
+        tau[j] = tn;
+      }
+      if (sa >= 0 && (sa >> 5) == lane) bits ^= 1u << (sa & 31);
+      if (sb >= 0 && (sb >> 5) == lane) bits ^= 1u << (sb & 31);
+      if (g) bits = (~bits) & valid;
+      __syncwarp();
+    }
+    // sweep bookkeeping
+    if (st + 1 == nextEmit) {
+      const long long row = (long long)emitted * a.C + chain;  // time-major, chain-minor (sampler.py:323)
+      int32_t* dst = a.out + row * N;
+      for (int w = 0; w * 32 < N; ++w) {
+        uint32_t word = __shfl_sync(0xffffffffu, bits, w);
+        int i = w * 32 + lane;
+        if (i < N) dst[i] = (int32_t)((word >> lane) & 1u);
+      }
+      ++emitted;
+      nextEmit += a.K;
+    }
+    if ((st + 1) % a.K == 0) {
+      if (++sweepCtr >= a.refreshEvery && st + 1 < total) { sweepCtr = 0; refresh(); }
+    }
+  }
+  // persist chain state and counters
+  for (int w = 0; w * 32 < N; ++w) {
+    uint32_t word = __shfl_sync(0xffffffffu, bits, w);
+    int i = w * 32 + lane;
+    if (i < N) a.states[chain * N + i] = (int32_t)((word >> lane) & 1u);
+  }
+  if (lane == 0) {
+    atomicAdd(a.counters + 0, nProp);
+    atomicAdd(a.counters + 1, nAcc);
+  }
+}
+
+}  // namespace
+
+extern "C" int jvmc_rbm_mcmc(int32_t* states, long long C, int N, int M, const double* W, const double* bias,
+                             const double* tables, unsigned long long seed, unsigned long long step0,
+                             long long chain0, int proposer, double mu, int sweepSteps, long long thermSteps,
+                             int numSamplesPerChain, int refreshEvery, int32_t* out, unsigned long long* counters,
+                             void* stream) {
+  if (!states || !W || !tables || !counters || C < 0 || N <= 0 || M <= 0) return JVMC_ERR_ARG;
+  if (numSamplesPerChain > 0 && !out) return JVMC_ERR_ARG;
+  if (N > 1024) return JVMC_ERR_UNSUPPORTED;
+  if (proposer < 0 || proposer > 2 || sweepSteps <= 0 || thermSteps < 0 || numSamplesPerChain < 0) return JVMC_ERR_ARG;
+  if (proposer == 2 && (N % 2 != 0)) return JVMC_ERR_ARG;
+  if (C == 0) return JVMC_OK;
+  McmcArgs a;
+  a.states = states; a.C = C; a.N = N; a.M = M;
+  a.W = (const cplx*)W; a.bias = (const cplx*)bias;
+  a.T = (const cplx*)tables; a.lc = a.T + (size_t)N * M; a.tb2 = a.lc + N; a.lcb = a.tb2 + M;
+  a.seed = seed; a.step0 = step0; a.chain0 = chain0; a.proposer = proposer; a.mu = mu;
+  a.K = sweepSteps; a.thermSteps = thermSteps; a.numSamples = numSamplesPerChain;
+  a.refreshEvery = refreshEvery > 0 ? refreshEvery : 1;
+  a.out = out; a.counters = counters;
+  size_t smem = (size_t)MC_WPC * M * sizeof(cplx) + MC_WPC * 32 * sizeof(uint32_t);
+  if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(rbm_mcmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  unsigned grid = (unsigned)((C + MC_WPC - 1) / MC_WPC);
+  rbm_mcmc_kernel<<<grid, MC_WPC * 32, smem, (cudaStream_t)stream>>>(a);
+  JVMC_CHECK_LAUNCH();
+  return JVMC_OK;
+}

@@ -1,0 +1,213 @@
+"""Tensor-level wrappers around the C ABI (one function per entry point of include/jvmc_b200.h).
+
+torch is used for device memory and streams only; all arithmetic of the hot path happens in the
+kernels of libjvmc_b200.so.  Complex tensors are complex128, configurations int32."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ptr, call
+
+CPX = torch.complex128
+F64 = torch.float64
+I32 = torch.int32
+
+PROPOSER_IDS = {"spin_flip": 0, "spin_flip_Z2": 1, "spin_flip_zeroMag": 2}
+
+
+def _c(t, dtype=None):
+    if t is None:
+        return None
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def rbm_logpsi(s, W, b=None, want_tau=True):
+    """s int32[B,N]; W complex128[N,M]; b complex128[M]|None -> logpsi[B], tau[B,M]|None."""
+    s = _c(s, I32)
+    W = _c(W, CPX)
+    b = _c(b, CPX)
+    B, N = s.shape
+    M = W.shape[1]
+    assert W.shape[0] == N
+    logpsi = torch.empty(B, dtype=CPX, device=s.device)
+    tau = torch.empty((B, M), dtype=CPX, device=s.device) if want_tau else None
+    call("jvmc_rbm_logpsi", ptr(s), B, N, M, ptr(W), ptr(b), ptr(logpsi), ptr(tau))
+    return logpsi, tau
+
+
+def rbm_tables(W, b=None):
+    W = _c(W, CPX)
+    b = _c(b, CPX)
+    N, M = W.shape
+    n = _lib.load().jvmc_rbm_tables_elems(N, M)
+    tables = torch.empty(n, dtype=CPX, device=W.device)
+    call("jvmc_rbm_tables", N, M, ptr(W), ptr(b), ptr(tables))
+    return tables
+
+
+def rbm_mcmc(states, W, b, tables, seed, step0, chain0, proposer, mu, sweepSteps, thermSteps, numSamplesPerChain,
+             counters, refreshEvery=1):
+    """states int32[C,N] updated in place; returns configs int32[numSamplesPerChain*C, N]."""
+    assert states.dtype == I32 and states.is_contiguous()
+    C, N = states.shape
+    W = _c(W, CPX)
+    b = _c(b, CPX)
+    M = W.shape[1]
+    out = torch.empty((numSamplesPerChain * C, N), dtype=I32, device=states.device)
+    pid = PROPOSER_IDS[proposer] if isinstance(proposer, str) else int(proposer)
+    call("jvmc_rbm_mcmc", ptr(states), C, N, M, ptr(W), ptr(b), ptr(tables), ctypes.c_ulonglong(seed),
+         ctypes.c_ulonglong(step0), chain0, pid, float(mu), int(sweepSteps), int(thermSteps),
+         int(numSamplesPerChain), int(refreshEvery), ptr(out), ptr(counters))
+    return out
+
+
+class OpTables:
+    """Device copy of the compiled operator tables (BranchFreeOperator.compile)."""
+
+    def __init__(self, idx, mp, matEls, fermi, isDiag, device):
+        self.numOps, self.len = idx.shape
+        self.lDim = mp.shape[2]
+        self.idx = torch.as_tensor(idx, dtype=I32).contiguous().to(device)
+        self.map = torch.as_tensor(mp, dtype=I32).contiguous().to(device)
+        self.matEls = torch.as_tensor(matEls, dtype=CPX).contiguous().to(device)
+        self.fermi = torch.as_tensor(fermi, dtype=I32).contiguous().to(device)
+        self.isDiag = torch.as_tensor(isDiag, dtype=torch.uint8).contiguous().to(device)
+        self.numDiag = int(torch.as_tensor(isDiag).sum())
+
+    def args(self):
+        return (self.numOps, self.len, self.lDim, ptr(self.idx), ptr(self.map), ptr(self.matEls), ptr(self.fermi),
+                ptr(self.isDiag))
+
+
+def bfo_s_primes(s, tab, pref):
+    """Operator.get_s_primes on the device: returns sp[B*Kmax,N], matEl[B,Kmax], count[B]."""
+    s = _c(s, I32)
+    pref = _c(pref, CPX)
+    B, N = s.shape
+    dev = s.device
+    mAll = torch.empty((B, tab.numOps), dtype=CPX, device=dev)
+    choice = torch.empty((B, tab.numOps), dtype=I32, device=dev)
+    count = torch.empty(B, dtype=I32, device=dev)
+    maxCount = torch.zeros(1, dtype=I32, device=dev)
+    call("jvmc_bfo_matels", ptr(s), B, N, *tab.args(), tab.numDiag, ptr(pref), ptr(mAll), ptr(choice), ptr(count),
+         ptr(maxCount))
+    Kmax = int(maxCount.item())   # data-dependent output shape: the one host sync of this API (base.py:157)
+    sp = torch.empty((B * Kmax, N), dtype=I32, device=dev)
+    matEl = torch.empty((B, Kmax), dtype=CPX, device=dev)
+    call("jvmc_bfo_emit", ptr(s), B, N, *tab.args(), ptr(mAll), ptr(choice), ptr(count), Kmax, ptr(sp), ptr(matEl))
+    return sp, matEl, count
+
+
+def oloc_reduce(matEl, logPsiS, logPsiSP):
+    matEl = _c(matEl, CPX)
+    logPsiS = _c(logPsiS, CPX)
+    logPsiSP = _c(logPsiSP, CPX)
+    B, K = matEl.shape
+    out = torch.empty(B, dtype=CPX, device=matEl.device)
+    call("jvmc_oloc_reduce", ptr(matEl), ptr(logPsiS), ptr(logPsiSP), B, K, ptr(out))
+    return out
+
+
+def rbm_eloc(s, tau, tables, tab, pref):
+    s = _c(s, I32)
+    tau = _c(tau, CPX)
+    pref = _c(pref, CPX)
+    B, N = s.shape
+    M = tau.shape[1]
+    out = torch.empty(B, dtype=CPX, device=s.device)
+    err = torch.zeros(1, dtype=I32, device=s.device)
+    call("jvmc_rbm_eloc_bfo", ptr(s), ptr(tau), B, N, M, ptr(tables), *tab.args(), tab.numDiag, ptr(pref), ptr(out),
+         ptr(err))
+    return out, err
+
+
+def rbm_grad(s, tau, hasBias, layout):
+    s = _c(s, I32)
+    tau = _c(tau, CPX)
+    B, N = s.shape
+    M = tau.shape[1]
+    Mb = M if hasBias else 0
+    P = 2 * (Mb + N * M) if layout == 0 else Mb + N * M
+    out = torch.empty((B, P), dtype=CPX, device=s.device)
+    call("jvmc_rbm_grad", ptr(s), ptr(tau), B, N, M, int(hasBias), int(layout), ptr(out))
+    return out
+
+
+def rbm_moments(s, tau, wgt, hasBias, conjTau):
+    """out[r,j] = sum_n wgt_n sigma_nr (conj?)tau_nj, r = [bias pseudo-site,] sites."""
+    s = _c(s, I32)
+    tau = _c(tau, CPX)
+    wgt = _c(wgt, CPX)
+    B, N = s.shape
+    M = tau.shape[1]
+    R = N + (1 if hasBias else 0)
+    chunks = _lib.load().jvmc_rbm_moments_chunks(B)
+    ws = torch.empty(chunks * R * M, dtype=CPX, device=s.device)
+    out = torch.empty((R, M), dtype=CPX, device=s.device)
+    call("jvmc_rbm_moments", ptr(s), ptr(tau), ptr(wgt), B, N, M, int(hasBias), int(conjTau), ptr(ws), ptr(out))
+    return out
+
+
+def pack_sigma(s, hasBias):
+    s = _c(s, I32)
+    B, N = s.shape
+    R = N + (1 if hasBias else 0)
+    words = (B + 31) // 32
+    sigT = torch.empty((R, max(words, 1)), dtype=I32, device=s.device)
+    call("jvmc_pack_sigma", ptr(s), B, N, int(hasBias), ptr(sigT))
+    return sigT
+
+
+def rbm_gram_S(Y, sigT, mu, alpha, kappa, out=None, tile=0):
+    """A[(r,j),(r',l)] (row-major [R*M, R*M] complex128)."""
+    Y = _c(Y, CPX)
+    B, M = Y.shape
+    R = sigT.shape[0]
+    mu = _c(mu, CPX)
+    if out is None:
+        out = torch.empty((R * M, R * M), dtype=CPX, device=Y.device)
+    call("jvmc_rbm_gram_S", ptr(Y), B, M, R, ptr(sigT), ptr(mu), float(alpha), float(kappa), ptr(out), int(tile))
+    return out
+
+
+def expand_S(A, M, N, hasBias, mode, shift):
+    """Column-major S = q(S0) in the reference's flat layout (returned as a [P,P] tensor holding S^T)."""
+    Mb = M if hasBias else 0
+    P = 2 * (Mb + N * M)
+    out = torch.empty((P, P), dtype=F64 if mode == 0 else CPX, device=A.device)
+    call("jvmc_expand_S", ptr(A), M, N, int(hasBias), int(mode), float(shift), ptr(out))
+    return out
+
+
+def eigh_inplace(St):
+    """Eigen-decomposition of the Hermitian matrix whose column-major image is ``St`` (i.e. St = S^T as
+    a row-major tensor; lower triangle of S referenced).  Overwrites St with the eigenvectors: row k of
+    the result is eigenvector k.  Returns (ev ascending, Vt)."""
+    n = St.shape[0]
+    isC = St.is_complex()
+    lib = _lib.load()
+    d = ctypes.c_longlong(0)
+    h = ctypes.c_longlong(0)
+    _lib.require_cuda()
+    _lib.check(lib.jvmc_eigh_workspace(n, int(isC), ctypes.byref(d), ctypes.byref(h)), "jvmc_eigh_workspace")
+    work = torch.empty(max(d.value, 8), dtype=torch.uint8, device=St.device)
+    w = torch.empty(n, dtype=F64, device=St.device)
+    info = torch.zeros(1, dtype=I32, device=St.device)
+    call("jvmc_eigh", n, int(isC), ptr(St), ptr(w), ptr(work), d.value, ptr(info))
+    return w, St, info
+
+
+def tdvp_regularize(ev, VtF, snr, F, pinvTol, pinvCutoff, snrTol):
+    n = ev.shape[0]
+    ev = _c(ev, F64)
+    VtF = _c(VtF, CPX)
+    F = _c(F, CPX)
+    snr = _c(snr, F64)
+    pinvEv = torch.empty(n, dtype=F64, device=ev.device)
+    scal = torch.empty(2, dtype=F64, device=ev.device)
+    call("jvmc_tdvp_regularize", n, ptr(ev), ptr(VtF), ptr(snr), ptr(F), float(pinvTol), float(pinvCutoff),
+         float(snrTol), ptr(pinvEv), ptr(scal))
+    return pinvEv, scal
