@@ -1,0 +1,414 @@
+"""-m gpu: the jVMC-compatible Python API on top of the CUDA kernels, written like the reference's own
+tests (tests/tdvp_test.py, minsr_test.py, sampler_test.py, operator_test.py, stats_test.py, vqs_test.py)
+and checked against the reference's golden values and the CPU oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import jVMC  # noqa: E402  (alias of vmc_jax_b200)
+import jVMC.nets as nets  # noqa: E402
+import jVMC.operator as op  # noqa: E402
+import jVMC.sampler as sampler  # noqa: E402
+import jVMC.util.stepper as jVMCstepper  # noqa: E402
+from jVMC.util import measure, ground_state_search  # noqa: E402
+from jVMC.vqs import NQS  # noqa: E402
+from jVMC.stats import SampledObs, RBMGradientObs  # noqa: E402
+import jVMC.mpi_wrapper as mpi  # noqa: E402
+
+from oracle import rbm as orbm, bfo as obfo, stats as ostats, solve as osolve  # noqa: E402
+
+with open(os.path.join(os.path.dirname(__file__), "golden", "reference_goldens.json")) as f:
+    REFG = json.load(f)
+WEIGHTS = torch.tensor(REFG["rbm_weights"], dtype=torch.float64)
+
+
+def tfim(L, J, hx):
+    h = op.BranchFreeOperator()
+    for l in range(L):
+        h.add(op.scal_opstr(J, (op.Sz(l), op.Sz((l + 1) % L))))
+        h.add(op.scal_opstr(hx, (op.Sx(l),)))
+    return h
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------ tests/tdvp_test.py
+@pytest.mark.parametrize("k", [0, 1])
+def test_gs_search_cpx(k):
+    """reference tests/tdvp_test.py:27-56."""
+    L, J = 4, -1.0
+    hx, exE = REFG["gs_hx"][k], REFG["gs_energies"][k]
+    psi = NQS(nets.CpxRBM(numHidden=6, bias=False))
+    H = tfim(L, J, hx)
+    exactSampler = sampler.ExactSampler(psi, L)
+    tdvpEquation = jVMC.util.TDVP(exactSampler, snrTol=1, pinvTol=0.0, pinvCutoff=1e-8, rhsPrefactor=1.,
+                                  diagonalShift=2, makeReal='real')
+    ground_state_search(psi, H, tdvpEquation, exactSampler, numSteps=100, stepSize=5e-2)
+    obs = measure({"energy": H}, psi, exactSampler)
+    assert float(torch.max(torch.abs((obs['energy']['mean'] - exE) / exE))) < 1e-3
+
+
+def test_time_evolution_golden():
+    """reference tests/tdvp_test.py:60-128: <ZZ>(t) golden trajectory + energy conservation."""
+    L, J, hx = 4, -1.0, -0.3
+    psi = NQS(nets.CpxRBM(numHidden=2, bias=False))
+    psi(torch.tensor([[[1, 1, 1, 1]]], dtype=torch.int32))
+    psi.set_parameters(WEIGHTS)
+    hamiltonian = tfim(L, J, hx)
+    ZZ = op.BranchFreeOperator()
+    for l in range(L):
+        ZZ.add((op.Sz(l), op.Sz((l + 1) % L)))
+    exactSampler = sampler.ExactSampler(psi, L)
+    stepper = jVMCstepper.AdaptiveHeun(timeStep=1e-3, tol=1e-5)
+    tdvpEquation = jVMC.util.TDVP(exactSampler, snrTol=1, pinvTol=0.0, pinvCutoff=1e-8, rhsPrefactor=1.j,
+                                  diagonalShift=0., makeReal='imag')
+    t, obs, times = 0, [], [0]
+    newMeas = measure({'E': hamiltonian, 'ZZ': ZZ}, psi, exactSampler)
+    obs.append([float(newMeas['E']['mean'][0]), float(newMeas['ZZ']['mean'][0])])
+    while t < 0.5:
+        dp, dt = stepper.step(0, tdvpEquation, psi.get_parameters(), hamiltonian=hamiltonian, psi=psi, numSamples=0)
+        psi.set_parameters(dp)
+        t += dt
+        times.append(t)
+        newMeas = measure({'E': [(hamiltonian, t)], 'ZZ': ZZ}, psi, exactSampler)
+        obs.append([float(newMeas['E']['mean'][0]), float(newMeas['ZZ']['mean'][0])])
+    obs = np.array(obs)
+    assert np.max(np.abs((obs[:, 0] - obs[0, 0]) / obs[0, 0])) < 1e-3
+    refTimes = np.arange(0, 0.5, 0.05)
+    netZZ = np.interp(refTimes, np.array(times), obs[:, 1])
+    assert np.max(np.abs(netZZ - np.array(REFG["zz_trajectory"])[:len(netZZ)])) < 1e-3
+    err, res = tdvpEquation.get_residuals()
+    assert float(err) >= 0 and float(res) >= 0
+
+
+def test_time_evolution_mc_sampler():
+    """reference tests/tdvp_test.py:131-198 (MCSampler, mu=1, crossValidation)."""
+    L, J, hx = 4, -1.0, -0.3
+    psi = NQS(nets.CpxRBM(numHidden=2, bias=False), batchSize=5000)
+    psi(torch.tensor([[[1, 1, 1, 1]]], dtype=torch.int32))
+    psi.set_parameters(WEIGHTS)
+    hamiltonian = tfim(L, J, hx)
+    ZZ = op.BranchFreeOperator()
+    for l in range(L):
+        ZZ.add((op.Sz(l), op.Sz((l + 1) % L)))
+    MCsampler = sampler.MCSampler(psi, (L,), 0, numSamples=50000, updateProposer=sampler.propose_spin_flip, mu=1,
+                                  numChains=500)
+    stepper = jVMCstepper.AdaptiveHeun(timeStep=1e-3, tol=1e-4)
+    tdvpEquation = jVMC.util.TDVP(MCsampler, snrTol=1, pinvTol=1e-8, rhsPrefactor=1.j, diagonalShift=0.,
+                                  makeReal='imag', crossValidation=True)
+    t, obs, times = 0, [], [0]
+    newMeas = measure({'E': hamiltonian, 'ZZ': ZZ}, psi, MCsampler)
+    obs.append([float(newMeas['E']['mean'][0]), float(newMeas['ZZ']['mean'][0])])
+    while t < 0.2:
+        dp, dt = stepper.step(0, tdvpEquation, psi.get_parameters(), hamiltonian=hamiltonian, psi=psi,
+                              numSamples=5000)
+        psi.set_parameters(dp)
+        t += dt
+        times.append(t)
+        newMeas = measure({'E': [(hamiltonian, t)], 'ZZ': ZZ}, psi, MCsampler)
+        obs.append([float(newMeas['E']['mean'][0]), float(newMeas['ZZ']['mean'][0])])
+    obs = np.array(obs)
+    assert np.max(np.abs((obs[:, 0] - obs[0, 0]) / obs[0, 0])) < 1e-1
+    refTimes = np.arange(0, 0.2, 0.05)
+    netZZ = np.interp(refTimes, np.array(times), obs[:, 1])
+    assert np.max(np.abs(netZZ - np.array(REFG["zz_trajectory"])[:len(netZZ)])) < 2e-2
+    assert "tdvp_residual_cross_validation_ratio" in tdvpEquation.get_metadata()
+
+
+def test_snr_matches_oracle():
+    """SNR / rhoVar of the factorised path vs the oracle's covar_data().transform().var() (reference
+    tests/tdvp_test.py:201-263 compares the same quantity against its legacy formula)."""
+    L = 4
+    psi = NQS(nets.CpxRBM(numHidden=2, bias=False))
+    psi(torch.tensor([[[1, 1, 1, 1]]], dtype=torch.int32))
+    psi.set_parameters(WEIGHTS)
+    H = tfim(L, -1.0, -0.3)
+    smp = sampler.MCSampler(psi, (L,), 0, numSamples=10, updateProposer=sampler.propose_spin_flip, mu=2,
+                            numChains=500)
+    s, logPsi, p = smp.sample()
+    Eloc = H.get_O_loc(s, psi, logPsi, 0.0)
+    td = jVMC.util.TDVP(smp, snrTol=1, pinvTol=1e-8, rhsPrefactor=1.j, makeReal='imag')
+    upd, res, cut = td.solve(SampledObs(Eloc, p), RBMGradientObs(psi, s, p))
+    W, b = orbm.unflatten_params(np.array(REFG["rbm_weights"]), 4, 2)
+    sn, pn, En = host(s)[0], host(p)[0], host(Eloc)[0]
+    otd = osolve.TDVP(snrTol=1, pinvTol=1e-8, rhsPrefactor=1.j, makeReal='imag')
+    oE, oG = ostats.SampledObs(En, pn), ostats.SampledObs(orbm.gradients_holomorphic(sn, W, b), pn)
+    upd_ref, res_ref, cut_ref = otd.solve(oE, oG, mpi.globNumSamples)
+    assert np.allclose(host(td.ev), otd.ev, atol=1e-12)
+    # rhoVar summed over each (numerically) degenerate eigenspace is basis independent
+    assert np.isclose(host(td.rhoVar).sum(), otd.rhoVar.sum(), rtol=1e-8)
+    assert np.isclose(float(td.ElocVar), otd.ElocVar, rtol=1e-10)
+    assert np.allclose(host(td.F0), otd.F0, rtol=1e-10, atol=1e-14)
+
+
+# ------------------------------------------------------------------ tests/minsr_test.py
+@pytest.mark.parametrize("k", [0, 1])
+def test_minsr_gs_search(k):
+    """reference tests/minsr_test.py:15-43."""
+    L, J = 4, -1.0
+    hx, exE = REFG["gs_hx"][k], REFG["gs_energies"][k]
+    psi = NQS(nets.CpxRBM(numHidden=8, bias=False), seed=1234)
+    H = tfim(L, J, hx)
+    exactSampler = sampler.ExactSampler(psi, L)
+    tdvpEquation = jVMC.util.MinSR(exactSampler, pinvTol=1e-6, diagonalShift=0.)
+    ground_state_search(psi, H, tdvpEquation, exactSampler, numSteps=200, stepSize=1e-2)
+    obs = measure({"energy": H}, psi, exactSampler)
+    assert float(torch.max(torch.abs((obs['energy']['mean'] - exE) / exE))) < 1e-3
+
+
+# ------------------------------------------------------------------ tests/sampler_test.py
+def state_to_int(s):
+    return (s.to(torch.int64) * (2 ** torch.arange(s.shape[-1], device=s.device))).sum(-1)
+
+
+@pytest.mark.parametrize("mu,kappa", [(2, 0.5), (1, 0.5), (1, 1.0)])
+def test_MCMC_sampling(mu, kappa):
+    """reference tests/sampler_test.py:32-182 (bare CpxRBM as in :563-593): histogram vs exact, 2e-3."""
+    L = 4
+    psi = NQS(nets.CpxRBM(numHidden=2, bias=False))
+    exactSampler = sampler.ExactSampler(psi, L, logProbFactor=kappa)
+    mcSampler = sampler.MCSampler(psi, (L,), 0, updateProposer=sampler.propose_spin_flip, numChains=777, mu=mu,
+                                  logProbFactor=kappa)
+    p0 = psi.get_parameters()
+    psi.set_parameters(WEIGHTS)
+    _, _, pex = exactSampler.sample()
+    numSamples = 500000
+    smc, _, p = mcSampler.sample(numSamples=numSamples)
+    assert smc.shape[1] >= numSamples and mcSampler.get_last_number_of_samples() == smc.shape[1]
+    ints = state_to_int(smc.reshape(-1, L))
+    pmc = torch.zeros(16, dtype=torch.float64, device=ints.device).index_add_(0, ints, p[0])
+    pmc = pmc / pmc.sum()
+    assert float(torch.max(torch.abs(pmc - pex.reshape(-1)[:16]))) < 2e-3
+    acc = float(mcSampler.acceptance_ratio())
+    assert 0.0 < acc <= 1.0
+    # sample(parameters=...) returns amplitudes of the temporary parameters and restores the net
+    s, psi_s, _ = mcSampler.sample(parameters=p0, numSamples=100)
+    assert torch.allclose(psi.get_parameters().cpu(), WEIGHTS)
+    psi.set_parameters(p0)
+    psi_s1 = psi(s)
+    assert float(torch.max(torch.abs((psi_s - psi_s1) / psi_s))) < 1e-14
+
+
+def test_sampler_output_contract():
+    """time-major / chain-minor order, rounding up per chain, persistent chains."""
+    L = 6
+    psi = NQS(nets.CpxRBM(numHidden=4, bias=True))
+    smp = sampler.MCSampler(psi, (L,), 123, updateProposer=sampler.propose_spin_flip_Z2, numChains=500,
+                            sweepSteps=L, thermalizationSweeps=25, numSamples=4096)
+    s, lp, p = smp.sample()
+    assert s.shape == (1, 4500, L) and s.dtype == torch.int32 and lp.shape == (1, 4500) and p.shape == (1, 4500)
+    assert smp.get_last_number_of_samples() == 4500
+    assert torch.allclose(p.sum(), torch.tensor(1.0, dtype=torch.float64, device=p.device))
+    assert torch.allclose(p, torch.full_like(p, 1 / 4500))
+    # the last emitted sweep is the persistent chain state
+    assert torch.equal(s[0, -500:], smp.states[0])
+    with pytest.raises(ValueError):
+        sampler.MCSampler(psi, (L,), 0, updateProposer=sampler.propose_spin_flip, mu=2.5)
+
+
+def test_exact_sampler():
+    """reference tests/sampler_test.py:563-593."""
+    L = 4
+    psi = NQS(nets.CpxRBM(numHidden=2, bias=False))
+    exactSampler = sampler.ExactSampler(psi, L)
+    p0 = psi.get_parameters()
+    psi.set_parameters(WEIGHTS)
+    s, psi_s, pex = exactSampler.sample()
+    assert float(torch.max(torch.abs((psi(s) - psi_s) / psi_s))) < 1e-14
+    assert abs(float(pex.sum()) - 1) < 1e-14
+    s, psi_s, pex = exactSampler.sample(parameters=p0)
+    psi.set_parameters(p0)
+    assert float(torch.max(torch.abs((psi(s) - psi_s) / psi_s))) < 1e-14
+
+
+# ------------------------------------------------------------------ tests/operator_test.py
+def test_nonzeros_and_prefactor_arguments():
+    """reference tests/operator_test.py:48-93."""
+    L = 4
+    s = torch.as_tensor(np.random.default_rng(3).integers(0, 2, (1, 24, L)).astype(np.int32)).cuda()
+    h = op.BranchFreeOperator()
+    h += 2. * op.Sp(0)
+    h += 2. * op.Sp(1)
+    h += 2. * op.Sp(2)
+    sp, matEl = h.get_s_primes(s)
+    logPsi = torch.ones(s.shape[:-1], dtype=torch.complex128, device="cuda")
+    logPsiSP = torch.ones(sp.shape[:-1], dtype=torch.complex128, device="cuda")
+    tmp = h.get_O_loc_unbatched(logPsi, logPsiSP)
+    assert float(torch.sum(torch.abs(tmp - 2. * torch.sum(-(s[..., :3] - 1), dim=-1).to(torch.float64)))) < 1e-7
+
+    def f(t):
+        return 2.0 * t
+    ht = op.BranchFreeOperator()
+    for i in range(3):
+        ht.add(op.scal_opstr(f, (op.Sp(i),)))
+    for t in [0.5, 2, 13.9]:
+        sp, matEl = ht.get_s_primes(s, t)
+        logPsiSP = torch.ones(sp.shape[:-1], dtype=torch.complex128, device="cuda")
+        tmp = ht.get_O_loc_unbatched(logPsi, logPsiSP)
+        assert float(torch.sum(torch.abs(tmp - f(t) * torch.sum(-(s[..., :3] - 1), dim=-1).to(torch.float64)))) < 1e-7
+
+
+def test_op_2d_shapes():
+    """reference tests/operator_test.py:95-110."""
+    L = 4
+    s = torch.as_tensor(np.random.default_rng(3).integers(0, 2, (1, 24, L, L)).astype(np.int32)).cuda()
+    h = op.BranchFreeOperator()
+    h += 0.3 * op.Sp(0)
+    h += 1.1 * op.Sp(1)
+    h += 0.15 * op.Sp(4)
+    sp, matEl = h.get_s_primes(s)
+    assert tuple(sp.shape[2:]) == (L, L) and sp.shape[1] == 24 * matEl.shape[2]
+
+
+def test_batched_Oloc():
+    """reference tests/operator_test.py:112-162: batched (13) == unbatched == fused."""
+    L = 4
+    h, hb = op.BranchFreeOperator(), op.BranchFreeOperator(ElocBatchSize=13)
+    for i in range(L):
+        for o in (h, hb):
+            o.add(op.scal_opstr(2., (op.Sx(i),)))
+            o.add(op.scal_opstr(2., (op.Sy(i), op.Sz((i + 1) % L))))
+    psi = NQS(nets.CpxRBM(numHidden=2, bias=False))
+    mcSampler = sampler.MCSampler(psi, (L,), 0, updateProposer=sampler.propose_spin_flip, numChains=1)
+    s, logPsi, _ = mcSampler.sample(numSamples=100)
+    sp, matEl = h.get_s_primes(s)
+    Oloc1 = h.get_O_loc_unbatched(logPsi, psi(sp))
+    Oloc2 = h.get_O_loc_batched(s, psi, logPsi, 13)
+    Oloc3 = h.get_O_loc(s, psi, logPsi)     # fused kernel
+    assert float(torch.abs(torch.sum(Oloc1) - torch.sum(Oloc2))) < 1e-5
+    assert torch.allclose(Oloc1, Oloc2, rtol=1e-12, atol=1e-14) and torch.allclose(Oloc1, Oloc3, rtol=1e-10, atol=1e-13)
+
+
+def test_fermionic_operators_generic_path():
+    """reference tests/operator_test.py:174-212: {c_i, c_j^dagger} = delta_ij (generic s' path, JW signs)."""
+    L = 2
+    psi = NQS(nets.CpxRBM(numHidden=2, bias=True))
+    smp = sampler.ExactSampler(psi, (L,))
+
+    def commutator(i, j):
+        Comm = op.BranchFreeOperator()
+        Comm.add(op.scal_opstr(1., (op.creation(j), op.annihilation(i))))
+        Comm.add(op.scal_opstr(1., (op.annihilation(i), op.creation(j))))
+        return Comm
+    out = measure({"same_site": [commutator(0, 0), commutator(1, 1)],
+                   "distinct_site": [commutator(0, 1), commutator(1, 0)]}, psi, smp)
+    vals = torch.cat((out["same_site"]['mean'], out["distinct_site"]['mean']))
+    assert torch.allclose(vals, torch.tensor([1., 1., 0., 0.], dtype=torch.float64, device=vals.device), atol=1e-14)
+    var = torch.cat((out["same_site"]['variance'], out["distinct_site"]['variance']))
+    assert float(var.abs().max()) < 1e-14
+
+
+# ------------------------------------------------------------------ tests/stats_test.py
+def test_sampled_obs():
+    """reference tests/stats_test.py:15-38."""
+    Obs1Loc = torch.tensor([[1., 2., 3.]], device="cuda", dtype=torch.float64)
+    Obs2Loc = torch.tensor([[[1., 4.], [2., 5.], [3., 7.]]], device="cuda", dtype=torch.float64)
+    p = torch.ones((1, 3), device="cuda", dtype=torch.float64) / 3
+    obs1, obs2 = SampledObs(Obs1Loc, p), SampledObs(Obs2Loc, p)
+    assert abs(float(obs1.mean()[0]) - 2.) < 1e-12 and abs(float(obs1.var()[0]) - 2. / 3) < 1e-12
+    dd = dict(device="cuda", dtype=torch.float64)
+    assert torch.allclose(obs2.covar(), torch.tensor([[2. / 3, 1], [1., 14. / 9]], **dd))
+    assert torch.allclose(obs2.mean(), torch.tensor([2, 16. / 3], **dd))
+    assert torch.allclose(obs1.covar(obs2), torch.tensor([2. / 3, 1.], **dd))
+    assert torch.allclose(obs1.covar(obs2), obs1.covar_data(obs2).mean())
+    assert torch.allclose(obs1.covar_var(obs2), obs1.covar_data(obs2).var())
+    O = obs2._data.reshape(-1, 2)
+    assert torch.allclose(obs2.tangent_kernel(), O @ O.conj().T)
+
+
+def test_subset_function():
+    """reference tests/stats_test.py:85-106."""
+    N = 10
+    Obs1 = torch.arange(N, dtype=torch.float64, device="cuda").reshape(1, N, 1)
+    p = torch.rand((1, N), dtype=torch.float64, device="cuda")
+    p = p / mpi.global_sum(p)
+    obs1 = SampledObs(Obs1, p)
+    obs2 = obs1.subset(0, N // 2)
+    assert torch.allclose(obs1.mean()[0], mpi.global_sum(Obs1.reshape(1, N) * p))
+    assert torch.allclose(obs2.mean(), mpi.global_sum(Obs1.reshape(1, N)[:, :N // 2] * p[:, :N // 2])
+                          / mpi.global_sum(p[:, :N // 2]))
+    obs3 = SampledObs(Obs1[:, :N // 2, :], p[:, :N // 2] / mpi.global_sum(p[:, :N // 2]))
+    assert torch.allclose(obs3.covar(), obs2.covar())
+
+
+@pytest.mark.parametrize("bias", [False, True])
+def test_rbm_gradient_obs_equals_generic(bias):
+    """The factorised observable reproduces the generic SampledObs on the materialised gradients."""
+    L, M = 5, 6
+    psi = NQS(nets.CpxRBM(numHidden=M, bias=bias), seed=3)
+    s = torch.as_tensor(np.random.default_rng(1).integers(0, 2, (1, 40, L)).astype(np.int32)).cuda()
+    psi(s)
+    W, b = orbm.init_o1(L, M, bias, 5)
+    psi.set_parameters(torch.as_tensor(orbm.flatten_params(W, b)))
+    p = torch.rand((1, 40), dtype=torch.float64, device="cuda")
+    p = p / p.sum()
+    E = torch.randn(1, 40, dtype=torch.complex128, device="cuda")
+    gen, fac, eo = SampledObs(psi.gradients(s), p), RBMGradientObs(psi, s, p), SampledObs(E, p)
+    assert torch.allclose(fac.mean(), gen.mean(), rtol=1e-12, atol=1e-15)
+    assert torch.allclose(fac.covar(), gen.covar(), rtol=1e-10, atol=1e-14)
+    assert torch.allclose(fac.covar(eo), gen.covar(eo), rtol=1e-10, atol=1e-14)
+    assert torch.allclose(eo.covar(fac), eo.covar(gen), rtol=1e-10, atol=1e-14)
+    assert torch.allclose(fac.var(), gen.var().reshape(-1), rtol=1e-10, atol=1e-14)
+    assert torch.allclose(fac._data, gen._data, rtol=1e-12, atol=1e-15)
+    assert torch.allclose(fac.tangent_kernel(), gen.tangent_kernel(), rtol=1e-10, atol=1e-14)
+    sub_f, sub_g = fac.subset(start=1, step=2), gen.subset(start=1, step=2)
+    assert torch.allclose(sub_f.covar(), sub_g.covar(), rtol=1e-9, atol=1e-13)
+    x = torch.randn(40, dtype=torch.complex128, device="cuda")
+    ref = -gen._data.reshape(40, -1).conj().T @ x
+    assert torch.allclose(fac.minsr_contract(x), ref, rtol=1e-10, atol=1e-13)
+    u = torch.randn(gen._data.shape[-1], dtype=torch.float64, device="cuda")
+    S0 = gen.covar()
+    assert torch.allclose(fac.quad_form(u), (u.to(S0.dtype) @ (S0 @ u.to(S0.dtype))).real, rtol=1e-9)
+
+
+# ------------------------------------------------------------------ tests/vqs_test.py
+@pytest.mark.parametrize("net", ["cpx", "real"])
+def test_gradients_finite_difference(net):
+    """reference tests/vqs_test.py:99-164: every flat index."""
+    L = 3
+    psiC = NQS(nets.CpxRBM(numHidden=2, bias=True) if net == "cpx" else nets.RBM(numHidden=2, bias=True))
+    s = torch.zeros((1, 4, L), dtype=torch.int32, device="cuda")
+    s[..., 0, 1] = 1
+    s[..., 2, 2] = 1
+    psi0 = psiC(s)
+    assert psiC.holomorphic == (net == "cpx")
+    G = psiC.gradients(s)
+    delta = 1e-6
+    params = psiC.get_parameters()
+    assert G.shape[-1] == params.shape[0]
+    for j in range(G.shape[-1]):
+        u = torch.zeros(G.shape[-1], dtype=torch.float64, device="cuda")
+        u[j] = 1
+        psiC.update_parameters(delta * u)
+        psi1 = psiC(s)
+        psiC.set_parameters(params)
+        Gfd = (psi1 - psi0) / delta
+        assert float(torch.max(torch.abs(Gfd - G[..., j]))) < 1e-4
+
+
+def test_gradient_dict_and_param_roundtrip():
+    """reference tests/vqs_test.py:272-289 + parameter (un)flattening (jVMC/vqs.py:430-466)."""
+    psi = NQS(nets.CpxRBM(numHidden=8, bias=False), seed=1234)
+    s = torch.zeros((1, 3, 4), dtype=torch.int32, device="cuda")
+    psi(s)
+    g1 = psi.gradients(s)
+    g2 = psi.gradients_dict(s)["Dense_0"]["kernel"]
+    assert float(torch.linalg.norm(g1 - g2)) == 0.0
+    P = psi.get_parameters()
+    assert P.shape == (2 * 4 * 8,) and psi.numParameters == 32
+    psi.set_parameters(P * 2)
+    assert torch.allclose(psi.get_parameters(), 2 * P)
+    psi.set_parameters(WEIGHTS.repeat(4))
+    W = psi.params["Dense_0"]["kernel"]
+    w = WEIGHTS.repeat(4).to(W.device)
+    assert torch.allclose(W, (w[:32] + 1j * w[32:]).reshape(4, 8))
+    psi2 = NQS(nets.CpxRBM(numHidden=8))
+    with pytest.raises(RuntimeError):
+        psi2.set_parameters(P)

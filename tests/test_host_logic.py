@@ -1,0 +1,152 @@
+"""CPU tests of the host-side logic and of the C-ABI surface (no kernel launches)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import vmc_jax_b200 as jVMC
+import vmc_jax_b200.operator as op
+from vmc_jax_b200 import _lib, mpi_wrapper as mpi
+from vmc_jax_b200.util import stepper
+
+from oracle import bfo as obfo, sampling as osamp
+
+
+def test_library_exports_every_declared_symbol():
+    names = _lib.declared_symbols()
+    assert len(names) >= 19 and "jvmc_rbm_mcmc" in names and "jvmc_rbm_gram_S" in names
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(names) == set(_lib._SIGS.keys())
+    l = _lib.load()
+    assert l.jvmc_version() >= 100
+    assert l.jvmc_error_string(-1) == b"invalid argument"
+    assert l.jvmc_rbm_tables_elems(4, 3) == 4 * 3 + 4 + 3 + 1
+    assert l.jvmc_rbm_moments_chunks(1) == 1 and l.jvmc_rbm_moments_chunks(10 ** 7) == 64
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    psi = jVMC.vqs.NQS(jVMC.nets.CpxRBM(numHidden=2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        psi(torch.zeros((1, 3, 4), dtype=torch.int32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        jVMC.sampler.MCSampler(psi, (4,), 0, updateProposer=jVMC.sampler.propose_spin_flip)
+
+
+def test_unsupported_components_raise():
+    with pytest.raises(NotImplementedError):
+        jVMC.vqs.NQS(object())
+    with pytest.raises(NotImplementedError):
+        jVMC.vqs.NQS((jVMC.nets.RBM(), jVMC.nets.RBM()))
+
+
+def test_opstr_algebra():
+    """reference tests/operator_test.py:256-265."""
+    op1, op2 = op.Sz(3), op.Sx(5)
+    opstr1 = 13. * op1 * op2
+    opstr2 = 1.j * opstr1 * op1
+    assert np.allclose(opstr2[0](), 13.j)
+    for o in opstr2[1:]:
+        assert isinstance(o, (op.LocalOp, dict))
+    s = op.scal_opstr(lambda t: 2.0 * t, (op.Sp(0),))
+    assert s[0](3.0) == 6.0
+    s2 = 0.5 * s
+    assert s2[0](3.0) == 3.0
+    with pytest.raises(RuntimeError):
+        op.scal_opstr(2.0, op.Sz(0))
+
+
+def _product_ham(L, g, h=None):
+    H = op.BranchFreeOperator()
+    S = []
+    for l in range(L):
+        H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz((l + 1) % L))))
+        S.append((-1., [obfo.Sz(l), obfo.Sz((l + 1) % L)]))
+        H.add(op.scal_opstr(g, (op.Sx(l),)))
+        S.append((g, [obfo.Sx(l)]))
+        if h is not None:
+            H.add(op.scal_opstr(h, (op.Sy(l), op.Sz((l + 1) % L), op.Sp((l + 2) % L))))
+            S.append((h, [obfo.Sy(l), obfo.Sz((l + 1) % L), obfo.Sp((l + 2) % L)]))
+    return H, obfo.Tables(S)
+
+
+def test_compile_tables_match_oracle():
+    """BranchFreeOperator.compile (reference branch_free.py:348-441): padding with Id(0), reversed order."""
+    H, T = _product_ham(5, 0.7, h=lambda t: 0.1 * t)
+    tab = H.compile()
+    assert np.array_equal(tab.idx, T.idx) and np.array_equal(tab.map, T.map)
+    assert np.array_equal(tab.matEls, T.matEls) and np.array_equal(tab.fermionic, T.fermi)
+    assert np.array_equal(tab.diag, T.diag)
+    assert tab.maxOpStrLength == 3
+    assert not tab.fused_ok(object())
+    # fermionic flags
+    F = op.BranchFreeOperator()
+    F.add(op.scal_opstr(1., (op.creation(1), op.annihilation(0))))
+    F.add(op.scal_opstr(2., (op.number(0),)))
+    ft = F.compile()
+    assert ft.fermionic.tolist() == [[1, 1], [0, 0]] and ft.isDiag.tolist() == [0, 1]
+
+
+def test_td_prefactor_compiles():
+    """reference tests/operator_test.py:164-172."""
+    hamiltonian = op.BranchFreeOperator()
+    hamiltonian.add((op.Sz(0),))
+    hamiltonian.add((op.Sz(1),))
+    hamiltonian.add(op.scal_opstr(0.1, (op.Sx(0), op.Sx(1))))
+    hamiltonian.compile()
+
+
+@pytest.mark.parametrize("n,commSize,chains", [(4096, 1, 500), (10, 3, 1), (65536, 8, 1184), (7, 2, 3)])
+def test_distribute_sampling_matches_oracle(n, commSize, chains, monkeypatch):
+    for rank in range(commSize):
+        monkeypatch.setattr(mpi, "_refresh", lambda: None)
+        monkeypatch.setattr(mpi, "rank", rank)
+        monkeypatch.setattr(mpi, "commSize", commSize)
+        assert mpi.distribute_sampling(n, localDevices=1, numChainsPerDevice=chains) == \
+            osamp.distribute_sampling(n, commSize, rank, 1, chains)
+        assert mpi.distribute_sampling(n) == osamp.distribute_sampling(n, commSize, rank)
+    # first_sample_id partitions [0, n)
+    firsts = []
+    for rank in range(commSize):
+        monkeypatch.setattr(mpi, "rank", rank)
+        cnt, _ = mpi.distribute_sampling(n)
+        firsts.append((mpi.first_sample_id(), cnt))
+    pos = 0
+    for f, c in firsts:
+        assert f == pos
+        pos += c
+    assert pos == n
+
+
+def test_steppers_on_linear_ode():
+    """reference tests/stepper_test.py:14-39."""
+    from scipy.linalg import expm
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    y0 = rng.normal(size=4) + 0j
+    f = lambda y, t, intStep=0: A @ y
+    st = stepper.AdaptiveHeun(timeStep=1e-2, tol=1e-7)
+    y, t = y0.copy(), 0.0
+    while t < 0.3:
+        y, dt = st.step(t, f, y)
+        t += dt
+    assert np.linalg.norm(y - expm(A * t) @ y0) < 1e-5
+    At = torch.as_tensor(A)
+    ft = lambda y, t, intStep=0: At @ y
+    yt, dt = stepper.Heun(timeStep=1e-3).step(0., ft, torch.as_tensor(y0))
+    assert np.allclose(yt.numpy(), expm(A * 1e-3) @ y0, atol=1e-8)
+    ye, _ = stepper.Euler(timeStep=1e-3).step(0., f, y0)
+    assert np.allclose(ye, y0 + 1e-3 * A @ y0)
+
+
+def test_sampler_argument_validation():
+    class FakeNet:
+        is_generator = False
+    with pytest.raises(RuntimeError):
+        jVMC.sampler.MCSampler(FakeNet(), (4,), 0, updateProposer=None)
+    with pytest.raises(NotImplementedError):
+        jVMC.sampler.MCSampler(FakeNet(), (4,), 0, updateProposer=lambda k, s, i: s)

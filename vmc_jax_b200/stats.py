@@ -1,0 +1,333 @@
+"""Mirror of jVMC/stats.py: SampledObs statistics on device arrays.
+
+``SampledObs`` is the generic container (any observable, arrays [dev, B, ...]); its reductions are
+plain device tensor operations followed by the in-stream all-reduce of mpi_wrapper.
+``RBMGradientObs`` is the B200-native specialisation for the per-sample gradients of a (Cpx)RBM: it
+stores only (configs, tanh(theta), weights) -- the Khatri-Rao factors of O -- and evaluates mean, force,
+S (Gram), SNR projections and the MinSR contraction with the kernels of csrc/stats.cu and csrc/gram.cu
+without ever materialising O [N_s x P]."""
+import numpy as np
+import torch
+
+from . import global_defs
+from . import kernels as K
+from . import mpi_wrapper as mpi
+
+
+def _w_like(w, data):
+    return w.reshape(w.shape + (1,) * (data.dim() - 2))
+
+
+class SampledObs:
+    """Statistics of a sampled observable (reference jVMC/stats.py:136-336).
+
+    Args: ``observations`` [dev, B, ...], ``weights`` [dev, B] (normalised over all ranks).
+    ``estimator`` / ``params`` (autodiff estimators) are not supported on the B200 path."""
+
+    def __init__(self, observations=None, weights=None, estimator=None, params=None):
+        if estimator is not None:
+            raise NotImplementedError("estimator functions need autodiff and are outside the B200 hot path")
+        self._weights = None if weights is None else torch.as_tensor(weights).to(global_defs.myDevice)
+        self._data = None
+        self._mean = None
+        self._configs = None
+
+        def estimator_not_implemented(p, s):
+            raise Exception("No estimator function given.")
+        self._estimator = estimator_not_implemented
+        self._estimator_grad = estimator_not_implemented
+        if observations is not None:
+            observations = torch.as_tensor(observations).to(global_defs.myDevice)
+        self._compute_data_and_mean(observations)
+
+    def _compute_data_and_mean(self, observations):
+        """reference :197-205: mean = sum_n w_n O_n, data = sqrt(w_n) (O_n - mean)."""
+        if (observations is not None) and (self._weights is not None):
+            if observations.dim() == 2:
+                observations = observations[..., None]
+            if not observations.is_floating_point() and not observations.is_complex():
+                observations = observations.to(torch.float64)
+            w = _w_like(self._weights, observations)
+            self._mean = mpi.global_sum((w.to(observations.dtype) * observations))
+            self._data = torch.sqrt(w) * (observations - self._mean)
+
+    def mean(self, params=None):
+        if params is not None:
+            raise NotImplementedError("estimator functions are not supported")
+        return self._mean
+
+    def covar(self, other=None):
+        """reference :235-245: sum_n conj(data1_n) (x) data2_n."""
+        if other is None:
+            other = self
+        if isinstance(other, RBMGradientObs) and not isinstance(self, RBMGradientObs):
+            return other.covar(self).conj().T
+        d1 = self._data.reshape(-1, int(np.prod(self._data.shape[2:])))
+        d2 = other._data.reshape(-1, int(np.prod(other._data.shape[2:])))
+        if d1.dtype != d2.dtype:
+            ct = torch.promote_types(d1.dtype, d2.dtype)
+            d1, d2 = d1.to(ct), d2.to(ct)
+        return mpi._all_reduce_sum(d1.conj().T @ d2)
+
+    def var(self):
+        """reference :248-252."""
+        return mpi.global_sum((self._data.conj() * self._data).real)
+
+    def covar_data(self, other=None):
+        """reference :255-265: per-sample outer(conj(d1), d2)/w as a new SampledObs."""
+        if other is None:
+            other = self
+        d1 = self._data.reshape(self._data.shape[:2] + (-1,))
+        d2 = other._data.reshape(other._data.shape[:2] + (-1,))
+        obs = d1.conj()[..., :, None] * d2[..., None, :] / self._weights[..., None, None]
+        return SampledObs(obs, self._weights)
+
+    def covar_var(self, other=None):
+        """reference :268-279."""
+        if other is None:
+            other = self
+        d1 = self._data.reshape(self._data.shape[:2] + (-1,))
+        d2 = other._data.reshape(other._data.shape[:2] + (-1,))
+        outer = d1.conj()[..., :, None] * d2[..., None, :]
+        return mpi.global_sum(outer.abs() ** 2 / self._weights[..., None, None]) - self.covar(other).abs() ** 2
+
+    def transform(self, nonLinearFun=lambda x: x, linearFun=None):
+        """reference :282-292: f(data/sqrt(w) + mean), optionally followed by a matrix product."""
+        x = nonLinearFun(self._data / torch.sqrt(_w_like(self._weights, self._data)) + self._mean)
+        if linearFun is not None:
+            lf = torch.as_tensor(linearFun).to(x.device)
+            ct = torch.promote_types(lf.dtype, x.dtype)
+            x = torch.matmul(lf.to(ct), x.to(ct))
+        return SampledObs(x, self._weights)
+
+    def select(self, ixs):
+        """reference :295-307."""
+        newObs = SampledObs()
+        newObs._data = self._data[:, :, ixs]
+        newObs._mean = self._mean[ixs]
+        newObs._weights = self._weights
+        return newObs
+
+    def subset(self, start=None, end=None, step=None):
+        """reference :310-329."""
+        sl = slice(start, end, step)
+        newObs = SampledObs()
+        w = self._weights[:, sl]
+        normalization = mpi.global_sum(w)
+        d = self._data[:, sl] / torch.sqrt(normalization)
+        w = w / normalization
+        newObs._weights = w
+        newObs._mean = mpi.global_sum(torch.sqrt(_w_like(w, d)) * d) + self._mean
+        newObs._data = d + torch.sqrt(_w_like(w, d)) * (self._mean - newObs._mean)
+        return newObs
+
+    def tangent_kernel(self):
+        """reference :332-336."""
+        all_data = mpi.gather(self._data)
+        all_data = all_data.reshape(all_data.shape[0], -1)
+        return all_data @ all_data.conj().T
+
+
+class RBMGradientObs(SampledObs):
+    """Per-sample (Cpx)RBM gradients as Khatri-Rao factors: O_n[(r, j)] = sigma_{n,r} tau_{n,j}.
+
+    Holds configs int32[B, N], tau complex128[B, M], weights float64[B]; everything the TDVP / MinSR
+    equations need is computed from these by the fused kernels."""
+
+    def __init__(self, psi, configs, weights):
+        SampledObs.__init__(self)
+        s = torch.as_tensor(configs).to(global_defs.myDevice).to(torch.int32)
+        self.psi = psi
+        self._lead = tuple(s.shape[:2])
+        self._s = s.reshape(self._lead[0] * self._lead[1], -1).contiguous()
+        self._tau = psi._tau(self._s)
+        self._weights = torch.as_tensor(weights).to(global_defs.myDevice)
+        self._p = self._weights.reshape(-1).contiguous()
+        self.N, self.M = self._s.shape[1], self._tau.shape[1]
+        self.hasBias = psi.b is not None
+        self.holomorphic = psi.holomorphic
+        self.R = self.N + (1 if self.hasBias else 0)
+        self._mu = None          # [R, M] Khatri-Rao mean (global)
+        self._A = None
+        self._sigT = None
+        self._dense = None
+
+    # ---- Khatri-Rao <-> reference flat layout
+    def _kr_to_flat(self, v):
+        """complex vector in c = r*M + j order -> reference flat layout (holomorphic: per leaf [g, i g])."""
+        v = v.reshape(-1)
+        if not self.holomorphic:
+            return v
+        Mb = self.M if self.hasBias else 0
+        parts = []
+        if self.hasBias:
+            parts += [v[:Mb], 1j * v[:Mb]]
+        parts += [v[Mb:], 1j * v[Mb:]]
+        return torch.cat(parts)
+
+    def kr_mean(self):
+        if self._mu is None:
+            mu = K.rbm_moments(self._s, self._tau, self._p.to(torch.complex128), self.hasBias, 0)
+            self._mu = mpi._all_reduce_sum(mu)
+        return self._mu
+
+    def mean(self, params=None):
+        if self._mean is None:
+            self._mean = self._kr_to_flat(self.kr_mean())
+        return self._mean
+
+    @property
+    def _data(self):
+        """Dense centred data sqrt(w)(O - mean) [dev, B, P] -- only for small problems / generic callers."""
+        if self._dense is None and self._s is not None:
+            B = self._s.shape[0]
+            P = (2 if self.holomorphic else 1) * self.R * self.M
+            if B * P * 16 > 8 * 2 ** 30:
+                raise MemoryError("dense gradient matrix would need %.1f GB; use the implicit RBMGradientObs methods"
+                                  % (B * P * 16 / 2 ** 30))
+            g = K.rbm_grad(self._s, self._tau, self.hasBias, 0 if self.holomorphic else 1)
+            d = torch.sqrt(self._p)[:, None] * (g - self.mean()[None, :])
+            self._dense = d.reshape(self._lead + (P,))
+        return self._dense
+
+    @_data.setter
+    def _data(self, val):
+        self._dense = val
+
+    def kr_covar_with(self, other):
+        """Khatri-Rao order vector sum_n conj(sqrt(w) (O_n - mu)) d_n for a scalar observable ``other``."""
+        d = other._data.reshape(-1).to(torch.complex128)
+        wgt = torch.sqrt(self._p) * d
+        Fk = K.rbm_moments(self._s, self._tau, wgt, self.hasBias, 1)
+        Fk = Fk - self.kr_mean().conj() * wgt.sum()
+        return mpi._all_reduce_sum(Fk)
+
+    def covar(self, other=None):
+        if other is None:
+            return self._expand_S0()
+        if isinstance(other, RBMGradientObs):
+            return SampledObs.covar(self, other)
+        nd = int(np.prod(other._data.shape[2:]))
+        if nd != 1:
+            return SampledObs.covar(self, other)
+        Fk = self.kr_covar_with(other)
+        if self.holomorphic:
+            Mb = self.M if self.hasBias else 0
+            parts = []
+            if self.hasBias:
+                parts += [Fk.reshape(-1)[:Mb], -1j * Fk.reshape(-1)[:Mb]]
+            parts += [Fk.reshape(-1)[Mb:], -1j * Fk.reshape(-1)[Mb:]]
+            return torch.cat(parts)[:, None]
+        return Fk.reshape(-1)[:, None]
+
+    def gram_A(self):
+        """A[(r,j),(r',l)] = <conj(O) O>_c, complex Hermitian [R*M, R*M] (global)."""
+        if self._A is None:
+            mu = self.kr_mean()
+            if self._sigT is None:
+                self._sigT = K.pack_sigma(self._s, self.hasBias)
+            p = self._p
+            kappa = 1.0 / mpi.commSize
+            if p.numel() > 0 and bool((p == p[0]).all()):
+                A = K.rbm_gram_S(self._tau, self._sigT, mu, float(p[0]), kappa)
+            else:
+                A = K.rbm_gram_S(self._tau * torch.sqrt(p)[:, None], self._sigT, mu, 1.0, kappa)
+            self._A = mpi._all_reduce_sum(A)
+        return self._A
+
+    def _expand_S0(self):
+        A = self.gram_A()
+        if not self.holomorphic:
+            return A
+        Mb = self.M if self.hasBias else 0
+        Pc = A.shape[0]
+        idx = []
+        for lo, hi in ([(0, Mb)] if self.hasBias else []) + [(Mb, Pc)]:
+            r = torch.arange(lo, hi, device=A.device)
+            idx += [(r, 1.0), (r, 1j)]
+        rows = torch.cat([i for i, _ in idx])
+        ph = torch.cat([torch.full((len(i),), f, dtype=torch.complex128, device=A.device) for i, f in idx])
+        return ph.conj()[:, None] * A[rows][:, rows] * ph[None, :]
+
+    def var(self):
+        """sum_n w_n |O_n - mean|^2 per flat component: |sigma tau|^2 = |tau|^2 for every site."""
+        second = mpi._all_reduce_sum((self._p[:, None] * (self._tau.conj() * self._tau).real).sum(0))
+        v = second[None, :].expand(self.R, self.M).reshape(-1) - (self.kr_mean().conj() * self.kr_mean()).real.reshape(-1)
+        if not self.holomorphic:
+            return v
+        Mb = self.M if self.hasBias else 0
+        parts = ([v[:Mb], v[:Mb]] if self.hasBias else []) + [v[Mb:], v[Mb:]]
+        return torch.cat(parts)
+
+    def quad_form(self, u):
+        """u^T S0 u for a real flat vector u (TDVP error, reference jVMC/util/tdvp.py:102-104) from A."""
+        u = torch.as_tensor(u).to(self._tau.device)
+        if not self.holomorphic:
+            z = u.to(torch.complex128)
+        else:
+            Mb = self.M if self.hasBias else 0
+            NM = self.N * self.M
+            zs = []
+            off = 0
+            for n in ([Mb] if self.hasBias else []) + [NM]:
+                zs.append(u[off:off + n] + 1j * u[off + n:off + 2 * n])
+                off += 2 * n
+            z = torch.cat(zs).to(torch.complex128)
+        return (z.conj() @ (self.gram_A() @ z)).real
+
+    def subset(self, start=None, end=None, step=None):
+        """reference :310-329 -- equals a fresh observable on the slice with renormalised weights."""
+        sl = slice(start, end, step)
+        w = self._weights[:, sl]
+        w = w / mpi.global_sum(w)
+        cfg = self._s.reshape(self._lead + (self.N,))[:, sl].contiguous()
+        return RBMGradientObs(self.psi, cfg, w.contiguous())
+
+    def snr_rho_var(self, Eloc, Vt, prefactor, mode):
+        """Variance over samples of rho_n = V^dagger q(-x conj(dO_n) dE_n)  (reference
+        jVMC/util/tdvp.py:173-181 via stats.py covar_data/transform/var), chunked over samples so that
+        only [chunk, P] rows of O exist at a time.  Vt: rows = eigenvectors."""
+        B = self._s.shape[0]
+        P = Vt.shape[0]
+        dE = (Eloc._data.reshape(-1) / torch.sqrt(self._p)).to(torch.complex128)
+        mean = self.mean()
+        s1 = torch.zeros(P, dtype=torch.complex128, device=Vt.device)
+        s2 = torch.zeros(P, dtype=torch.float64, device=Vt.device)
+        chunk = max(1, min(B, (2 ** 28) // max(P, 1)))
+        VtH = Vt.conj().to(torch.complex128)
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            g = K.rbm_grad(self._s[lo:hi].contiguous(), self._tau[lo:hi].contiguous(), self.hasBias,
+                           0 if self.holomorphic else 1)
+            x = (-prefactor) * (g - mean[None, :]).conj() * dE[lo:hi, None]
+            if mode == 0 and not Vt.is_complex():
+                rho = (x.real @ Vt.T).to(torch.complex128)
+            else:
+                x = x.real.to(torch.complex128) if mode == 0 else 1j * x.imag
+                rho = x @ VtH.T
+            w = self._p[lo:hi]
+            s1 += (w[:, None] * rho).sum(0)
+            s2 += (w[:, None] * (rho.conj() * rho).real).sum(0)
+        s1 = mpi._all_reduce_sum(s1)
+        s2 = mpi._all_reduce_sum(s2)
+        return s2 - (s1.conj() * s1).real
+
+    def tangent_kernel(self):
+        all_data = mpi.gather(self._data)
+        all_data = all_data.reshape(all_data.shape[0], -1)
+        return all_data @ all_data.conj().T
+
+    def minsr_contract(self, x):
+        """-Obar^dagger x in the reference flat layout (jVMC/util/minsr.py:65) for the gathered vector x,
+        evaluated as a Khatri-Rao moment reduction (no dense O)."""
+        B = self._s.shape[0]
+        off = mpi.gather_offset(B)
+        xl = x[off:off + B].to(torch.complex128)
+        wgt = torch.sqrt(self._p) * xl
+        Fk = K.rbm_moments(self._s, self._tau, wgt, self.hasBias, 1)
+        Fk = mpi._all_reduce_sum(Fk - self.kr_mean().conj() * wgt.sum()).reshape(-1)
+        if not self.holomorphic:
+            return -Fk
+        Mb = self.M if self.hasBias else 0
+        parts = ([Fk[:Mb], -1j * Fk[:Mb]] if self.hasBias else []) + [Fk[Mb:], -1j * Fk[Mb:]]
+        return -torch.cat(parts)

@@ -1,0 +1,230 @@
+"""Mirror of jVMC/vqs.py: the NQS wrapper (evaluation, gradients, flat parameter vector).
+
+Only (Cpx)RBM ansaetze are on the B200 hot path; other nets raise NotImplementedError (there is no
+CPU / eager fallback)."""
+import numpy as np
+import torch
+
+from . import global_defs
+from . import kernels as K
+from .nets.rbm import CpxRBM, RBM, _RBMBase
+
+
+def _to_dev(x, dtype=None):
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(np.asarray(x))
+    x = x.to(global_defs.myDevice)
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    return x
+
+
+class NQS:
+    """Variational wave function psi_theta(s) = exp(r_theta(s)) (reference jVMC/vqs.py:85-491).
+
+    Args mirror the reference (:115-120): ``net``, ``logarithmic``, ``batchSize``, ``seed``,
+    ``orbit``, ``avgFun``.  ``batchSize`` is accepted for compatibility: the kernels tile the batch
+    themselves and never materialise more than the outputs."""
+
+    def __init__(self, net, logarithmic=True, batchSize=1000, seed=1234, orbit=None, avgFun=None):
+        if isinstance(net, (tuple, list)):
+            raise NotImplementedError("two-network ansatz (TwoNets) is outside the B200 hot path (SURVEY 2a-16)")
+        if orbit is not None:
+            raise NotImplementedError("symmetrised nets (SymNet) are outside the B200 hot path (SURVEY 2a-15)")
+        if not isinstance(net, _RBMBase):
+            raise NotImplementedError("only jVMC.nets.CpxRBM / RBM have B200 kernels; got %r" % (net,))
+        if not logarithmic:
+            raise NotImplementedError("non-logarithmic networks are not supported")
+        self.net = net
+        self.logarithmic = logarithmic
+        self.batchSize = batchSize
+        self.seed = seed
+        self.initialized = False
+        self.parameters = None
+        self.realParams = not net.cpx
+        self.realNets = False
+        self.holomorphic = False
+        self._isGenerator = False
+        self._version = 0
+        self._cache = None
+        self._tables = None
+        self.sampleShape = None
+
+    # ------------------------------------------------------------------ initialisation
+    def init_net(self, s):
+        """reference :187-218 (lazy init on first use; holomorphy known analytically here)."""
+        if self.initialized:
+            return
+        self.sampleShape = tuple(s.shape[2:])
+        if not self.net.cpx and len(self.sampleShape) != 1:
+            raise NotImplementedError("real RBM acts on the last axis only (rbm.py:88); use 1-d sampleShape")
+        self.N = int(np.prod(self.sampleShape))
+        self.M = self.net.numHidden
+        self.parameters = {"params": self.net.init(self.seed, self.sampleShape, global_defs.myDevice)}
+        self.holomorphic = bool(self.net.cpx)
+        leaves = self._leaves()
+        self.paramShapes = [(int(p.numel()), tuple(p.shape)) for p in leaves]
+        self.numParameters = int(sum(p.numel() for p in leaves))
+        self.initialized = True
+
+    def _leaves(self, tree=None):
+        d = (self.parameters["params"] if tree is None else tree)["Dense_0"]
+        return [d[k] for k in sorted(d.keys())]      # Flax sorted-key order: bias, kernel
+
+    @property
+    def W(self):
+        return self.parameters["params"]["Dense_0"]["kernel"]
+
+    @property
+    def b(self):
+        return self.parameters["params"]["Dense_0"].get("bias", None)
+
+    def _cW(self):
+        return self.W.to(torch.complex128), (None if self.b is None else self.b.to(torch.complex128))
+
+    def _bump(self):
+        self._version += 1
+        self._cache = None
+        self._tables = None
+
+    # ------------------------------------------------------------------ evaluation
+    def _flat_configs(self, s):
+        s = _to_dev(s, torch.int32)
+        lead = tuple(s.shape[:2])
+        return s.reshape(lead[0] * lead[1], -1).contiguous(), lead
+
+    def __call__(self, s):
+        """log psi(s) for configurations s[dev, B, *shape] -> complex128[dev, B] (reference :223-251)."""
+        s = _to_dev(s, torch.int32)
+        self.init_net(s)
+        flat, lead = self._flat_configs(s)
+        W, b = self._cW()
+        logpsi, tau = K.rbm_logpsi(flat, W, b)
+        self._remember(flat, tau)
+        return logpsi.reshape(lead)
+
+    def _remember(self, flat, tau):
+        # the cache keeps `flat` alive, so its storage cannot be recycled for other data while cached
+        self._cache = (flat, flat._version, self._version, tau)
+
+    def _tau(self, flat):
+        """tanh(theta) for the given flat configurations (cached from the last evaluation)."""
+        c = self._cache
+        if c is not None and c[0].data_ptr() == flat.data_ptr() and c[0].shape == flat.shape \
+                and c[1] == flat._version and c[2] == self._version:
+            return c[3]
+        W, b = self._cW()
+        _, tau = K.rbm_logpsi(flat, W, b)
+        self._remember(flat, tau)
+        return tau
+
+    def flip_tables(self):
+        if self._tables is None:
+            W, b = self._cW()
+            self._tables = K.rbm_tables(W, b)
+        return self._tables
+
+    def gradients(self, s):
+        """d log psi / d theta_k for every configuration: complex128[dev, B, P] in the reference's flat
+        layout (holomorphic: per leaf [g, i g], reference :66-69; real parameters: :46-51)."""
+        s = _to_dev(s, torch.int32)
+        self.init_net(s)
+        flat, lead = self._flat_configs(s)
+        g = K.rbm_grad(flat, self._tau(flat), self.b is not None, 0 if self.holomorphic else 1)
+        return g.reshape(lead + (g.shape[-1],))
+
+    def gradients_dict(self, s):
+        """reference :292-314."""
+        g = self.gradients(s)
+        out, start = {}, 0
+        for name, (size, _) in zip(sorted(self.parameters["params"]["Dense_0"].keys()), self.paramShapes):
+            n = 2 * size if self.holomorphic else size
+            out[name] = g[..., start:start + n]
+            start += n
+        return {"Dense_0": out}
+
+    def grad_dict_to_vec_map(self):
+        """reference :319-334."""
+        out, start = {}, 0
+        for name, (size, _) in zip(sorted(self.parameters["params"]["Dense_0"].keys()), self.paramShapes):
+            n = 2 * size if self.holomorphic else size
+            out[name] = torch.arange(start, start + n)
+            start += n
+        return {"Dense_0": out}
+
+    def get_sampler_net(self):
+        """reference :337-352: (function evaluating Re log psi, current parameters)."""
+        def evalReal(p, x):
+            tmp = self.parameters
+            self.parameters = p
+            self._bump()
+            try:
+                return self(x[None, None, ...] if x.dim() == len(self.sampleShape) else x).real
+            finally:
+                self.parameters = tmp
+                self._bump()
+        return evalReal, self.parameters
+
+    def sample(self, numSamples, key, parameters=None):
+        return None     # (Cpx)RBM is not a generator (reference :356-375)
+
+    # ------------------------------------------------------------------ parameters
+    def update_parameters(self, deltaP):
+        """reference :384-404."""
+        if not self.initialized:
+            self.set_parameters(deltaP)
+        new = self._param_unflatten(deltaP)
+        cur = self.parameters["params"]["Dense_0"]
+        self.parameters = {"params": {"Dense_0": {k: cur[k] + new["Dense_0"][k] for k in cur}}}
+        self._bump()
+
+    def set_parameters(self, P):
+        """reference :409-425.  P: flat vector (real, or complex for MinSR updates) or a parameter dict."""
+        if not self.initialized:
+            raise RuntimeError("Error in NQS.set_parameters(): Network not initialized. Evaluate net on example "
+                               "input for initialization.")
+        if isinstance(P, dict):
+            self.params = P
+        else:
+            self.params = self._param_unflatten(P)
+
+    def _param_unflatten(self, P):
+        """reference :430-444."""
+        P = _to_dev(P)
+        names = sorted(self.parameters["params"]["Dense_0"].keys())
+        out, start = {}, 0
+        for name, (size, shape) in zip(names, self.paramShapes):
+            if not self.realParams:
+                out[name] = (P[start:start + size] + 1j * P[start + size:start + 2 * size]).reshape(shape) \
+                    .to(torch.complex128)
+                start += 2 * size
+            else:
+                out[name] = P[start:start + size].reshape(shape)
+                start += size
+        return {"Dense_0": out}
+
+    def get_parameters(self):
+        """reference :449-466: per leaf [Re ravel, Im ravel] (complex) or ravel (real)."""
+        if not self.initialized:
+            return None
+        leaves = self._leaves()
+        if not self.realParams:
+            return torch.cat([torch.cat([p.reshape(-1).real, p.reshape(-1).imag]) for p in leaves])
+        return torch.cat([p.reshape(-1) for p in leaves])
+
+    @property
+    def is_generator(self):
+        return self._isGenerator
+
+    @property
+    def params(self):
+        if self.initialized:
+            return self.parameters["params"]
+        return None
+
+    @params.setter
+    def params(self, val):
+        if "params" in val and "Dense_0" not in val:
+            val = val["params"]
+        self.parameters = {"params": {"Dense_0": {k: _to_dev(v) for k, v in val["Dense_0"].items()}}}
+        self._bump()
