@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py -- VMC step throughput (sample + E_loc + S/F) on B200, next to the reference's CPU algorithm.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's algorithm (oracle port) on the host cores
+
+Workload (BASELINE.json configs[1]): 2D TFIM 10x10 (pbc) at g = 3.04, CpxRBM alpha = 4 (N = 100, M = 400,
+P_c = 40 000 complex parameters), 2^16 samples per GPU (weak scaling), Metropolis sampler with
+sweepSteps = N, 25 thermalisation sweeps, propose_spin_flip.  One step = MCSampler.sample (MCMC kernel + logpsi/tau)
+-> BranchFreeOperator.get_O_loc (fused kernel) -> <E>, Var E, mu = <O>, F = <O* E>_c -> S = <O* O>_c
+(Hermitian P_c x P_c, DMMA Gram kernel) [-> all-reduce of mu, F, S over ranks].  Synthetic random-init weights
+(Re, Im ~ U(-1/sqrt(N), 1/sqrt(N)), seed 4321).
+
+Prints ONE JSON line (rank 0)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (lattice shape, g, alpha, bias, samples per GPU, numChains per GPU)
+    "tfim2d_10x10_cpxrbm_a4_2p16": ((10, 10), 3.04, 4, False, 2 ** 16, 2368),
+    "tfim1d_L20_cpxrbm_a2_2p12": ((20,), -0.7, 2, False, 2 ** 12, 500),
+    "tfim1d_L40_cpxrbm_a2_bias_2p16": ((40,), -0.7, 2, True, 2 ** 16, 2368),
+    "tfim2d_6x6_cpxrbm_a4_2p14": ((6, 6), 3.04, 4, False, 2 ** 14, 1184),
+}
+DEFAULT_WORKLOAD = "tfim2d_10x10_cpxrbm_a4_2p16"
+METRIC = "VMC step samples/sec (sample + E_loc + S/F)"
+UNIT = "samples/s"
+
+
+def o1_weights(N, M, bias, seed=4321):
+    rng = np.random.default_rng(seed)
+    a = 1.0 / np.sqrt(N)
+    W = rng.uniform(-a, a, (N, M)) + 1j * rng.uniform(-a, a, (N, M))
+    b = (rng.uniform(-a, a, M) + 1j * rng.uniform(-a, a, M)) if bias else None
+    return W, b
+
+
+def flat_params(W, b):
+    leaves = ([b] if b is not None else []) + [W]
+    return np.concatenate([np.concatenate([x.ravel().real, x.ravel().imag]) for x in leaves])
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for k, nme in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [c for c, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step(shape, g, alpha, bias, nsamp, chains, rng_seed=0, gram_cols=4000):
+    """The reference's algorithm on the host cores (oracle port): Metropolis with a full forward pass per proposal
+    (jVMC/sampler.py:327-356), get_s_primes -> psi(s') local energy (jVMC/operator/base.py:166-192), materialised
+    per-sample gradients and the zgemm Gram (jVMC/stats.py:52-58) -- the Gram is timed on a column block of
+    ``gram_cols`` complex parameters and scaled to P_c (the full P_c x P_c host matrix does not fit every box).
+    Returns (seconds for nsamp samples, detail)."""
+    from oracle import rbm as orbm, bfo as obfo, sampling as osamp, stats as ostats
+    N = int(np.prod(shape))
+    M = alpha * N
+    W, b = o1_weights(N, M, bias)
+    ham = obfo.Tables(obfo.tfim_strings(shape, g, -1.0))
+    f = lambda s: orbm.cpx_rbm_logpsi(s, W, b)
+    spc = max(1, nsamp // chains)
+    # thermalisation amortised as in the full workload: 25 sweeps per 28 emitted samples per chain
+    therm = max(1, int(round(25.0 * spc / 28.0)))
+    smp = osamp.MCSampler(lambda s: np.real(f(s)), N, numChains=chains, proposer="spin_flip",
+                          thermalizationSweeps=therm, sweepSteps=N, seed=rng_seed)
+    t0 = time.perf_counter()
+    cfg, _ = smp.sample(spc * chains)
+    lp = f(cfg)
+    t1 = time.perf_counter()
+    E = obfo.get_O_loc(ham, cfg, f, 0.0, logPsiS=lp)
+    t2 = time.perf_counter()
+    p = np.ones(cfg.shape[0]) / cfg.shape[0]
+    th = np.tanh(orbm.theta(cfg, W, b))
+    sig = 2.0 * cfg - 1.0
+    O = (sig[:, :, None] * th[:, None, :]).reshape(cfg.shape[0], -1)        # Khatri-Rao order, [n, P_c]
+    mu = p @ O
+    D = np.sqrt(p)[:, None] * (O - mu[None, :])
+    Fv = D.conj().T @ (np.sqrt(p) * (E - np.sum(p * E)))
+    cols = min(gram_cols, D.shape[1])
+    t3 = time.perf_counter()
+    Ablk = D.conj().T @ D[:, :cols]
+    t4 = time.perf_counter()
+    t_gram = (t4 - t3) * (D.shape[1] / cols)
+    total = (t1 - t0) + (t2 - t1) + (t3 - t2) + t_gram
+    detail = {"samples": int(cfg.shape[0]), "t_sample_s": t1 - t0, "t_eloc_s": t2 - t1, "t_grad_moments_s": t3 - t2,
+              "t_gram_scaled_s": t_gram, "gram_cols_timed": int(cols), "checksum": float(np.abs(Ablk).sum() + np.abs(Fv).sum())}
+    return total, detail
+
+
+def run_reference_arm(args, wl):
+    shape, g, alpha, bias, nsamp_gpu, chains_gpu = WORKLOADS[wl]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nsamp, chains = 64, 32
+    for _ in range(args.warmup):
+        cpu_reference_step(shape, g, alpha, bias, chains, chains, gram_cols=500)
+    times = []
+    for k in range(args.steps):
+        t, detail = cpu_reference_step(shape, g, alpha, bias, nsamp, chains, rng_seed=k)
+        times.append(t)
+    sec = float(np.mean(times))
+    value = nsamp / sec
+    sample = ("oracle port of the reference algorithm (jax not installable): %d samples/step from %d chains, full forward "
+              "pass per proposal, s'->psi(s') E_loc, dense O and zgemm Gram timed on %d of %d columns and scaled"
+              % (nsamp, chains, detail["gram_cols_timed"], alpha * int(np.prod(shape)) ** 2))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl, "samples_per_step": nsamp, "bounded_sample": True},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "detail": detail}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0, help="override samples per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tdvp", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = args.workload
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import vmc_jax_b200 as jVMC
+    from vmc_jax_b200 import kernels as K, mpi_wrapper as mpi
+    from vmc_jax_b200.stats import SampledObs, RBMGradientObs
+    import vmc_jax_b200.operator as op
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    mpi.init_distributed()
+    rank, world = mpi.rank, mpi.commSize
+    dev = jVMC.global_defs.myDevice
+    shape, g, alpha, bias, nsamp, chains = WORKLOADS[wl]
+    if args.samples:
+        nsamp = args.samples
+    N = int(np.prod(shape))
+    M = alpha * N
+    Pc = (N + (1 if bias else 0)) * M
+
+    # ---- problem set-up (untimed): net, Hamiltonian, sampler
+    psi = jVMC.vqs.NQS(jVMC.nets.CpxRBM(numHidden=M, bias=bias), seed=1234)
+    psi(torch.zeros((1, 1) + shape, dtype=torch.int32, device=dev))
+    W, b = o1_weights(N, M, bias)
+    P_host = torch.as_tensor(flat_params(W, b)).pin_memory()
+    psi.set_parameters(P_host.to(dev))
+    H = op.BranchFreeOperator()
+    if len(shape) == 1:
+        L = shape[0]
+        for l in range(L):
+            H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz((l + 1) % L))))
+            H.add(op.scal_opstr(g, (op.Sx(l),)))
+    else:
+        Lx, Ly = shape
+        for x in range(Lx):
+            for y in range(Ly):
+                l = x * Ly + y
+                H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz(x * Ly + (y + 1) % Ly))))
+                H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz(((x + 1) % Lx) * Ly + y))))
+                H.add(op.scal_opstr(g, (op.Sx(l),)))
+    smp = jVMC.sampler.MCSampler(psi, shape, 4321, updateProposer=jVMC.sampler.propose_spin_flip, numChains=chains,
+                                 sweepSteps=N, thermalizationSweeps=25, numSamples=nsamp * world)
+    smp.refreshEvery = 8
+
+    ev_g0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + args.warmup + 8)]
+    ev_g1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + args.warmup + 8)]
+    state = {"i": 0, "launches": 0}
+    K_COUNT = {"sample": 2, "eloc": 1, "moments": 4, "pack": 1, "gram": 1}
+
+    def vmc_step():
+        s, logPsi, p = smp.sample()
+        Eloc = H.get_O_loc(s, psi, logPsi, 0.0)
+        E = SampledObs(Eloc, p)
+        G = RBMGradientObs(psi, s, p)
+        Emean, Evar = E.mean()[0], E.var()[0]
+        F = G.covar(E)
+        i = state["i"]
+        G.kr_mean()
+        G._sigT = K.pack_sigma(G._s, G.hasBias)
+        ev_g0[i].record()
+        A = G.gram_A()
+        ev_g1[i].record()
+        state["i"] = i + 1
+        state["launches"] += sum(K_COUNT.values())
+        return s, Emean, Evar, F, A
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        out = vmc_step()
+    barrier()
+    nLocal = out[0].shape[1]
+    nGlobal = smp.get_last_number_of_samples()
+    del out
+
+    # ---- timed region: K steps, device-resident inputs
+    clocks = ClockSampler(dev.index if dev.index is not None else 0)
+    clocks.start()
+    time.sleep(0.3)
+    state["launches"] = 0
+    i0 = state["i"]
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = vmc_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = state["launches"]
+    gram_ms = float(np.mean([ev_g0[i].elapsed_time(ev_g1[i]) for i in range(i0, state["i"])]))
+    energy = complex(out[1].item())
+    del out
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    ms_per_step = ms / args.steps
+    value = nGlobal / (ms_per_step * 1e-3)
+
+    # ---- e2e: same step through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    res_host = torch.empty(2 + 2 * Pc, dtype=torch.float64).pin_memory()
+    e2e_steps = max(1, min(args.steps, 2))
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        psi.set_parameters(P_host.to(dev, non_blocking=True))             # H2D: flat parameter vector
+        s, Emean, Evar, F, A = vmc_step()
+        res = torch.cat([torch.view_as_real(Emean.reshape(1)).reshape(-1)[:1], Evar.reshape(1).to(torch.float64),
+                         torch.view_as_real(F.reshape(-1)[:Pc].contiguous()).reshape(-1)])
+        res_host.copy_(res, non_blocking=True)                            # D2H: <E>, Var E, F (S stays on device)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    e2e_value = nGlobal / (float(tms.item()) / e2e_steps * 1e-3)
+    h2d = int(P_host.numel() * 8)
+    d2h = int(res_host.numel() * 8)
+    del s, Emean, Evar, F, A
+
+    # ---- per-phase breakdown (diagnostic, untimed w.r.t. the headline)
+    phases = {}
+    if rank == 0 or world > 1:
+        def timed(fn):
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); r = fn(); b_.record(); torch.cuda.synchronize()
+            return r, a.elapsed_time(b_)
+        (s, logPsi, p), phases["sampling_ms"] = timed(lambda: smp.sample())
+        Eloc, phases["eloc_ms"] = timed(lambda: H.get_O_loc(s, psi, logPsi, 0.0))
+        def mom():
+            E = SampledObs(Eloc, p); G = RBMGradientObs(psi, s, p)
+            return E, G, E.mean(), E.var(), G.covar(E), G.kr_mean()
+        (E, G, *_), phases["moments_F_ms"] = timed(mom)
+        _, phases["gram_S_ms"] = timed(lambda: G.gram_A())
+        phases["acceptance"] = float(smp.acceptance_ratio())
+        del E, G, Eloc, s, logPsi, p
+    torch.cuda.empty_cache()
+
+    # ---- roofline of the dominant kernel (Gram): fp64 tensor pipe
+    R = N + (1 if bias else 0)
+    algo_flop = 4.0 * nLocal * float(Pc) ** 2                 # 4 N_s P_c^2 (complex Hermitian half)
+    TS = 80 if (M % 80 == 0 or M == 40) else 64
+    nT = (M + TS - 1) // TS
+    exec_flop = 8.0 * nLocal * (R * (R + 1) / 2) * (nT * (nT + 1) / 2) * TS * TS   # DMMA flops issued (incl. padding)
+    peak_tf, peak_src = None, None
+    try:
+        n = 8192
+        a = torch.randn(n, n, dtype=torch.float64, device=dev)
+        c = torch.empty_like(a)
+        best = 1e9
+        for _ in range(4):
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record(); torch.matmul(a, a, out=c); x1.record(); torch.cuda.synchronize()
+            best = min(best, x0.elapsed_time(x1))
+        peak_tf = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+        peak_src = "cuBLAS DGEMM 8192^3 measured live (best of 4); MEASURED_PEAKS.json holds no fp64 figure"
+        del a, c
+    except Exception as ex:  # pragma: no cover
+        peak_tf, peak_src = 37.0, "fallback: DMMA issue-rate probe tools/fp64_probe.cu (37.05 TF/s); live DGEMM failed: %r" % (ex,)
+    achieved = algo_flop / (gram_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "gram_s_kernel (fp64 DMMA m8n8k4)", "achieved": achieved, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "launch_ms": gram_ms,
+                "algorithmic_flop_per_launch": algo_flop,
+                "executed_tensor_flop_per_launch": exec_flop,
+                "executed_tflops": exec_flop / (gram_ms * 1e-3) / 1e12,
+                "note": "algorithmic = SURVEY 8d figure 4*N_s*P_c^2 (Hermitian half); the kernel additionally uses the "
+                        "site-pair symmetry of the Khatri-Rao Gram and issues about half of that on the tensor pipe"}
+    tp = os.path.join(ROOT, "profiles", "gram_traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as fh:
+                tj = json.load(fh)
+            if tj.get("workload") == wl:
+                roofline["traffic"] = tj.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = tj.get("source")
+        except Exception:
+            pass
+
+    # ---- TDVP step (sample + E_loc + O_k + S/F + SNR + solve) on the CPU-runnable config 1, for the "TDVP step ms" half
+    tdvp_info = None
+    if not args.no_tdvp and world == 1:
+        try:
+            tdvp_info = tdvp_step_ms(jVMC, op, torch)
+        except Exception as ex:  # pragma: no cover
+            tdvp_info = {"error": repr(ex)}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t, detail = cpu_reference_step(shape, g, alpha, bias, 64, 32)
+        cpu = {"value": 64 / t, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "oracle port of the reference algorithm on 64 samples (32 chains): full-forward Metropolis, "
+                         "s'->psi(s') E_loc, dense O + zgemm Gram timed on %d of %d columns and scaled"
+                         % (detail["gram_cols_timed"], Pc), "detail": detail}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl, "lattice": list(shape), "g": g, "numHidden": M, "P_complex": Pc,
+                           "samples_per_gpu": nLocal, "samples_global": nGlobal, "numChains_per_gpu": chains,
+                           "sweepSteps": N, "thermalizationSweeps": 25, "proposer": "spin_flip",
+                           "l2": "inputs_exceed_L2 (tau %.0f MB, S %.1f GB per GPU)" % (nLocal * M * 16 / 1e6, Pc * Pc * 16 / 1e9),
+                           "parallelism": "chains sharded, %d rank(s), all-reduce of mu/F/S" % world},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "note": "parameters H2D from pinned memory; <E>, VarE, F D2H; S stays on device for the solver"},
+                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+                "phases_ms": phases, "energy_mean": [energy.real, energy.imag], "tdvp_step": tdvp_info}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def tdvp_step_ms(jVMC, op, torch, L=20, alpha=2, nsamp=4096, chains=500, steps=5):
+    """Full TDVP/SR step (TDVP.__call__: sample + E_loc + gradients + S,F + eigh + SNR + regularised solve) on
+    BASELINE configs[0] (1D TFIM L=20, CpxRBM alpha=2, 500 chains, 2^12 -> 4500 samples, ex0-style SR)."""
+    dev = jVMC.global_defs.myDevice
+    psi = jVMC.vqs.NQS(jVMC.nets.CpxRBM(numHidden=alpha * L, bias=False), seed=1234)
+    psi(torch.zeros((1, 1, L), dtype=torch.int32, device=dev))
+    H = op.BranchFreeOperator()
+    for l in range(L):
+        H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz((l + 1) % L))))
+        H.add(op.scal_opstr(-0.7, (op.Sx(l),)))
+    smp = jVMC.sampler.MCSampler(psi, (L,), 4321, updateProposer=jVMC.sampler.propose_spin_flip_Z2, numChains=chains,
+                                 sweepSteps=L, numSamples=nsamp, thermalizationSweeps=25)
+    tdvp = jVMC.util.TDVP(smp, rhsPrefactor=1., pinvTol=1e-8, diagonalShift=10, makeReal='real')
+    stepper = jVMC.util.stepper.Euler(timeStep=1e-2)
+    times = []
+    for k in range(steps + 2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dp, _ = stepper.step(0, tdvp, psi.get_parameters(), hamiltonian=H, psi=psi, numSamples=None)
+        psi.set_parameters(dp)
+        torch.cuda.synchronize()
+        times.append((time.perf_counter() - t0) * 1e3)
+    return {"config": "1D TFIM L=%d, CpxRBM alpha=%d (P=%d), %d chains, %d samples, SR (makeReal=real, diagonalShift=10)"
+                      % (L, alpha, 2 * L * alpha * L, chains, smp.get_last_number_of_samples()),
+            "ms_per_step": float(np.median(times[2:])), "energy_per_site": float(tdvp.ElocMean0.real) / L}
+
+
+if __name__ == "__main__":
+    main()

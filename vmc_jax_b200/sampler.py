@@ -116,10 +116,13 @@ class MCSampler:
             numSamples = self.numSamples
         configs, logPsi = self._get_samples_mcmc(parameters, numSamples, multipleOf)
         expo = 1.0 / self.logProbFactor - self.mu
-        if expo == 0.0:
-            p = torch.ones(logPsi.shape, dtype=torch.float64, device=logPsi.device)
-        else:
-            p = torch.exp(expo * logPsi.real)
+        if expo == 0.0 and multipleOf == 1:
+            # Born sampling: weights are exactly 1/N_glob; tagged so that the Gram kernel can use
+            # a scalar weight without inspecting the array
+            p = torch.full(logPsi.shape, 1.0 / self.globNumSamples, dtype=torch.float64, device=logPsi.device)
+            p._jvmc_uniform = 1.0 / self.globNumSamples
+            return configs, logPsi, p
+        p = torch.exp(expo * logPsi.real)
         return configs, logPsi, p / mpi.global_sum(p)
 
     def _get_samples_mcmc(self, params, numSamples, multipleOf=1):

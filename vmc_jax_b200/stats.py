@@ -141,6 +141,7 @@ class RBMGradientObs(SampledObs):
         self._lead = tuple(s.shape[:2])
         self._s = s.reshape(self._lead[0] * self._lead[1], -1).contiguous()
         self._tau = psi._tau(self._s)
+        self._uniform = getattr(weights, "_jvmc_uniform", None)
         self._weights = torch.as_tensor(weights).to(global_defs.myDevice)
         self._p = self._weights.reshape(-1).contiguous()
         self.N, self.M = self._s.shape[1], self._tau.shape[1]
@@ -228,8 +229,8 @@ class RBMGradientObs(SampledObs):
                 self._sigT = K.pack_sigma(self._s, self.hasBias)
             p = self._p
             kappa = 1.0 / mpi.commSize
-            if p.numel() > 0 and bool((p == p[0]).all()):
-                A = K.rbm_gram_S(self._tau, self._sigT, mu, float(p[0]), kappa)
+            if self._uniform is not None:
+                A = K.rbm_gram_S(self._tau, self._sigT, mu, float(self._uniform), kappa)
             else:
                 A = K.rbm_gram_S(self._tau * torch.sqrt(p)[:, None], self._sigT, mu, 1.0, kappa)
             self._A = mpi._all_reduce_sum(A)
