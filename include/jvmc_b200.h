@@ -86,6 +86,11 @@ int jvmc_rbm_moments_chunks(long long B);
 int jvmc_rbm_moments(const int32_t* s, const double* tau, const double* wgt, long long B, int N, int M,
                      int hasBias, int conjTau, double* workspace, double* out, void* stream);
 
+/* out[n] = sum_{r,j} sigma_{n,r} (conjTau ? conj tau_nj : tau_nj) x[r,j] = O_n . x without forming O: the per-sample
+ * projection used by the centred MinSR kernel (jVMC/stats.py:332-336) and by matrix-free S.v products. */
+int jvmc_rbm_krmatvec(const int32_t* s, const double* tau, const double* x, long long B, int N, int M,
+                      int hasBias, int conjTau, double* out, void* stream);
+
 /* sigT[R][ceil(B/32)] bit-packed transposed spins (bias pseudo-site row first). */
 int jvmc_pack_sigma(const int32_t* s, long long B, int N, int hasBias, unsigned int* sigT, void* stream);
 
@@ -94,6 +99,15 @@ int jvmc_pack_sigma(const int32_t* s, long long B, int N, int hasBias, unsigned 
  * [R*M, R*M] complex128, fully populated.  tile: 0 auto | 64 | 80. */
 int jvmc_rbm_gram_S(const double* Y, long long B, int M, int R, const unsigned int* sigT, const double* mu,
                     double alpha, double kappa, double* A, int tile, void* stream);
+
+/* SampledObs.tangent_kernel (jVMC/stats.py:332-336; MinSR, jVMC/util/minsr.py:59-60), Khatri-Rao form:
+ * T[n,m] = scale sqrt(p_n p_m) [ (sum_r sigma_nr sigma_mr)(sum_j tau_nj conj tau_mj) - v_n - conj(v_m) + c ],
+ * v = O.conj(mu) (jvmc_rbm_krmatvec), c[0] = |mu|^2 (device scalar); sigR from jvmc_pack_sigma_rows
+ * ([B][ceil(R/32)] words).  T row-major [B,B] complex128, fully populated Hermitian.  scale = 2: reference's doubled
+ * holomorphic layout. */
+int jvmc_pack_sigma_rows(const int32_t* s, long long B, int N, int hasBias, unsigned int* sigR, void* stream);
+int jvmc_rbm_gram_T(const double* Y, long long B, int M, int R, const unsigned int* sigR, const double* p,
+                    const double* v, const double* c, double scale, double* T, void* stream);
 
 /* S = q(S0) (+ diagonal shift) in the reference's flat layout from A: jVMC/util/tdvp.py:140-146.
  * mode 0: Re -> double[P,P]; mode 1: i*Im -> complex128[P,P]; column-major. */

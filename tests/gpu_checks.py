@@ -197,6 +197,59 @@ def check_moments_gram(N=7, M=24, B=211, bias=True, seed=11, uniform=True, tile=
     return r
 
 
+def check_gram_T(N=7, M=24, B=211, bias=True, seed=21, uniform=False):
+    """Khatri-Rao tangent kernel T = 2 Obar Obar^dagger and O.x mat-vec vs the dense oracle (stats.py:332-336)."""
+    W, b = orbm.init_o1(N, M, bias, seed)
+    s = rand_configs(B, N, seed + 1)
+    rng = np.random.default_rng(seed + 2)
+    p = np.ones(B) / B if uniform else rng.uniform(0.5, 1.5, B)
+    p = p / p.sum()
+    G = ostats.SampledObs(orbm.gradients_holomorphic(s, W, b), p)
+    T_ref = G.tangent_kernel()
+    ds, dp = dev(s), dev(p)
+    _, tau = K.rbm_logpsi(ds, dev(W), None if b is None else dev(b))
+    mu = K.rbm_moments(ds, tau, dp.to(torch.complex128), bias, 0)
+    T = host(K.rbm_gram_T(ds, tau, dp, mu, bias, 2.0))
+    # scale: the uncentred kernel (T is a difference of such terms; exactly 0 for a single sample)
+    scale = 2.0 * np.max(p) * np.max(np.sum(np.abs(kr_gradients(s, W, b)) ** 2, axis=1))
+    r = float(np.max(np.abs(T - T_ref)) / scale)
+    assert r < RTOL, r
+    assert np.array_equal(T, T.conj().T)
+    x = rng.normal(size=mu.numel()) + 1j * rng.normal(size=mu.numel())
+    u = host(K.rbm_krmatvec(ds, tau, dev(x).reshape(mu.shape), bias))
+    assert relerr(u, kr_gradients(s, W, b) @ x) < RTOL
+    return r
+
+
+def check_minsr_solve(N=4, M=8, bias=False, seed=23):
+    """MinSR update from the factorised path vs oracle minsr_solve (minsr.py:53-80) on the exact basis."""
+    from vmc_jax_b200.util.minsr import pinv_hermitian
+    W, b = orbm.init_o1(N, M, bias, seed)
+    basis = osamp.basis_states(N)
+    lp = orbm.cpx_rbm_logpsi(basis, W, b)
+    p, _ = osamp.exact_probabilities(lp)
+    ham = obfo.Tables(obfo.tfim_strings((N,), -0.9, -1.0))
+    E = obfo.get_O_loc(ham, basis, lambda x: orbm.cpx_rbm_logpsi(x, W, b), logPsiS=lp)
+    oE, oG = ostats.SampledObs(E, p), ostats.SampledObs(orbm.gradients_holomorphic(basis, W, b), p)
+    upd_ref = osolve.minsr_solve(oE, oG, True, pinvTol=1e-6)
+    ds, dp = dev(basis), dev(p)
+    _, tau = K.rbm_logpsi(ds, dev(W), None if b is None else dev(b))
+    mu = K.rbm_moments(ds, tau, dp.to(torch.complex128), bias, 0)
+    T = K.rbm_gram_T(ds, tau, dp, mu, bias, 2.0)
+    Tinv = pinv_hermitian(T, 1e-6)
+    assert relerr(host(Tinv), osolve.pinv_hermitian(oG.tangent_kernel(), 1e-6)) < 1e-7
+    e = dev(oE._data.reshape(-1))
+    x = Tinv @ e
+    wgt = torch.sqrt(dp) * x
+    Fk = (K.rbm_moments(ds, tau, wgt, bias, 1) - mu.conj() * wgt.sum()).reshape(-1)
+    Mb = M if bias else 0
+    parts = ([Fk[:Mb], -1j * Fk[:Mb]] if bias else []) + [Fk[Mb:], -1j * Fk[Mb:]]
+    upd = -torch.cat(parts)
+    r = relerr(host(upd), upd_ref)
+    assert r < 1e-7, r
+    return r
+
+
 # ---------------------------------------------------------------- solve
 def check_tdvp_solve(N=4, M=3, bias=True, makeReal='real', rhsPrefactor=1.0, shift=2.0, seed=13):
     """S expansion + eigh + regulariser vs oracle TDVP.solve on the exact basis (no SNR cut, unique update)."""
@@ -310,4 +363,5 @@ def smoke_check():
     check_eloc(obfo.tfim_strings((8,), -0.7), N=8, M=16, B=64)
     check_moments_gram(N=5, M=16, B=100)
     check_tdvp_solve()
+    check_gram_T(N=5, M=16, B=70)
     check_sampler_chi2(N=4, M=2, numSamples=200_000, C=148)

@@ -1,0 +1,155 @@
+"""-m gpu: BASELINE.json full-size checks through size-independent properties (no oracle run at this size):
+config 2 (2D TFIM 10x10, CpxRBM alpha=4, N=100, M=400, 2^16 samples) and the config-5 lattice (20x20, M=1600)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import jVMC  # noqa: E402
+import jVMC.operator as op  # noqa: E402
+from jVMC.stats import SampledObs, RBMGradientObs  # noqa: E402
+from vmc_jax_b200 import kernels as K  # noqa: E402
+
+import gpu_checks as G  # noqa: E402
+from oracle import rbm as orbm, bfo as obfo  # noqa: E402
+
+
+def tfim2d(Lx, Ly, g, parts="all"):
+    H = op.BranchFreeOperator()
+    for x in range(Lx):
+        for y in range(Ly):
+            l = x * Ly + y
+            if parts in ("all", "zz"):
+                H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz(x * Ly + (y + 1) % Ly))))
+                H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz(((x + 1) % Lx) * Ly + y))))
+            if parts in ("all", "x"):
+                H.add(op.scal_opstr(g, (op.Sx(l),)))
+    return H
+
+
+@pytest.fixture(scope="module")
+def cfg2():
+    shape, M = (10, 10), 400
+    N = 100
+    psi = jVMC.vqs.NQS(jVMC.nets.CpxRBM(numHidden=M, bias=False), seed=1)
+    psi(torch.zeros((1, 1) + shape, dtype=torch.int32, device="cuda"))
+    W, b = orbm.init_o1(N, M, False, 4321)
+    psi.set_parameters(torch.as_tensor(orbm.flatten_params(W, b)))
+    smp = jVMC.sampler.MCSampler(psi, shape, 4321, updateProposer=jVMC.sampler.propose_spin_flip, numChains=2368,
+                                 sweepSteps=N, thermalizationSweeps=25, numSamples=2 ** 16)
+    s, logPsi, p = smp.sample()
+    return dict(psi=psi, smp=smp, s=s, logPsi=logPsi, p=p, W=W, N=N, M=M)
+
+
+def test_cfg2_sampler_and_logpsi(cfg2):
+    s, logPsi, p, psi = cfg2["s"], cfg2["logPsi"], cfg2["p"], cfg2["psi"]
+    assert s.shape == (1, 66304, 10, 10) and cfg2["smp"].get_last_number_of_samples() == 66304
+    assert int(s.min()) == 0 and int(s.max()) == 1
+    assert abs(float(p.sum()) - 1.0) < 1e-12
+    acc = float(cfg2["smp"].acceptance_ratio())
+    assert 0.02 < acc < 0.98
+    # Z2 property: without bias logpsi is invariant under a global spin flip (cosh is even)
+    lp2 = psi(1 - s)
+    assert float(torch.max(torch.abs(lp2.real - logPsi.real))) < 1e-10
+    # spot parity with the oracle on 256 of the 66304 samples
+    idx = torch.arange(0, 66304, 259, device="cuda")
+    ref = orbm.cpx_rbm_logpsi(G.host(s[0, idx]).reshape(len(idx), -1), cfg2["W"])
+    assert np.max(np.abs(G.host(logPsi[0, idx]) - ref) / np.abs(ref)) < 1e-10
+
+
+def test_cfg2_eloc_linearity_and_spot_parity(cfg2):
+    s, logPsi, psi = cfg2["s"], cfg2["logPsi"], cfg2["psi"]
+    g = 3.04
+    E = tfim2d(10, 10, g).get_O_loc(s, psi, logPsi)
+    Ezz = tfim2d(10, 10, g, "zz").get_O_loc(s, psi, logPsi)
+    Ex = tfim2d(10, 10, g, "x").get_O_loc(s, psi, logPsi)
+    E2 = tfim2d(10, 10, 2 * g).get_O_loc(s, psi, logPsi)
+    scale = float(E.abs().max())
+    assert float((E - (Ezz + Ex)).abs().max()) < 1e-10 * scale          # additivity over operator strings
+    assert float((E2 - E - Ex).abs().max()) < 1e-10 * scale             # linearity in the prefactor
+    assert float(Ezz.imag.abs().max()) == 0.0                           # diagonal part is real
+    idx = torch.arange(0, 66304, 1031, device="cuda")
+    sub = G.host(s[0, idx]).reshape(len(idx), -1)
+    tab = obfo.Tables(obfo.tfim_strings((10, 10), g, -1.0))
+    ref = obfo.get_O_loc(tab, sub, lambda x: orbm.cpx_rbm_logpsi(x, cfg2["W"]))
+    assert G.relerr(G.host(E[0, idx]), ref) < 1e-10
+
+
+def test_cfg2_s_primes_structure(cfg2):
+    """get_s_primes at full size on a 4096-sample slice (2.6 GB would be needed for all): structural invariants."""
+    s = cfg2["s"][:, :4096].contiguous()
+    H = tfim2d(10, 10, 3.04)
+    sp, matEl = H.get_s_primes(s)
+    Kmax = matEl.shape[2]
+    assert Kmax in (100, 101) and sp.shape == (1, 4096 * Kmax, 10, 10)
+    spv = sp.reshape(4096, Kmax, 100)
+    flips = (spv != s.reshape(4096, 1, 100)).sum(-1)
+    cnt = H.numNonzero.reshape(-1)
+    # slot 0 = merged diagonal (no flip) when non-zero, then one single-site flip per Sx string in site order
+    has_diag = cnt == 101
+    assert bool(((flips[:, 0] == 0) == has_diag).all())
+    assert bool((flips[has_diag][:, 1:101] == 1).all())
+    assert torch.allclose(matEl.reshape(4096, Kmax)[has_diag][:, 1:101], torch.full((1,), 3.04, dtype=torch.complex128,
+                                                                                   device="cuda"))
+    zz = (2.0 * s.reshape(4096, 10, 10) - 1)
+    ediag = -(zz * torch.roll(zz, -1, 2)).sum((1, 2)) - (zz * torch.roll(zz, -1, 1)).sum((1, 2))
+    assert torch.allclose(matEl.reshape(4096, Kmax)[has_diag][:, 0].real, ediag[has_diag].to(torch.float64))
+
+
+def test_cfg2_gram_matvec_identity(cfg2):
+    """S at P_c = 40 000 (25.6 GB): exactly Hermitian, and S.v equals the matrix-free Khatri-Rao product
+    sum_n p_n conj(dO_n) (dO_n . v) built from the moment / mat-vec kernels (validated against the oracle at small
+    sizes) -- 1e-10 relative."""
+    psi, s, p = cfg2["psi"], cfg2["s"], cfg2["p"]
+    Gobs = RBMGradientObs(psi, s, p)
+    A = Gobs.gram_A()
+    assert A.shape == (40000, 40000)
+    blk = A[:4000, 36000:]
+    assert torch.equal(blk, A[36000:, :4000].conj().T)
+    assert float(torch.diagonal(A).imag.abs().max()) == 0.0 and float(torch.diagonal(A).real.min()) > 0.0
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    v = torch.randn(40000, dtype=torch.complex128, device="cuda", generator=gen)
+    mu = Gobs.kr_mean()
+    u = K.rbm_krmatvec(Gobs._s, Gobs._tau, v.reshape(mu.shape), False) - (mu.reshape(-1) * v).sum()
+    w = K.rbm_moments(Gobs._s, Gobs._tau, Gobs._p * u, False, 1) - mu.conj() * (Gobs._p * u).sum()
+    Av = A @ v
+    assert float((Av - w.reshape(-1)).abs().max() / Av.abs().max()) < 1e-10
+    # trace identity: tr S = sum_c Var(O_c)
+    assert abs(float(torch.diagonal(A).real.sum() / Gobs.var()[:40000].sum()) - 1.0) < 1e-10
+    del A
+
+
+def test_cfg5_lattice_sampler_eloc_minsr():
+    """20x20 TFIM, CpxRBM alpha=4 (N=400, M=1600, P_c=640 000): sampler + fused E_loc + Khatri-Rao MinSR kernel
+    on 4096 samples; T checked through T.x = Obar (Obar^dagger x) computed matrix-free."""
+    shape, N, M = (20, 20), 400, 1600
+    psi = jVMC.vqs.NQS(jVMC.nets.CpxRBM(numHidden=M, bias=False), seed=1)
+    psi(torch.zeros((1, 1) + shape, dtype=torch.int32, device="cuda"))
+    W, b = orbm.init_o1(N, M, False, 4321)
+    psi.set_parameters(torch.as_tensor(orbm.flatten_params(W, b)))
+    smp = jVMC.sampler.MCSampler(psi, shape, 11, updateProposer=jVMC.sampler.propose_spin_flip, numChains=1024,
+                                 sweepSteps=N, thermalizationSweeps=5, numSamples=4096)
+    s, logPsi, p = smp.sample()
+    assert s.shape == (1, 4096, 20, 20)
+    H = tfim2d(20, 20, 3.04)
+    E = H.get_O_loc(s, psi, logPsi)
+    idx = torch.arange(0, 4096, 257, device="cuda")
+    tab = obfo.Tables(obfo.tfim_strings((20, 20), 3.04, -1.0))
+    ref = obfo.get_O_loc(tab, G.host(s[0, idx]).reshape(len(idx), -1), lambda x: orbm.cpx_rbm_logpsi(x, W))
+    assert G.relerr(G.host(E[0, idx]), ref) < 1e-10
+    Gobs = RBMGradientObs(psi, s, p)
+    T = Gobs.tangent_kernel()
+    assert T.shape == (4096, 4096) and torch.equal(T, T.conj().T)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(4096, dtype=torch.complex128, device="cuda", generator=gen)
+    # Obar^dagger x (Khatri-Rao order), then Obar (.)  ; factor 2 = doubled holomorphic layout
+    mu = Gobs.kr_mean()
+    wgt = torch.sqrt(Gobs._p) * x
+    y = K.rbm_moments(Gobs._s, Gobs._tau, wgt, False, 1) - mu.conj() * wgt.sum()       # conj(Obar)^T x
+    Tx = 2.0 * torch.sqrt(Gobs._p) * (K.rbm_krmatvec(Gobs._s, Gobs._tau, y, False) - (mu * y).sum())
+    ref = T @ x
+    assert float((Tx - ref).abs().max() / ref.abs().max()) < 1e-10
+    upd = jVMC.util.MinSR(smp, pinvTol=1e-8).solve(SampledObs(E, p), Gobs, holomorphic=True)
+    assert upd.shape == (2 * 2 * N * M // 2 * 1,) or upd.numel() == 2 * N * M
+    assert bool(torch.isfinite(upd.real).all())

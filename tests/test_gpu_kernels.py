@@ -94,6 +94,18 @@ def test_moments_and_gram(N, M, B, bias, uniform, tile):
     G.check_moments_gram(N, M, B, bias, uniform=uniform, tile=tile)
 
 
+@pytest.mark.parametrize("N,M,B,bias,uniform", [(7, 24, 211, True, False), (7, 24, 64, False, True),
+                                                 (5, 40, 129, False, False), (40, 7, 65, True, False),
+                                                 (3, 16, 1, False, True), (12, 33, 300, True, True)])
+def test_tangent_kernel_T(N, M, B, bias, uniform):
+    G.check_gram_T(N, M, B, bias, uniform=uniform)
+
+
+@pytest.mark.parametrize("bias", [False, True])
+def test_minsr_solve(bias):
+    G.check_minsr_solve(bias=bias)
+
+
 @pytest.mark.parametrize("makeReal,x,shift,bias", [('real', 1.0, 2.0, False), ('real', 1.0, 0.0, True),
                                                   ('imag', 1.j, 0.0, False), ('imag', 1.j, 0.0, True)])
 def test_tdvp_solve(makeReal, x, shift, bias):

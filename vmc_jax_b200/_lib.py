@@ -38,6 +38,9 @@ _SIGS = {
     "jvmc_rbm_grad": (c_int, [c_ptr, c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "jvmc_rbm_moments_chunks": (c_int, [c_ll]),
     "jvmc_rbm_moments": (c_int, [c_ptr, c_ptr, c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "jvmc_rbm_krmatvec": (c_int, [c_ptr, c_ptr, c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
+    "jvmc_pack_sigma_rows": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr]),
+    "jvmc_rbm_gram_T": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr]),
     "jvmc_pack_sigma": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr]),
     "jvmc_rbm_gram_S": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_int, c_ptr]),
     "jvmc_expand_S": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr]),
@@ -84,6 +87,7 @@ def ptr(t):
     if t is None:
         return None
     assert t.is_contiguous(), "kernel arguments must be contiguous"
+    assert not (t.is_complex() and t.is_conj()), "kernel arguments must have their conjugation materialised"
     return ctypes.c_void_p(t.data_ptr())
 
 

@@ -119,6 +119,32 @@ __global__ void moments_finish_kernel(const cplx* __restrict__ partial, int chun
   out[k] = a;
 }
 
+// out[n] = sum_{r,j} sigma_{n,r} tau~_{n,j} x[r,j]  (O_n . x, Khatri-Rao mat-vec; one warp per sample).
+// x is staged through shared memory in site blocks; lanes stride over hidden units.
+__global__ void __launch_bounds__(256)
+rbm_krmatvec_kernel(const int32_t* __restrict__ s, const cplx* __restrict__ tau, const cplx* __restrict__ x,
+                    long long B, int N, int M, int hasBias, int conjTau, cplx* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n = (long long)blockIdx.x * 8 + warp;
+  if (n >= B) return;
+  const int R = N + (hasBias ? 1 : 0);
+  cplx acc = cmk(0.0, 0.0);
+  for (int j = lane; j < M; j += 32) {
+    cplx t = tau[n * M + j];
+    if (conjTau) t.y = -t.y;
+    cplx col = cmk(0.0, 0.0);
+    for (int r = 0; r < R; ++r) {
+      double sg = (hasBias && r == 0) ? 1.0 : (double)(2 * s[n * N + (r - (hasBias ? 1 : 0))] - 1);
+      cplx xv = x[(size_t)r * M + j];
+      col.x = fma(sg, xv.x, col.x);
+      col.y = fma(sg, xv.y, col.y);
+    }
+    acc = cadd(acc, cmul(t, col));
+  }
+  acc = warp_csum(acc);
+  if (lane == 0) out[n] = acc;
+}
+
 // sigT[r][w] bit k of word w = (sigma_{32w+k, r} == +1); bias pseudo-site row (all ones) first.
 __global__ void pack_sigma_kernel(const int32_t* __restrict__ s, long long B, int N, int hasBias, long long words,
                                   uint32_t* __restrict__ sigT) {
@@ -170,6 +196,16 @@ extern "C" int jvmc_rbm_moments(const int32_t* s, const double* tau, const doubl
   long long RM = (long long)R * M;
   moments_finish_kernel<<<(unsigned)((RM + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const cplx*)workspace, chunks, RM, (cplx*)out);
+  JVMC_CHECK_LAUNCH();
+  return JVMC_OK;
+}
+
+extern "C" int jvmc_rbm_krmatvec(const int32_t* s, const double* tau, const double* x, long long B, int N, int M,
+                                 int hasBias, int conjTau, double* out, void* stream) {
+  if (B == 0) return JVMC_OK;
+  if (!s || !tau || !x || !out || B < 0 || N <= 0 || M <= 0) return JVMC_ERR_ARG;
+  rbm_krmatvec_kernel<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      s, (const cplx*)tau, (const cplx*)x, B, N, M, hasBias, conjTau, (cplx*)out);
   JVMC_CHECK_LAUNCH();
   return JVMC_OK;
 }

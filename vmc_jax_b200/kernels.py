@@ -21,6 +21,8 @@ def _c(t, dtype=None):
         return None
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
+    if t.is_complex():
+        t = t.resolve_conj()      # torch conjugates lazily: kernels read raw memory
     return t.contiguous()
 
 
@@ -151,6 +153,18 @@ def rbm_moments(s, tau, wgt, hasBias, conjTau):
     return out
 
 
+def rbm_krmatvec(s, tau, x, hasBias, conjTau=False):
+    """out[n] = sum_{r,j} sigma_nr (conj?)tau_nj x[r,j]  (O_n . x)."""
+    s = _c(s, I32)
+    tau = _c(tau, CPX)
+    x = _c(x, CPX)
+    B, N = s.shape
+    M = tau.shape[1]
+    out = torch.empty(B, dtype=CPX, device=s.device)
+    call("jvmc_rbm_krmatvec", ptr(s), ptr(tau), ptr(x), B, N, M, int(hasBias), int(conjTau), ptr(out))
+    return out
+
+
 def pack_sigma(s, hasBias):
     s = _c(s, I32)
     B, N = s.shape
@@ -171,6 +185,25 @@ def rbm_gram_S(Y, sigT, mu, alpha, kappa, out=None, tile=0):
         out = torch.empty((R * M, R * M), dtype=CPX, device=Y.device)
     call("jvmc_rbm_gram_S", ptr(Y), B, M, R, ptr(sigT), ptr(mu), float(alpha), float(kappa), ptr(out), int(tile))
     return out
+
+
+def rbm_gram_T(s, tau, p, mu, hasBias, scale=1.0):
+    """Centred tangent kernel T = scale * Obar Obar^dagger [B,B] from the Khatri-Rao factors (no dense O)."""
+    s = _c(s, I32)
+    tau = _c(tau, CPX)
+    p = _c(p, F64)
+    mu = _c(mu, CPX)
+    B, N = s.shape
+    M = tau.shape[1]
+    R = N + (1 if hasBias else 0)
+    wordsR = (R + 31) // 32
+    sigR = torch.empty((B, wordsR), dtype=I32, device=s.device)
+    call("jvmc_pack_sigma_rows", ptr(s), B, N, int(hasBias), ptr(sigR))
+    v = rbm_krmatvec(s, tau, mu.conj().contiguous(), hasBias)
+    c = (mu.conj() * mu).real.sum().reshape(1).contiguous()
+    T = torch.empty((B, B), dtype=CPX, device=s.device)
+    call("jvmc_rbm_gram_T", ptr(tau), B, M, R, ptr(sigR), ptr(p), ptr(v), ptr(c), float(scale), ptr(T))
+    return T
 
 
 def expand_S(A, M, N, hasBias, mode, shift):

@@ -314,9 +314,16 @@ class RBMGradientObs(SampledObs):
         return s2 - (s1.conj() * s1).real
 
     def tangent_kernel(self):
-        all_data = mpi.gather(self._data)
-        all_data = all_data.reshape(all_data.shape[0], -1)
-        return all_data @ all_data.conj().T
+        """Obar Obar^dagger over the samples of all ranks (reference stats.py:332-336) from the gathered
+        Khatri-Rao factors (configs, tau, weights) -- O itself is never formed or communicated."""
+        mu = self.kr_mean()
+        if mpi.commSize > 1:
+            s_all = mpi.gather(self._s[None])
+            tau_all = mpi.gather(self._tau[None])
+            p_all = mpi.gather(self._p[None])
+        else:
+            s_all, tau_all, p_all = self._s, self._tau, self._p
+        return K.rbm_gram_T(s_all, tau_all, p_all, mu, self.hasBias, 2.0 if self.holomorphic else 1.0)
 
     def minsr_contract(self, x):
         """-Obar^dagger x in the reference flat layout (jVMC/util/minsr.py:65) for the gathered vector x,

@@ -1,13 +1,20 @@
 """Mirror of jVMC/util/minsr.py: energy minimisation via MinSR (arXiv:2302.01941)."""
 import torch
 
+from .. import kernels as K
 from .. import mpi_wrapper as mpi
 from ..stats import SampledObs, RBMGradientObs
 
 
 def pinv_hermitian(T, rtol):
     """jnp.linalg.pinv(T, rtol=..., hermitian=True): eigh-based, |ev| <= rtol * max|ev| dropped."""
-    ev, V = torch.linalg.eigh(T)
+    if T.is_cuda:
+        # cuSOLVER through the C ABI: T.T.contiguous() is the column-major image of T; row k of the result is
+        # eigenvector k
+        ev, Vt, _ = K.eigh_inplace(T.T.contiguous())
+        V = Vt.T
+    else:
+        ev, V = torch.linalg.eigh(T)
     cut = rtol * ev.abs().max()
     inv = torch.where(ev.abs() > cut, 1.0 / torch.where(ev == 0, torch.ones_like(ev), ev), torch.zeros_like(ev))
     return (V * inv.to(V.dtype)[None, :]) @ V.conj().T
