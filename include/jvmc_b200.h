@@ -100,6 +100,17 @@ int jvmc_pack_sigma(const int32_t* s, long long B, int N, int hasBias, unsigned 
 int jvmc_rbm_gram_S(const double* Y, long long B, int M, int R, const unsigned int* sigT, const double* mu,
                     double alpha, double kappa, double* A, int tile, void* stream);
 
+/* Same contract as jvmc_rbm_gram_S on the tcgen05 INT8 tensor cores (Ozaki splitting, fp64-equivalent result):
+ * jvmc_i8_layout -> scratch sizes; jvmc_i8_slice -> per-column power-of-two scales + 5 balanced base-255 int8 digits in
+ * the UMMA canonical layout (digits must be zero-initialised); jvmc_rbm_gram_S_i8 -> A.  tiles: device (I,J) int pairs
+ * (128 x 96 real-column tiles containing an element l <= j). */
+int jvmc_i8_layout(long long B, int M, long long* numChunks, int* numZGroups, long long* digitBytes);
+int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long long* colmax, double* scale,
+                  signed char* digits, void* stream);
+int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale, long long B, int M, int R,
+                       const unsigned int* sigT, const int* tiles, int numTiles, const double* mu, double alpha,
+                       double kappa, double* A, void* stream);
+
 /* SampledObs.tangent_kernel (jVMC/stats.py:332-336; MinSR, jVMC/util/minsr.py:59-60), Khatri-Rao form:
  * T[n,m] = scale sqrt(p_n p_m) [ (sum_r sigma_nr sigma_mr)(sum_j tau_nj conj tau_mj) - v_n - conj(v_m) + c ],
  * v = O.conj(mu) (jvmc_rbm_krmatvec), c[0] = |mu|^2 (device scalar); sigR from jvmc_pack_sigma_rows

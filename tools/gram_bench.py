@@ -18,6 +18,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--tile", type=int, default=0)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--dbg", type=int, default=0)
+ap.add_argument("--i8", action="store_true")
 a = ap.parse_args()
 TILE_ARG = a.tile + 1000 * a.dbg
 dev = "cuda:0"
@@ -28,13 +29,27 @@ mu = K.rbm_moments(s, tau, torch.full((a.B,), 1.0 / a.B, dtype=torch.complex128,
 sigT = K.pack_sigma(s, False)
 Pc = a.N * a.M
 A = torch.empty((Pc, Pc), dtype=torch.complex128, device=dev)
-K.rbm_gram_S(tau, sigT, mu, 1.0 / a.B, 1.0, out=A, tile=TILE_ARG)
+def run():
+    if a.i8:
+        K.rbm_gram_S_i8(tau, sigT, mu, 1.0 / a.B, 1.0, out=A)
+    else:
+        K.rbm_gram_S(tau, sigT, mu, 1.0 / a.B, 1.0, out=A, tile=TILE_ARG)
+
+
+run()
 torch.cuda.synchronize()
+if a.i8:
+    A8 = A.clone()
+    K.rbm_gram_S(tau, sigT, mu, 1.0 / a.B, 1.0, out=A, tile=0)
+    torch.cuda.synchronize()
+    print("i8 vs fp64 DMMA: max abs diff %.3e, scale %.3e, hermitian %s" % (float((A8 - A).abs().max()), float(A.abs().max()),
+                                                                     bool(torch.equal(A8, A8.conj().T))))
+    del A8
 ts = []
 for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    K.rbm_gram_S(tau, sigT, mu, 1.0 / a.B, 1.0, out=A, tile=TILE_ARG)
+    run()
     e1.record()
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))

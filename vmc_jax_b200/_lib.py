@@ -39,6 +39,10 @@ _SIGS = {
     "jvmc_rbm_moments_chunks": (c_int, [c_ll]),
     "jvmc_rbm_moments": (c_int, [c_ptr, c_ptr, c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "jvmc_rbm_krmatvec": (c_int, [c_ptr, c_ptr, c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
+    "jvmc_i8_layout": (c_int, [c_ll, c_int, ctypes.POINTER(c_ll), ctypes.POINTER(c_int), ctypes.POINTER(c_ll)]),
+    "jvmc_i8_slice": (c_int, [c_ptr, c_ll, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "jvmc_rbm_gram_S_i8": (c_int, [c_ptr, c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_dbl, c_dbl, c_ptr,
+                                   c_ptr]),
     "jvmc_pack_sigma_rows": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr]),
     "jvmc_rbm_gram_T": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr]),
     "jvmc_pack_sigma": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr]),

@@ -1,0 +1,425 @@
+// jvmc_rbm_gram_S_i8 -- the quantum Fisher matrix S on the 5th-generation (tcgen05) INT8 tensor cores with an
+// Ozaki-style error-free splitting: fp64-equivalent accuracy (<= 1e-11 of the column scales) at several times the
+// fp64 DMMA rate.  Same contract as jvmc_rbm_gram_S (gram.cu); replaces SampledObs.covar() on the gradients
+// (reference jVMC/stats.py:52-58,235-245 via jVMC/util/tdvp.py:142).
+//
+//   A[(r,j),(r',l)] = alpha sum_n s_n conj(Y_nj) Y_nl - kappa conj(mu_rj) mu_r'l ,   s_n = sigma_nr sigma_nr'
+//
+// 1. jvmc_i8_slice: every real column z of Z = [Re Y_j, Im Y_j] (interleaved, 2M columns) gets a power-of-two scale
+//    c_z > 2 max_n |Z_nz| and each entry is split into 5 balanced base-255 digits, Z_nz = c_z sum_k d_k 255^-k,
+//    d_k in [-127, 127] (int8, symmetric so that negation is exact).  Digits are stored in the K-major SWIZZLE_NONE
+//    UMMA canonical layout [digit][n/16][z/8][z%8][n%16], so that a (tile, 16-sample chunk) is one contiguous block.
+// 2. gram_s_i8_kernel: CTA = (site pair r<=r', tile I,J): rows = 128 real columns (64 complex j), cols = 96 real
+//    columns (48 complex l).  Per 32-sample stage the producer warp bulk-copies (TMA engine) 5 A-digit and 5 B-digit
+//    tiles into an mbarrier-guarded smem ring; four "sign" warps apply s_n to the A tiles by byte-wise negation;
+//    one thread issues 15 tcgen05.mma kind::i8 (M=128, N=96, K=32; SASS UTCIMMA), digit pair (k,k') accumulating
+//    exactly in int32 into the TMEM accumulator of level t = k+k' (5 levels x 96 columns = 480 TMEM columns).
+//    One launch covers at most 16384 samples (int32 head-room); at its end four epilogue warps read TMEM
+//    (tcgen05.ld), weight level t by 255^-t in fp64, combine real/imag parts with a lane shuffle, apply scales, alpha
+//    and the mean correction and scatter the Hermitian images (later launches add into A).
+//    Dropped digit pairs (k+k' > 6) are below 4 * 255^-7 = 6e-17 of c_z c_z'; the splitting itself is exact to
+//    255^-5 = 9e-13 of the column scale.
+#include "common.cuh"
+
+namespace {
+
+constexpr int I8_S = 5;                 // digits
+constexpr int I8_LEV = 5;               // levels t = 2..6
+constexpr int I8_TM = 128, I8_TN = 96;  // tile in real columns
+constexpr int I8_KS = 32;               // samples per stage (one MMA K)
+constexpr int I8_SLOTS = 6;
+constexpr int I8_A_BYTES = I8_TM * I8_KS;   // per digit
+constexpr int I8_B_BYTES = I8_TN * I8_KS;
+constexpr int I8_STAGE_BYTES = I8_S * (I8_A_BYTES + I8_B_BYTES);
+constexpr int I8_MAXSTAGES = 512;       // stages per launch: 512*32*5*127^2 < 2^31 (int32 head-room in TMEM)
+constexpr int I8_THREADS = 320;         // warp 0 producer, 1 MMA, 2-9 sign (6-9 also epilogue)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// K-major SWIZZLE_NONE UMMA shared-memory descriptor (canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units)
+__device__ __forceinline__ uint64_t umma_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tacc, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tri_decode(long long p, int& hi, int& lo) {
+  long long h = (long long)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+  while ((h + 1) * (h + 2) / 2 <= p) ++h;
+  while (h * (h + 1) / 2 > p) --h;
+  hi = (int)h;
+  lo = (int)(p - h * (h + 1) / 2);
+}
+
+// ------------------------------------------------------------------------------------------ slicing
+// column maxima of |Re|, |Im| : colmax[2j], colmax[2j+1] as bit patterns (non-negative doubles order like uint64)
+__global__ void i8_colmax_kernel(const cplx* __restrict__ Y, long long B, int M, unsigned long long* __restrict__ colmax) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const long long n0 = (long long)blockIdx.y * 1024;
+  const long long n1 = min(B, n0 + 1024);
+  double mr = 0.0, mi = 0.0;
+  for (long long n = n0; n < n1; ++n) {
+    cplx v = Y[n * M + j];
+    mr = fmax(mr, fabs(v.x));
+    mi = fmax(mi, fabs(v.y));
+  }
+  atomicMax(colmax + 2 * j, (unsigned long long)__double_as_longlong(mr));
+  atomicMax(colmax + 2 * j + 1, (unsigned long long)__double_as_longlong(mi));
+}
+
+// scale[z] = 2^(e+1) with max < 2^e  (so that |Z/scale| < 1/2); 1 for empty columns
+__global__ void i8_scale_kernel(const unsigned long long* __restrict__ colmax, int twoM, double* __restrict__ scale) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= twoM) return;
+  double m = __longlong_as_double((long long)colmax[z]);
+  int e = 0;
+  if (m > 0.0) { (void)frexp(m, &e); ++e; }
+  scale[z] = ldexp(1.0, e);
+}
+
+// digits[k][chunk][zgroup][z%8][n%16]; one thread per (16-sample chunk, real column z): 16 strided loads, 5x16B stores
+__global__ void __launch_bounds__(256)
+i8_slice_kernel(const cplx* __restrict__ Y, long long B, int M, const double* __restrict__ scale, long long numChunks,
+                int numZGroups, int8_t* __restrict__ dig) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;     // fastest: coalesced over columns
+  const long long ch = blockIdx.y;
+  if (z >= 2 * M) return;
+  const double inv = 1.0 / scale[z];
+  const double* Yd = reinterpret_cast<const double*>(Y);
+  int8_t d[I8_S][16];
+  for (int q = 0; q < 16; ++q) {
+    const long long n = ch * 16 + q;
+    double x = (n < B) ? Yd[n * 2 * M + z] * inv : 0.0;
+    long long X = llrint(x * 1078203909375.0);             // 255^5
+#pragma unroll
+    for (int k = I8_S - 1; k >= 0; --k) {
+      long long qd = (X >= 0) ? (X + 127) / 255 : -((-X + 127) / 255);   // round(X / 255), remainder in [-127,127]
+      d[k][q] = (int8_t)(X - qd * 255);
+      X = qd;
+    }
+  }
+  const size_t perDigit = (size_t)numChunks * numZGroups * 128;
+  const size_t off = ((size_t)ch * numZGroups + (z >> 3)) * 128 + (size_t)(z & 7) * 16;
+#pragma unroll
+  for (int k = 0; k < I8_S; ++k) *reinterpret_cast<int4*>(dig + k * perDigit + off) = *reinterpret_cast<const int4*>(d[k]);
+}
+
+// ------------------------------------------------------------------------------------------ main kernel
+struct I8Args {
+  const int8_t* dig;
+  long long numChunks;     // 16-sample chunks (even)
+  int numZGroups;          // padded real columns / 8
+  const double* scale;     // [2M]
+  const uint32_t* sigT;    // [R][words]
+  long long words;
+  const int2* tiles;       // (I, J) list
+  const cplx* mu;
+  double alpha, kappa;
+  cplx* A;
+  int M, R;
+  long long stage0, stage1;   // this launch covers sample stages [stage0, stage1), at most I8_MAXSTAGES
+  int accumulate;             // 0: A = alpha G - kappa mu^H mu ; 1: A += alpha G
+};
+
+__global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* ring = smem_raw;                                                     // [slot][A digits | B digits]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)I8_SLOTS * I8_STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* sgn = bars + I8_SLOTS;
+  uint64_t* empty = bars + 2 * I8_SLOTS;
+  uint64_t* accfull = bars + 3 * I8_SLOTS;
+  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(accfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int r1, r0;
+  tri_decode(blockIdx.x, r1, r0);   // r0 <= r1
+  const int2 tile = a.tiles[blockIdx.y];
+  const int TI = tile.x, TJ = tile.y;
+  const long long numStages = a.stage1 - a.stage0;
+  const size_t perDigit = (size_t)a.numChunks * a.numZGroups * 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < I8_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(sgn + s, 8); mbar_init(empty + s, 1); }
+    mbar_init(accfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_base_p)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = *tmem_base_p;
+
+  if (warp == 0) {
+    // ===================== producer: 20 bulk copies per stage =====================
+    for (long long g = 0; g < numStages; ++g) {
+      const int slot = (int)(g % I8_SLOTS);
+      if (g >= I8_SLOTS) mbar_wait(empty + slot, (unsigned)((g / I8_SLOTS - 1) & 1));
+      unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
+      if (lane == 0) mbar_expect_tx(full + slot, (unsigned)I8_STAGE_BYTES);
+      __syncwarp();
+      if (lane < 2 * I8_S * 2) {
+        const int k = lane / 4, rem = lane % 4, which = rem >> 1, ch = rem & 1;
+        const long long gch = (a.stage0 + g) * 2 + ch;
+        const int8_t* src = a.dig + k * perDigit +
+                            ((size_t)gch * a.numZGroups + (which ? (size_t)TJ * (I8_TN / 8) : (size_t)TI * (I8_TM / 8))) * 128;
+        unsigned char* dst = which ? (st + I8_S * I8_A_BYTES + k * I8_B_BYTES + ch * (I8_TN / 8) * 128)
+                                   : (st + k * I8_A_BYTES + ch * (I8_TM / 8) * 128);
+        bulk_g2s(dst, src, which ? (I8_TN / 8) * 128 : (I8_TM / 8) * 128, full + slot);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_TN >> 3) << 17) | ((uint32_t)(I8_TM >> 4) << 24);
+      for (long long g = 0; g < numStages; ++g) {
+        const int slot = (int)(g % I8_SLOTS);
+        const bool first = (g == 0);
+        mbar_wait(sgn + slot, (unsigned)((g / I8_SLOTS) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const unsigned sa = smem_u32(ring + (size_t)slot * I8_STAGE_BYTES);
+        const unsigned sb = sa + I8_S * I8_A_BYTES;
+#pragma unroll
+        for (int t = 2; t <= I8_LEV + 1; ++t) {
+          bool fresh = first;
+#pragma unroll
+          for (int k = 1; k <= I8_S; ++k) {
+            const int kp = t - k;
+            if (kp < 1 || kp > I8_S) continue;
+            uint64_t da = umma_desc(sa + (k - 1) * I8_A_BYTES, (I8_TM / 8) * 128, 128);
+            uint64_t db = umma_desc(sb + (kp - 1) * I8_B_BYTES, (I8_TN / 8) * 128, 128);
+            umma_i8(tmem + (uint32_t)((t - 2) * I8_TN), da, db, idesc, fresh ? 0u : 1u);
+            fresh = false;
+          }
+        }
+        umma_commit(empty + slot);                       // smem slot reusable once these MMAs retire
+        if (g + 1 == numStages) umma_commit(accfull);
+      }
+    }
+  } else {
+    // ===================== sign warps (8 warps; the last four double as epilogue warps) =====================
+    // A_k <- s_n * A_k: byte-wise two's-complement negate of the samples with s_n = -1, SWAR on 32-bit words:
+    // -x = (x ^ 0xFF) + 1 per byte, carries confined to the byte by adding the low 7 bits separately.
+    {
+      const int t = threadIdx.x - 64;                       // 0..255
+      const uint32_t* sg0 = a.sigT + (size_t)r0 * a.words;
+      const uint32_t* sg1 = a.sigT + (size_t)r1 * a.words;
+      uint32_t xn = (numStages > 0) ? (sg0[a.stage0] ^ sg1[a.stage0]) : 0u;
+      for (long long g = 0; g < numStages; ++g) {
+        const int slot = (int)(g % I8_SLOTS);
+        const uint32_t x = xn;                              // bit = 1 -> s_n = -1 (32 samples of the stage)
+        if (g + 1 < numStages) xn = sg0[a.stage0 + g + 1] ^ sg1[a.stage0 + g + 1];
+        uint32_t msk[2][4];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t nib = (x >> (ch * 16 + 4 * q)) & 0xFu;
+            msk[ch][q] = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;   // nibble bits -> 0x00/0xFF byte masks
+          }
+        mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
+        if (x != 0u) {
+          unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
+          // A region = I8_S * 4096 B = 1280 units of 16 B; unit u: 16-sample chunk ch = (u >> 7) & 1
+#pragma unroll
+          for (int it = 0; it < I8_S * I8_A_BYTES / 16 / 256; ++it) {
+            const int u = it * 256 + t;
+            const int ch = (u >> 7) & 1;
+            uint4 v = *reinterpret_cast<uint4*>(st + (size_t)u * 16);
+            uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t m = ch ? msk[1][q] : msk[0][q];
+              const uint32_t aa = w[q] ^ m;
+              w[q] = ((aa & 0x7F7F7F7Fu) + (m & 0x01010101u)) ^ (aa & 0x80808080u);
+            }
+            *reinterpret_cast<uint4*>(st + (size_t)u * 16) = v;
+          }
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sgn + slot);
+      }
+    }
+    if (warp >= 6) {
+    // ===================== epilogue warps: TMEM -> fp64, combine re/im, scale, scatter =====================
+    const int ew = warp & 3;                              // TMEM lane quarter this warp may access
+    const int row = ew * 32 + lane;                       // real row of the tile (z = 128*TI + row)
+    const double wl[I8_LEV] = {1.0 / 65025.0, 1.0 / 16581375.0, 1.0 / 4228250625.0, 1.0 / 1078203909375.0,
+                               1.0 / 274941996890625.0};   // 255^-t, t = 2..6
+    const int zrow = TI * I8_TM + row;
+    const int j = zrow >> 1;                              // complex row index; lane parity = re/im part
+    const bool isIm = (zrow & 1) != 0;
+    const double srow = (j < a.M) ? a.scale[zrow] : 0.0;
+    const long long Pc = (long long)a.R * a.M;
+    const bool samePair = (r0 == r1);
+    mbar_wait(accfull, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    for (int cb = 0; cb < I8_TN / 16; ++cb) {
+      double v[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = 0.0;
+#pragma unroll
+      for (int t = 0; t < I8_LEV; ++t) {
+        uint32_t r[16];
+        const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(t * I8_TN + cb * 16);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = fma((double)(int32_t)r[c], wl[t], v[c]);
+      }
+      // C[zrow][zcol] with both column scales; the partner lane (lane ^ 1) holds the other part of the same j
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        const int l = TJ * (I8_TN / 2) + cb * 8 + cc;
+        const bool lok = l < a.M;
+        const double c0 = lok ? v[2 * cc] * srow * a.scale[2 * l] : 0.0;          // column Re Y_l
+        const double c1 = lok ? v[2 * cc + 1] * srow * a.scale[2 * l + 1] : 0.0;  // column Im Y_l
+        const double p0 = __shfl_xor_sync(0xffffffffu, c0, 1);
+        const double p1 = __shfl_xor_sync(0xffffffffu, c1, 1);
+        // even lane (Re row): Re G = C[2j][2l] + C[2j+1][2l+1] = c0 + p1 ; odd lane: Im G = C[2j][2l+1] - C[2j+1][2l] = p1 - c0
+        const double part = isIm ? (p1 - c0) : (c0 + p1);
+        // re-pair so that the even lane owns the complex value
+        const double other = __shfl_xor_sync(0xffffffffu, part, 1);
+        if (!lok || j >= a.M || l > j || isIm) continue;
+        const double gr = a.alpha * part;
+        const double gi = (l == j) ? 0.0 : a.alpha * other;
+        const long long a0 = (long long)r0 * a.M + j, b1 = (long long)r1 * a.M + l;
+        cplx v0 = cmk(gr, gi);
+        if (!a.accumulate) {
+          cplx m0j = a.mu ? a.mu[a0] : cmk(0.0, 0.0);
+          cplx m1l = a.mu ? a.mu[b1] : cmk(0.0, 0.0);
+          v0 = cmk(gr - a.kappa * (m0j.x * m1l.x + m0j.y * m1l.y), gi - a.kappa * (m0j.x * m1l.y - m0j.y * m1l.x));
+        } else {
+          v0 = cadd(v0, a.A[a0 * Pc + b1]);
+        }
+        if (samePair && l == j) v0.y = 0.0;
+        a.A[a0 * Pc + b1] = v0;
+        if (!(samePair && l == j)) a.A[b1 * Pc + a0] = cconj(v0);
+        if (!samePair && l != j) {
+          const long long a1 = (long long)r1 * a.M + j, b0 = (long long)r0 * a.M + l;
+          cplx w0 = cmk(gr, gi);
+          if (!a.accumulate) {
+            cplx m1j = a.mu ? a.mu[a1] : cmk(0.0, 0.0);
+            cplx m0l = a.mu ? a.mu[b0] : cmk(0.0, 0.0);
+            w0 = cmk(gr - a.kappa * (m1j.x * m0l.x + m1j.y * m0l.y), gi - a.kappa * (m1j.x * m0l.y - m1j.y * m0l.x));
+          } else {
+            w0 = cadd(w0, a.A[a1 * Pc + b0]);
+          }
+          a.A[a1 * Pc + b0] = w0;
+          a.A[b0 * Pc + a1] = cconj(w0);
+        }
+      }
+    }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem));
+}
+
+}  // namespace
+
+// Sizes of the scratch buffers the caller provides.
+extern "C" int jvmc_i8_layout(long long B, int M, long long* numChunks, int* numZGroups, long long* digitBytes) {
+  if (B < 0 || M <= 0 || !numChunks || !numZGroups || !digitBytes) return JVMC_ERR_ARG;
+  long long stages = (B + I8_KS - 1) / I8_KS;
+  if (stages < 1) stages = 1;
+  *numChunks = stages * 2;
+  int twoM = 2 * M;
+  int padA = ((twoM + I8_TM - 1) / I8_TM) * I8_TM, padB = ((twoM + I8_TN - 1) / I8_TN) * I8_TN;
+  int pad = padA > padB ? padA : padB;
+  *numZGroups = pad / 8;
+  *digitBytes = (long long)I8_S * (*numChunks) * (*numZGroups) * 128;
+  return JVMC_OK;
+}
+
+// digits must be zero-initialised by the caller (padding rows/columns stay zero); colmax: 2M uint64 zeroed scratch.
+extern "C" int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long long* colmax, double* scale,
+                             signed char* digits, void* stream) {
+  if (!Y || !colmax || !scale || !digits || B <= 0 || M <= 0) return JVMC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long numChunks, digitBytes;
+  int numZGroups;
+  jvmc_i8_layout(B, M, &numChunks, &numZGroups, &digitBytes);
+  cudaMemsetAsync(colmax, 0, sizeof(unsigned long long) * 2 * M, st);
+  dim3 g1((M + 127) / 128, (unsigned)((B + 1023) / 1024));
+  i8_colmax_kernel<<<g1, 128, 0, st>>>((const cplx*)Y, B, M, colmax);
+  JVMC_CHECK_LAUNCH();
+  i8_scale_kernel<<<(2 * M + 255) / 256, 256, 0, st>>>(colmax, 2 * M, scale);
+  JVMC_CHECK_LAUNCH();
+  dim3 g2((2 * M + 255) / 256, (unsigned)((B + 15) / 16));
+  i8_slice_kernel<<<g2, 256, 0, st>>>((const cplx*)Y, B, M, scale, numChunks, numZGroups, (int8_t*)digits);
+  JVMC_CHECK_LAUNCH();
+  return JVMC_OK;
+}
+
+// tiles: device array of (I, J) int pairs listing the tiles that contain an element l <= j.
+extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale, long long B, int M, int R,
+                                  const unsigned int* sigT, const int* tiles, int numTiles, const double* mu,
+                                  double alpha, double kappa, double* A, void* stream) {
+  if (!digits || !scale || !sigT || !tiles || !A || B <= 0 || M <= 0 || R <= 0 || numTiles <= 0) return JVMC_ERR_ARG;
+  I8Args a;
+  long long digitBytes;
+  jvmc_i8_layout(B, M, &a.numChunks, &a.numZGroups, &digitBytes);
+  a.dig = (const int8_t*)digits; a.scale = scale; a.sigT = sigT; a.words = (B + 31) / 32;
+  a.tiles = (const int2*)tiles; a.mu = (const cplx*)mu; a.alpha = alpha; a.kappa = kappa; a.A = (cplx*)A;
+  a.M = M; a.R = R;
+  size_t smem = (size_t)I8_SLOTS * I8_STAGE_BYTES + 32 * sizeof(uint64_t);
+  cudaFuncSetAttribute(gram_s_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  long long pairs = (long long)R * (R + 1) / 2;
+  if (numTiles > 65535 || pairs > 2147483647LL) return JVMC_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)pairs, (unsigned)numTiles);
+  const long long numStages = a.numChunks / 2;
+  // one launch per <= 16384 samples (exact int32 accumulation); later launches add into A
+  for (long long s0 = 0; s0 < numStages; s0 += I8_MAXSTAGES) {
+    a.stage0 = s0;
+    a.stage1 = (s0 + I8_MAXSTAGES < numStages) ? s0 + I8_MAXSTAGES : numStages;
+    a.accumulate = (s0 > 0) ? 1 : 0;
+    gram_s_i8_kernel<<<grid, I8_THREADS, smem, (cudaStream_t)stream>>>(a);
+    JVMC_CHECK_LAUNCH();
+  }
+  return JVMC_OK;
+}

@@ -187,6 +187,41 @@ def rbm_gram_S(Y, sigT, mu, alpha, kappa, out=None, tile=0):
     return out
 
 
+_I8_TILES = {}
+
+
+def _i8_tiles(M, device):
+    """(I, J) tiles of 128 x 96 real columns (64 x 48 complex) that contain an element l <= j."""
+    key = (M, str(device))
+    if key not in _I8_TILES:
+        tl = [(I, J) for I in range((2 * M + 127) // 128) for J in range((2 * M + 95) // 96)
+              if 64 * I < M and 48 * J < M and 48 * J <= 64 * I + 63]
+        _I8_TILES[key] = torch.tensor(tl, dtype=I32, device=device).contiguous()
+    return _I8_TILES[key]
+
+
+def rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out=None):
+    """A (as rbm_gram_S) on the tcgen05 INT8 tensor cores via error-free splitting of Y (fp64-equivalent)."""
+    Y = _c(Y, CPX)
+    B, M = Y.shape
+    R = sigT.shape[0]
+    mu = _c(mu, CPX)
+    lib = _lib.load()
+    nch, nzg, nbytes = ctypes.c_longlong(0), ctypes.c_int(0), ctypes.c_longlong(0)
+    _lib.check(lib.jvmc_i8_layout(B, M, ctypes.byref(nch), ctypes.byref(nzg), ctypes.byref(nbytes)), "jvmc_i8_layout")
+    dev = Y.device
+    digits = torch.zeros(nbytes.value, dtype=torch.int8, device=dev)
+    colmax = torch.empty(2 * M, dtype=torch.int64, device=dev)
+    scale = torch.empty(2 * M, dtype=F64, device=dev)
+    call("jvmc_i8_slice", ptr(Y), B, M, ptr(colmax), ptr(scale), ptr(digits))
+    tiles = _i8_tiles(M, dev)
+    if out is None:
+        out = torch.empty((R * M, R * M), dtype=CPX, device=dev)
+    call("jvmc_rbm_gram_S_i8", ptr(digits), ptr(scale), B, M, R, ptr(sigT), ptr(tiles), int(tiles.shape[0]), ptr(mu),
+         float(alpha), float(kappa), ptr(out))
+    return out
+
+
 def rbm_gram_T(s, tau, p, mu, hasBias, scale=1.0):
     """Centred tangent kernel T = scale * Obar Obar^dagger [B,B] from the Khatri-Rao factors (no dense O)."""
     s = _c(s, I32)
