@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--samples", type=int, default=0, help="override samples per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tdvp", action="store_true")
+    ap.add_argument("--gram", default="i8", choices=["i8", "dmma"], help="Gram backend: tcgen05 INT8 (default) or fp64 DMMA")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = args.workload
@@ -190,6 +191,7 @@ def main():
         run_reference_arm(args, wl)
         return
 
+    os.environ["JVMC_GRAM_BACKEND"] = args.gram
     import torch
     import torch.distributed as dist
     import vmc_jax_b200 as jVMC
@@ -236,7 +238,6 @@ def main():
     ev_g0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + args.warmup + 8)]
     ev_g1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + args.warmup + 8)]
     state = {"i": 0, "launches": 0}
-    K_COUNT = {"sample": 2, "eloc": 1, "moments": 4, "pack": 1, "gram": 1}
 
     def vmc_step():
         s, logPsi, p = smp.sample()
@@ -252,7 +253,6 @@ def main():
         A = G.gram_A()
         ev_g1[i].record()
         state["i"] = i + 1
-        state["launches"] += sum(K_COUNT.values())
         return s, Emean, Evar, F, A
 
     def barrier():
@@ -272,7 +272,8 @@ def main():
     clocks = ClockSampler(dev.index if dev.index is not None else 0)
     clocks.start()
     time.sleep(0.3)
-    state["launches"] = 0
+    from vmc_jax_b200 import _lib as _jl
+    launches0 = _jl.LAUNCHES
     i0 = state["i"]
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -282,7 +283,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = state["launches"]
+    launches = _jl.LAUNCHES - launches0
     gram_ms = float(np.mean([ev_g0[i].elapsed_time(ev_g1[i]) for i in range(i0, state["i"])]))
     energy = complex(out[1].item())
     del out
@@ -356,20 +357,47 @@ def main():
     except Exception as ex:  # pragma: no cover
         peak_tf, peak_src = 37.0, "fallback: DMMA issue-rate probe tools/fp64_probe.cu (37.05 TF/s); live DGEMM failed: %r" % (ex,)
     achieved = algo_flop / (gram_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gram_s_kernel (fp64 DMMA m8n8k4)", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
-                "launch_ms": gram_ms,
-                "algorithmic_flop_per_launch": algo_flop,
-                "executed_tensor_flop_per_launch": exec_flop,
-                "executed_tflops": exec_flop / (gram_ms * 1e-3) / 1e12,
-                "note": "algorithmic = SURVEY 8d figure 4*N_s*P_c^2 (Hermitian half); the kernel additionally uses the "
-                        "site-pair symmetry of the Khatri-Rao Gram and issues about half of that on the tensor pipe"}
+    if args.gram == "dmma":
+        roofline = {"bound": "tensor", "kernel": "gram_s_kernel (fp64 DMMA m8n8k4)", "achieved": achieved, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                    "launch_ms": gram_ms,
+                    "algorithmic_flop_per_launch": algo_flop,
+                    "executed_tensor_flop_per_launch": exec_flop,
+                    "executed_tflops": exec_flop / (gram_ms * 1e-3) / 1e12,
+                    "note": "algorithmic = SURVEY 8d figure 4*N_s*P_c^2 (Hermitian half); the kernel additionally uses the "
+                            "site-pair symmetry of the Khatri-Rao Gram and issues about half of that on the tensor pipe"}
+    else:
+        # INT8 tensor-core path: S is computed to fp64-equivalent accuracy by error-free splitting into 5 int8 digits,
+        # 15 digit-pair products (levels k+k' <= 6) on tcgen05 kind::i8 with exact int32 accumulation.
+        ntile = int(K._i8_tiles(M, dev).shape[0])
+        stages = (nLocal + 31) // 32
+        launches_i8 = (stages + 511) // 512
+        exec_ops = 2.0 * (R * (R + 1) / 2) * ntile * stages * (15 * 80) * 128 * 32
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            with open(peaks_path) as fh:
+                bf16 = float(json.load(fh)["bf16_tflops"])
+            i8_src = "2 x bf16_tflops of MEASURED_PEAKS.json (B200 dense INT8 rate = 2 x dense bf16 rate)"
+        else:
+            bf16, i8_src = 1590.0, "2 x 1.59 PFLOP/s bf16 fallback of B200_PROFILING.md"
+        i8_peak = 2.0 * bf16
+        ach = exec_ops / (gram_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "gram_s_i8_kernel (tcgen05.mma kind::i8, UTCIMMA) + i8 slicing",
+                    "achieved": ach, "peak": i8_peak, "unit": "TOP/s", "frac": ach / i8_peak, "traffic": None,
+                    "peak_source": i8_src, "launch_ms": gram_ms, "launches_per_step": launches_i8,
+                    "executed_int8_op_per_step": exec_ops,
+                    "algorithmic_flop_per_step": algo_flop,
+                    "fp64_equivalent": {"achieved_tflops": achieved, "dgemm_peak_tflops": peak_tf,
+                                        "ratio": achieved / peak_tf, "dgemm_peak_source": peak_src},
+                    "note": "fp64-equivalent Gram (4*N_s*P_c^2 algorithmic flop, SURVEY 8d) executed as 15 int8 digit-pair "
+                            "products per sample pair; at this tiling the kernel is bound by L2->SM operand traffic "
+                            "(33 KB per 32-sample stage and CTA), see DESIGN.md 4.1"}
     tp = os.path.join(ROOT, "profiles", "gram_traffic.json")
     if os.path.exists(tp):
         try:
             with open(tp) as fh:
                 tj = json.load(fh)
-            if tj.get("workload") == wl:
+            if tj.get("workload") == wl and tj.get("backend", "dmma") == args.gram:
                 roofline["traffic"] = tj.get("dram_bytes_per_launch")
                 roofline["traffic_source"] = tj.get("source")
         except Exception:

@@ -162,7 +162,7 @@ def check_grad(N=6, M=5, B=17, bias=True, seed=9):
     assert relerr(gr, orbm.gradients_real(s, Wr, br)) < RTOL
 
 
-def check_moments_gram(N=7, M=24, B=211, bias=True, seed=11, uniform=True, tile=0):
+def check_moments_gram(N=7, M=24, B=211, bias=True, seed=11, uniform=True, tile=0, backend="dmma"):
     """mu, F-kernel and the centred Gram A = <conj(O) O>_c vs the oracle's SampledObs.covar."""
     W, b = orbm.init_o1(N, M, bias, seed)
     s = rand_configs(B, N, seed + 1)
@@ -183,11 +183,12 @@ def check_moments_gram(N=7, M=24, B=211, bias=True, seed=11, uniform=True, tile=
     Fk = K.rbm_moments(ds, tau, dev(p * (E - Ebar)), bias, 1)
     assert relerr(host(Fk).ravel(), F_ref) < RTOL
     sigT = K.pack_sigma(ds, bias)
+    gram = (lambda Y, sg, m, al, ka: K.rbm_gram_S_i8(Y, sg, m, al, ka)) if backend == "i8" else \
+        (lambda Y, sg, m, al, ka: K.rbm_gram_S(Y, sg, m, al, ka, tile=tile))
     if uniform:
-        A = K.rbm_gram_S(tau, sigT, mu, p[0], 1.0, tile=tile)
+        A = gram(tau, sigT, mu, p[0], 1.0)
     else:
-        Y = tau * torch.sqrt(dp)[:, None]
-        A = K.rbm_gram_S(Y, sigT, mu, 1.0, 1.0, tile=tile)
+        A = gram(tau * torch.sqrt(dp)[:, None], sigT, mu, 1.0, 1.0)
     A = host(A)
     # scale: the uncentred second moment (A is a difference of two such terms)
     scale = max(np.max(np.abs(A_ref)), np.max(np.abs(obsO.mean())) ** 2)

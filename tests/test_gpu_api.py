@@ -141,7 +141,7 @@ def test_snr_matches_oracle():
     otd = osolve.TDVP(snrTol=1, pinvTol=1e-8, rhsPrefactor=1.j, makeReal='imag')
     oE, oG = ostats.SampledObs(En, pn), ostats.SampledObs(orbm.gradients_holomorphic(sn, W, b), pn)
     upd_ref, res_ref, cut_ref = otd.solve(oE, oG, mpi.globNumSamples)
-    assert np.allclose(host(td.ev), otd.ev, atol=1e-12)
+    assert np.allclose(host(td.ev), otd.ev, atol=1e-10 * np.abs(otd.ev).max())     # 1e-10 of the scale of S
     # rhoVar summed over each (numerically) degenerate eigenspace is basis independent
     assert np.isclose(host(td.rhoVar).sum(), otd.rhoVar.sum(), rtol=1e-8)
     assert np.isclose(float(td.ElocVar), otd.ElocVar, rtol=1e-10)
@@ -352,14 +352,15 @@ def test_rbm_gradient_obs_equals_generic(bias):
     E = torch.randn(1, 40, dtype=torch.complex128, device="cuda")
     gen, fac, eo = SampledObs(psi.gradients(s), p), RBMGradientObs(psi, s, p), SampledObs(E, p)
     assert torch.allclose(fac.mean(), gen.mean(), rtol=1e-12, atol=1e-15)
-    assert torch.allclose(fac.covar(), gen.covar(), rtol=1e-10, atol=1e-14)
+    S_ref = gen.covar()
+    assert float((fac.covar() - S_ref).abs().max()) < 1e-10 * float(S_ref.abs().max())   # norm-wise 1e-10 (north_star)
     assert torch.allclose(fac.covar(eo), gen.covar(eo), rtol=1e-10, atol=1e-14)
     assert torch.allclose(eo.covar(fac), eo.covar(gen), rtol=1e-10, atol=1e-14)
     assert torch.allclose(fac.var(), gen.var().reshape(-1), rtol=1e-10, atol=1e-14)
     assert torch.allclose(fac._data, gen._data, rtol=1e-12, atol=1e-15)
     assert torch.allclose(fac.tangent_kernel(), gen.tangent_kernel(), rtol=1e-10, atol=1e-14)
     sub_f, sub_g = fac.subset(start=1, step=2), gen.subset(start=1, step=2)
-    assert torch.allclose(sub_f.covar(), sub_g.covar(), rtol=1e-9, atol=1e-13)
+    assert float((sub_f.covar() - sub_g.covar()).abs().max()) < 1e-9 * float(sub_g.covar().abs().max())
     x = torch.randn(40, dtype=torch.complex128, device="cuda")
     ref = -gen._data.reshape(40, -1).conj().T @ x
     assert torch.allclose(fac.minsr_contract(x), ref, rtol=1e-10, atol=1e-13)

@@ -105,9 +105,19 @@ def check(rc, what=""):
         raise RuntimeError("libjvmc_b200 %s failed: %s (code %d)" % (what, msg, rc))
 
 
+# kernels launched per entry point (for the gpu_launches figure of bench.py)
+_KERNELS_PER_CALL = {"jvmc_bfo_matels": 2, "jvmc_rbm_moments": 2, "jvmc_i8_slice": 3, "jvmc_eigh": 0}
+LAUNCHES = 0
+
+
 def call(name, *args):
     """Invoke an int-returning entry point on the current stream (appended as last argument)."""
+    global LAUNCHES
     require_cuda()
     lib = load()
     rc = getattr(lib, name)(*args, stream())
     check(rc, name)
+    if name == "jvmc_rbm_gram_S_i8":
+        LAUNCHES += max(1, ((int(args[2]) + 31) // 32 + 511) // 512)    # one launch per 16384 samples
+    else:
+        LAUNCHES += _KERNELS_PER_CALL.get(name, 1)

@@ -8,7 +8,8 @@
 // 1. jvmc_i8_slice: every real column z of Z = [Re Y_j, Im Y_j] (interleaved, 2M columns) gets a power-of-two scale
 //    c_z > 2 max_n |Z_nz| and each entry is split into 5 balanced base-255 digits, Z_nz = c_z sum_k d_k 255^-k,
 //    d_k in [-127, 127] (int8, symmetric so that negation is exact).  Digits are stored in the K-major SWIZZLE_NONE
-//    UMMA canonical layout [digit][n/16][z/8][z%8][n%16], so that a (tile, 16-sample chunk) is one contiguous block.
+//    UMMA canonical layout [n/32][digit][z/8][(n/16)%2][z%8][n%16], so that a (tile, 32-sample stage, digit) is one
+//    contiguous block (one TMA bulk copy each).
 // 2. gram_s_i8_kernel: CTA = (site pair r<=r', tile I,J): rows = 128 real columns (64 complex j), cols = 96 real
 //    columns (48 complex l).  Per 32-sample stage the producer warp bulk-copies (TMA engine) 5 A-digit and 5 B-digit
 //    tiles into an mbarrier-guarded smem ring; four "sign" warps apply s_n to the A tiles by byte-wise negation;
@@ -25,14 +26,15 @@ namespace {
 
 constexpr int I8_S = 5;                 // digits
 constexpr int I8_LEV = 5;               // levels t = 2..6
-constexpr int I8_TM = 128, I8_TN = 96;  // tile in real columns
+constexpr int I8_TM = 128, I8_TN = 80;  // tile in real columns (5 levels x 80 + 2 x 40 A-operand columns = 480 of 512 TMEM columns)
 constexpr int I8_KS = 32;               // samples per stage (one MMA K)
 constexpr int I8_SLOTS = 6;
 constexpr int I8_A_BYTES = I8_TM * I8_KS;   // per digit
 constexpr int I8_B_BYTES = I8_TN * I8_KS;
 constexpr int I8_STAGE_BYTES = I8_S * (I8_A_BYTES + I8_B_BYTES);
 constexpr int I8_MAXSTAGES = 512;       // stages per launch: 512*32*5*127^2 < 2^31 (int32 head-room in TMEM)
-constexpr int I8_THREADS = 320;         // warp 0 producer, 1 MMA, 2-9 sign (6-9 also epilogue)
+constexpr int I8_THREADS = 192;         // warp 0 producer, 1 MMA issuer, 2-5 sign + epilogue
+constexpr int I8_ACOL = I8_LEV * I8_TN;  // first TMEM column of the double-buffered A operand (2 x 5 digits x 8 columns)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -66,13 +68,14 @@ __device__ __forceinline__ uint64_t umma_desc(unsigned saddr, unsigned lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
-__device__ __forceinline__ void umma_i8(uint32_t tacc, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// A operand from TMEM (lane = row, 8 columns = 32 K-bytes), B from shared memory
+__device__ __forceinline__ void umma_i8_ts(uint32_t tacc, uint32_t ta, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
-      "}\n" ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tacc), "r"(ta), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -112,7 +115,7 @@ __global__ void i8_scale_kernel(const unsigned long long* __restrict__ colmax, i
   scale[z] = ldexp(1.0, e);
 }
 
-// digits[k][chunk][zgroup][z%8][n%16]; one thread per (16-sample chunk, real column z): 16 strided loads, 5x16B stores
+// one thread per (16-sample chunk, real column z): 16 strided loads, 5 x 16 B stores
 __global__ void __launch_bounds__(256)
 i8_slice_kernel(const cplx* __restrict__ Y, long long B, int M, const double* __restrict__ scale, long long numChunks,
                 int numZGroups, int8_t* __restrict__ dig) {
@@ -133,10 +136,11 @@ i8_slice_kernel(const cplx* __restrict__ Y, long long B, int M, const double* __
       X = qd;
     }
   }
-  const size_t perDigit = (size_t)numChunks * numZGroups * 128;
-  const size_t off = ((size_t)ch * numZGroups + (z >> 3)) * 128 + (size_t)(z & 7) * 16;
+  // [stage][digit][zgroup][chunk of the stage][z%8][n%16]: a (tile, stage, digit) is one contiguous block
+  const size_t off = ((size_t)(z >> 3) * 2 + (size_t)(ch & 1)) * 128 + (size_t)(z & 7) * 16;
 #pragma unroll
-  for (int k = 0; k < I8_S; ++k) *reinterpret_cast<int4*>(dig + k * perDigit + off) = *reinterpret_cast<const int4*>(d[k]);
+  for (int k = 0; k < I8_S; ++k)
+    *reinterpret_cast<int4*>(dig + ((size_t)(ch >> 1) * I8_S + k) * numZGroups * 256 + off) = *reinterpret_cast<const int4*>(d[k]);
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
@@ -160,10 +164,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* ring = smem_raw;                                                     // [slot][A digits | B digits]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)I8_SLOTS * I8_STAGE_BYTES);
-  uint64_t* full = bars;
-  uint64_t* sgn = bars + I8_SLOTS;
-  uint64_t* empty = bars + 2 * I8_SLOTS;
-  uint64_t* accfull = bars + 3 * I8_SLOTS;
+  uint64_t* full = bars;                    // TMA bytes landed in the slot
+  uint64_t* empty = bars + I8_SLOTS;        // MMAs reading the slot retired
+  uint64_t* aready = bars + 2 * I8_SLOTS;   // [2] signed A digits of a stage are in TMEM buffer b
+  uint64_t* afree = aready + 2;             // [2] MMAs reading TMEM buffer b retired
+  uint64_t* accfull = afree + 2;
   uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(accfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,10 +177,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   const int2 tile = a.tiles[blockIdx.y];
   const int TI = tile.x, TJ = tile.y;
   const long long numStages = a.stage1 - a.stage0;
-  const size_t perDigit = (size_t)a.numChunks * a.numZGroups * 128;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < I8_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(sgn + s, 8); mbar_init(empty + s, 1); }
+    for (int s = 0; s < I8_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(aready + b, 4); mbar_init(afree + b, 1); }
     mbar_init(accfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -189,100 +194,107 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   const uint32_t tmem = *tmem_base_p;
 
   if (warp == 0) {
-    // ===================== producer: 20 bulk copies per stage =====================
+    // ===================== producer: one bulk copy per (operand, digit) and stage =====================
     for (long long g = 0; g < numStages; ++g) {
       const int slot = (int)(g % I8_SLOTS);
       if (g >= I8_SLOTS) mbar_wait(empty + slot, (unsigned)((g / I8_SLOTS - 1) & 1));
       unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
       if (lane == 0) mbar_expect_tx(full + slot, (unsigned)I8_STAGE_BYTES);
       __syncwarp();
-      if (lane < 2 * I8_S * 2) {
-        const int k = lane / 4, rem = lane % 4, which = rem >> 1, ch = rem & 1;
-        const long long gch = (a.stage0 + g) * 2 + ch;
-        const int8_t* src = a.dig + k * perDigit +
-                            ((size_t)gch * a.numZGroups + (which ? (size_t)TJ * (I8_TN / 8) : (size_t)TI * (I8_TM / 8))) * 128;
-        unsigned char* dst = which ? (st + I8_S * I8_A_BYTES + k * I8_B_BYTES + ch * (I8_TN / 8) * 128)
-                                   : (st + k * I8_A_BYTES + ch * (I8_TM / 8) * 128);
-        bulk_g2s(dst, src, which ? (I8_TN / 8) * 128 : (I8_TM / 8) * 128, full + slot);
+      if (lane < 2 * I8_S) {
+        const int k = lane >> 1, which = lane & 1;
+        const size_t base = ((size_t)(a.stage0 + g) * I8_S + k) * a.numZGroups;
+        if (which == 0) bulk_g2s(st + k * I8_A_BYTES, a.dig + (base + (size_t)TI * (I8_TM / 8)) * 256, I8_A_BYTES, full + slot);
+        else bulk_g2s(st + I8_S * I8_A_BYTES + k * I8_B_BYTES, a.dig + (base + (size_t)TJ * (I8_TN / 8)) * 256, I8_B_BYTES,
+                      full + slot);
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
+    // ===================== MMA issuer (one thread): 15 UTCIMMA per stage, A from TMEM, B from smem =====================
     if (lane == 0) {
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_TN >> 3) << 17) | ((uint32_t)(I8_TM >> 4) << 24);
+      // Digit tiles of B are contiguous in smem ([digit][rowgroup][chunk]), and the level accumulators are adjacent
+      // TMEM column blocks, so ONE instruction with N = 80 n multiplies A_k with B_k'..B_k'+n-1 and accumulates into
+      // levels k+k' .. k+k'+n-1: 7 instructions per stage instead of 15 (UTCIMMA issue is the scarce resource).
+      const uint32_t ibase = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_TM >> 4) << 24);
+      const uint32_t idesc1 = ibase | ((uint32_t)((1 * I8_TN) >> 3) << 17);
+      const uint32_t idesc2 = ibase | ((uint32_t)((2 * I8_TN) >> 3) << 17);
+      const uint32_t idesc3 = ibase | ((uint32_t)((3 * I8_TN) >> 3) << 17);
       for (long long g = 0; g < numStages; ++g) {
         const int slot = (int)(g % I8_SLOTS);
-        const bool first = (g == 0);
-        mbar_wait(sgn + slot, (unsigned)((g / I8_SLOTS) & 1));
+        const int b = (int)(g & 1);
+        const uint32_t acc = (g == 0) ? 0u : 1u;
+        mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
+        mbar_wait(aready + b, (unsigned)((g >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const unsigned sa = smem_u32(ring + (size_t)slot * I8_STAGE_BYTES);
-        const unsigned sb = sa + I8_S * I8_A_BYTES;
-#pragma unroll
-        for (int t = 2; t <= I8_LEV + 1; ++t) {
-          bool fresh = first;
-#pragma unroll
-          for (int k = 1; k <= I8_S; ++k) {
-            const int kp = t - k;
-            if (kp < 1 || kp > I8_S) continue;
-            uint64_t da = umma_desc(sa + (k - 1) * I8_A_BYTES, (I8_TM / 8) * 128, 128);
-            uint64_t db = umma_desc(sb + (kp - 1) * I8_B_BYTES, (I8_TN / 8) * 128, 128);
-            umma_i8(tmem + (uint32_t)((t - 2) * I8_TN), da, db, idesc, fresh ? 0u : 1u);
-            fresh = false;
-          }
-        }
+        const unsigned sb = smem_u32(ring + (size_t)slot * I8_STAGE_BYTES) + I8_S * I8_A_BYTES;
+        const uint32_t ta = tmem + (uint32_t)(I8_ACOL + b * I8_S * 8);
+        // (digit k, first k', count n): level column = (k + k' - 2) * 80
+        auto mma = [&](int k, int kp, int n, uint32_t idesc, uint32_t accumulate) {
+          uint64_t db = umma_desc(sb + (kp - 1) * I8_B_BYTES, 128, 256);   // LBO: next 16-sample chunk, SBO: next 8 rows
+          umma_i8_ts(tmem + (uint32_t)((k + kp - 2) * I8_TN), ta + (uint32_t)((k - 1) * 8), db, idesc, accumulate);
+        };
+        mma(1, 1, 3, idesc3, acc);      // levels 2,3,4 (first writer)
+        mma(1, 4, 2, idesc2, acc);      // levels 5,6   (first writer)
+        mma(2, 1, 3, idesc3, 1u);       // levels 3,4,5
+        mma(2, 4, 1, idesc1, 1u);       // level 6
+        mma(3, 1, 3, idesc3, 1u);       // levels 4,5,6
+        mma(4, 1, 2, idesc2, 1u);       // levels 5,6
+        mma(5, 1, 1, idesc1, 1u);       // level 6
         umma_commit(empty + slot);                       // smem slot reusable once these MMAs retire
+        umma_commit(afree + b);                          // ... and so is the TMEM A buffer
         if (g + 1 == numStages) umma_commit(accfull);
       }
     }
   } else {
-    // ===================== sign warps (8 warps; the last four double as epilogue warps) =====================
-    // A_k <- s_n * A_k: byte-wise two's-complement negate of the samples with s_n = -1, SWAR on 32-bit words:
-    // -x = (x ^ 0xFF) + 1 per byte, carries confined to the byte by adding the low 7 bits separately.
+    // ===================== sign warps: A_k <- s_n * A_k, smem -> registers -> TMEM =====================
+    // thread = tile row; per digit the row's 32 sample bytes are two 16-byte units of the canonical layout.
+    // Byte-wise two's-complement negate where s_n = -1, SWAR on 32-bit words: -x = (x ^ 0xFF) + 1 per byte.
+    const int ew = warp & 3;                              // TMEM lane quarter this warp may access
+    const int row = ew * 32 + lane;                       // real row of the tile (z = 128*TI + row)
     {
-      const int t = threadIdx.x - 64;                       // 0..255
       const uint32_t* sg0 = a.sigT + (size_t)r0 * a.words;
       const uint32_t* sg1 = a.sigT + (size_t)r1 * a.words;
       uint32_t xn = (numStages > 0) ? (sg0[a.stage0] ^ sg1[a.stage0]) : 0u;
+      const size_t rowOff = (size_t)(row >> 3) * 256 + (size_t)(row & 7) * 16;
       for (long long g = 0; g < numStages; ++g) {
         const int slot = (int)(g % I8_SLOTS);
+        const int b = (int)(g & 1);
         const uint32_t x = xn;                              // bit = 1 -> s_n = -1 (32 samples of the stage)
         if (g + 1 < numStages) xn = sg0[a.stage0 + g + 1] ^ sg1[a.stage0 + g + 1];
-        uint32_t msk[2][4];
+        uint32_t msk[8];
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t nib = (x >> (ch * 16 + 4 * q)) & 0xFu;
-            msk[ch][q] = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;   // nibble bits -> 0x00/0xFF byte masks
-          }
-        mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
-        if (x != 0u) {
-          unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
-          // A region = I8_S * 4096 B = 1280 units of 16 B; unit u: 16-sample chunk ch = (u >> 7) & 1
-#pragma unroll
-          for (int it = 0; it < I8_S * I8_A_BYTES / 16 / 256; ++it) {
-            const int u = it * 256 + t;
-            const int ch = (u >> 7) & 1;
-            uint4 v = *reinterpret_cast<uint4*>(st + (size_t)u * 16);
-            uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t m = ch ? msk[1][q] : msk[0][q];
-              const uint32_t aa = w[q] ^ m;
-              w[q] = ((aa & 0x7F7F7F7Fu) + (m & 0x01010101u)) ^ (aa & 0x80808080u);
-            }
-            *reinterpret_cast<uint4*>(st + (size_t)u * 16) = v;
-          }
-          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t nib = (x >> (4 * q)) & 0xFu;
+          msk[q] = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;     // nibble bits -> 0x00/0xFF byte masks
         }
+        if (g >= 2) mbar_wait(afree + b, (unsigned)(((g >> 1) - 1) & 1));
+        mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < I8_S; ++k) {
+          uint32_t w[8];
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            const uint4 v = *reinterpret_cast<const uint4*>(st + k * I8_A_BYTES + ch * 128 + rowOff);
+            w[ch * 4 + 0] = v.x; w[ch * 4 + 1] = v.y; w[ch * 4 + 2] = v.z; w[ch * 4 + 3] = v.w;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t aa = w[q] ^ msk[q];
+            w[q] = ((aa & 0x7F7F7F7Fu) + (msk[q] & 0x01010101u)) ^ (aa & 0x80808080u);
+          }
+          const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(I8_ACOL + b * I8_S * 8 + k * 8);
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr),
+                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(sgn + slot);
+        if (lane == 0) mbar_arrive(aready + b);
       }
     }
-    if (warp >= 6) {
-    // ===================== epilogue warps: TMEM -> fp64, combine re/im, scale, scatter =====================
-    const int ew = warp & 3;                              // TMEM lane quarter this warp may access
-    const int row = ew * 32 + lane;                       // real row of the tile (z = 128*TI + row)
+    // ===================== epilogue (same warps): TMEM -> fp64, combine re/im, scale, scatter =====================
     const double wl[I8_LEV] = {1.0 / 65025.0, 1.0 / 16581375.0, 1.0 / 4228250625.0, 1.0 / 1078203909375.0,
                                1.0 / 274941996890625.0};   // 255^-t, t = 2..6
     const int zrow = TI * I8_TM + row;
@@ -319,10 +331,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         const double c1 = lok ? v[2 * cc + 1] * srow * a.scale[2 * l + 1] : 0.0;  // column Im Y_l
         const double p0 = __shfl_xor_sync(0xffffffffu, c0, 1);
         const double p1 = __shfl_xor_sync(0xffffffffu, c1, 1);
-        // even lane (Re row): Re G = C[2j][2l] + C[2j+1][2l+1] = c0 + p1 ; odd lane: Im G = C[2j][2l+1] - C[2j+1][2l] = p1 - c0
+        // even lane (Re row): Re G = C[2j][2l] + C[2j+1][2l+1] = c0 + p1 ; odd lane (Im row): Im G = C[2j][2l+1] - C[2j+1][2l] = p1 - c0
+        (void)p0;
         const double part = isIm ? (p1 - c0) : (c0 + p1);
-        // re-pair so that the even lane owns the complex value
-        const double other = __shfl_xor_sync(0xffffffffu, part, 1);
+        const double other = __shfl_xor_sync(0xffffffffu, part, 1);   // even lane receives Im G
         if (!lok || j >= a.M || l > j || isIm) continue;
         const double gr = a.alpha * part;
         const double gi = (l == j) ? 0.0 : a.alpha * other;
@@ -352,7 +364,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
           a.A[b0 * Pc + a1] = cconj(w0);
         }
       }
-    }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");

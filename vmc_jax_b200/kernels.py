@@ -191,11 +191,11 @@ _I8_TILES = {}
 
 
 def _i8_tiles(M, device):
-    """(I, J) tiles of 128 x 96 real columns (64 x 48 complex) that contain an element l <= j."""
+    """(I, J) tiles of 128 x 80 real columns (64 x 40 complex) that contain an element l <= j."""
     key = (M, str(device))
     if key not in _I8_TILES:
-        tl = [(I, J) for I in range((2 * M + 127) // 128) for J in range((2 * M + 95) // 96)
-              if 64 * I < M and 48 * J < M and 48 * J <= 64 * I + 63]
+        tl = [(I, J) for I in range((2 * M + 127) // 128) for J in range((2 * M + 79) // 80)
+              if 64 * I < M and 40 * J < M and 40 * J <= 64 * I + 63]
         _I8_TILES[key] = torch.tensor(tl, dtype=I32, device=device).contiguous()
     return _I8_TILES[key]
 

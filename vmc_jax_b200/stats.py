@@ -6,12 +6,17 @@ plain device tensor operations followed by the in-stream all-reduce of mpi_wrapp
 stores only (configs, tanh(theta), weights) -- the Khatri-Rao factors of O -- and evaluates mean, force,
 S (Gram), SNR projections and the MinSR contraction with the kernels of csrc/stats.cu and csrc/gram.cu
 without ever materialising O [N_s x P]."""
+import os
+
 import numpy as np
 import torch
 
 from . import global_defs
 from . import kernels as K
 from . import mpi_wrapper as mpi
+
+
+GRAM_BACKEND = os.environ.get("JVMC_GRAM_BACKEND", "i8")
 
 
 def _w_like(w, data):
@@ -229,10 +234,13 @@ class RBMGradientObs(SampledObs):
                 self._sigT = K.pack_sigma(self._s, self.hasBias)
             p = self._p
             kappa = 1.0 / mpi.commSize
+            # backend: "i8" = tcgen05 INT8 tensor cores with error-free splitting (fp64-equivalent, default),
+            #          "dmma" = fp64 DMMA
+            gram = K.rbm_gram_S_i8 if GRAM_BACKEND == "i8" else K.rbm_gram_S
             if self._uniform is not None:
-                A = K.rbm_gram_S(self._tau, self._sigT, mu, float(self._uniform), kappa)
+                A = gram(self._tau, self._sigT, mu, float(self._uniform), kappa)
             else:
-                A = K.rbm_gram_S(self._tau * torch.sqrt(p)[:, None], self._sigT, mu, 1.0, kappa)
+                A = gram(self._tau * torch.sqrt(p)[:, None], self._sigT, mu, 1.0, kappa)
             self._A = mpi._all_reduce_sum(A)
         return self._A
 
