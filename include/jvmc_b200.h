@@ -105,6 +105,7 @@ int jvmc_rbm_gram_S(const double* Y, long long B, int M, int R, const unsigned i
  * the UMMA canonical layout (digits must be zero-initialised); jvmc_rbm_gram_S_i8 -> A.  tiles: device (I,J) int pairs
  * (128 x 96 real-column tiles containing an element l <= j). */
 int jvmc_i8_layout(long long B, int M, long long* numChunks, int* numZGroups, long long* digitBytes);
+int jvmc_i8_set_debug(int flags);   /* development ablations of the int8 Gram pipeline (timing only; results invalid) */
 int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long long* colmax, double* scale,
                   signed char* digits, void* stream);
 int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale, long long B, int M, int R,

@@ -20,7 +20,10 @@ ap.add_argument("--check", action="store_true")
 ap.add_argument("--dbg", type=int, default=0)
 ap.add_argument("--i8", action="store_true")
 a = ap.parse_args()
-TILE_ARG = a.tile + 1000 * a.dbg
+TILE_ARG = a.tile + 1000 * (0 if a.i8 else a.dbg)
+from vmc_jax_b200 import _lib  # noqa: E402
+if a.i8:
+    _lib.load().jvmc_i8_set_debug(a.dbg)
 dev = "cuda:0"
 rng = np.random.default_rng(0)
 s = torch.as_tensor(rng.integers(0, 2, (a.B, a.N)).astype(np.int32)).to(dev)

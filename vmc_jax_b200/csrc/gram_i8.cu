@@ -33,7 +33,7 @@ constexpr int I8_A_BYTES = I8_TM * I8_KS;   // per digit
 constexpr int I8_B_BYTES = I8_TN * I8_KS;
 constexpr int I8_STAGE_BYTES = I8_S * (I8_A_BYTES + I8_B_BYTES);
 constexpr int I8_MAXSTAGES = 512;       // stages per launch: 512*32*5*127^2 < 2^31 (int32 head-room in TMEM)
-constexpr int I8_THREADS = 192;         // warp 0 producer, 1 MMA issuer, 2-5 sign + epilogue
+constexpr int I8_THREADS = 320;         // warp 0 producer, 1 MMA issuer, 2-9 sign (2-5 also epilogue)
 constexpr int I8_ACOL = I8_LEV * I8_TN;  // first TMEM column of the double-buffered A operand (2 x 5 digits x 8 columns)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -158,6 +158,7 @@ struct I8Args {
   int M, R;
   long long stage0, stage1;   // this launch covers sample stages [stage0, stage1), at most I8_MAXSTAGES
   int accumulate;             // 0: A = alpha G - kappa mu^H mu ; 1: A += alpha G
+  int dbg;                    // development ablations: 1 = MMA issue only, 2 = TMA + MMA (no sign pass)
 };
 
 __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < I8_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(aready + b, 4); mbar_init(afree + b, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(aready + b, 8); mbar_init(afree + b, 1); }
     mbar_init(accfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
 
   if (warp == 0) {
     // ===================== producer: one bulk copy per (operand, digit) and stage =====================
-    for (long long g = 0; g < numStages; ++g) {
+    for (long long g = 0; g < ((a.dbg & 1) ? 0 : numStages); ++g) {
       const int slot = (int)(g % I8_SLOTS);
       if (g >= I8_SLOTS) mbar_wait(empty + slot, (unsigned)((g / I8_SLOTS - 1) & 1));
       unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
@@ -223,8 +224,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         const int slot = (int)(g % I8_SLOTS);
         const int b = (int)(g & 1);
         const uint32_t acc = (g == 0) ? 0u : 1u;
-        mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
-        mbar_wait(aready + b, (unsigned)((g >> 1) & 1));
+        if (!(a.dbg & 1)) mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
+        if (!(a.dbg & 3)) mbar_wait(aready + b, (unsigned)((g >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const unsigned sb = smem_u32(ring + (size_t)slot * I8_STAGE_BYTES) + I8_S * I8_A_BYTES;
         const uint32_t ta = tmem + (uint32_t)(I8_ACOL + b * I8_S * 8);
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       const uint32_t* sg1 = a.sigT + (size_t)r1 * a.words;
       uint32_t xn = (numStages > 0) ? (sg0[a.stage0] ^ sg1[a.stage0]) : 0u;
       const size_t rowOff = (size_t)(row >> 3) * 256 + (size_t)(row & 7) * 16;
-      for (long long g = 0; g < numStages; ++g) {
+      for (long long g = 0; g < ((a.dbg & 3) ? 0 : numStages); ++g) {
         const int slot = (int)(g % I8_SLOTS);
         const int b = (int)(g & 1);
         const uint32_t x = xn;                              // bit = 1 -> s_n = -1 (32 samples of the stage)
@@ -271,8 +272,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
+        // two warps share a TMEM lane quarter: warps 2-5 take digits 0-2, warps 6-9 digits 3-4
+        const int kbeg = (warp < 6) ? 0 : 3, kend = (warp < 6) ? 3 : I8_S;
 #pragma unroll
         for (int k = 0; k < I8_S; ++k) {
+          if (k < kbeg || k >= kend) continue;
           uint32_t w[8];
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
@@ -294,7 +298,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         if (lane == 0) mbar_arrive(aready + b);
       }
     }
-    // ===================== epilogue (same warps): TMEM -> fp64, combine re/im, scale, scatter =====================
+    if (warp < 6) {
+    // ===================== epilogue (warps 2-5): TMEM -> fp64, combine re/im, scale, scatter =====================
     const double wl[I8_LEV] = {1.0 / 65025.0, 1.0 / 16581375.0, 1.0 / 4228250625.0, 1.0 / 1078203909375.0,
                                1.0 / 274941996890625.0};   // 255^-t, t = 2..6
     const int zrow = TI * I8_TM + row;
@@ -365,6 +370,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         }
       }
     }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
@@ -372,6 +378,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
 }
 
 }  // namespace
+
+static int g_i8_dbg = 0;
+extern "C" int jvmc_i8_set_debug(int flags) { g_i8_dbg = flags; return JVMC_OK; }   // development ablations (timing only)
 
 // Sizes of the scratch buffers the caller provides.
 extern "C" int jvmc_i8_layout(long long B, int M, long long* numChunks, int* numZGroups, long long* digitBytes) {
@@ -429,6 +438,7 @@ extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale
     a.stage0 = s0;
     a.stage1 = (s0 + I8_MAXSTAGES < numStages) ? s0 + I8_MAXSTAGES : numStages;
     a.accumulate = (s0 > 0) ? 1 : 0;
+    a.dbg = g_i8_dbg;
     gram_s_i8_kernel<<<grid, I8_THREADS, smem, (cudaStream_t)stream>>>(a);
     JVMC_CHECK_LAUNCH();
   }
