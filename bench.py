@@ -192,6 +192,8 @@ def main():
         return
 
     os.environ["JVMC_GRAM_BACKEND"] = args.gram
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line
     import torch
     import torch.distributed as dist
     import vmc_jax_b200 as jVMC
