@@ -151,7 +151,7 @@ struct I8Args {
   const double* scale;     // [2M]
   const uint32_t* sigT;    // [R][words]
   long long words;
-  const int2* tiles;       // (I, J) list
+  const int4* tiles;       // (first row group, column block J, jlo, jhi): rows written are jlo <= j < jhi
   const cplx* mu;
   double alpha, kappa;
   cplx* A;
@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int r1, r0;
   tri_decode(blockIdx.x, r1, r0);   // r0 <= r1
-  const int2 tile = a.tiles[blockIdx.y];
-  const int TI = tile.x, TJ = tile.y;
+  const int4 tile = a.tiles[blockIdx.y];
+  const int RG = tile.x, TJ = tile.y;   // tile rows start at real column 8 RG (any multiple of 8), columns at 80 TJ
   const long long numStages = a.stage1 - a.stage0;
 
   if (threadIdx.x == 0) {
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       if (lane < 2 * I8_S) {
         const int k = lane >> 1, which = lane & 1;
         const size_t base = ((size_t)(a.stage0 + g) * I8_S + k) * a.numZGroups;
-        if (which == 0) bulk_g2s(st + k * I8_A_BYTES, a.dig + (base + (size_t)TI * (I8_TM / 8)) * 256, I8_A_BYTES, full + slot);
+        if (which == 0) bulk_g2s(st + k * I8_A_BYTES, a.dig + (base + (size_t)RG) * 256, I8_A_BYTES, full + slot);
         else bulk_g2s(st + I8_S * I8_A_BYTES + k * I8_B_BYTES, a.dig + (base + (size_t)TJ * (I8_TN / 8)) * 256, I8_B_BYTES,
                       full + slot);
       }
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
     // thread = tile row; per digit the row's 32 sample bytes are two 16-byte units of the canonical layout.
     // Byte-wise two's-complement negate where s_n = -1, SWAR on 32-bit words: -x = (x ^ 0xFF) + 1 per byte.
     const int ew = warp & 3;                              // TMEM lane quarter this warp may access
-    const int row = ew * 32 + lane;                       // real row of the tile (z = 128*TI + row)
+    const int row = ew * 32 + lane;                       // real row of the tile (z = 8 RG + row)
     {
       const uint32_t* sg0 = a.sigT + (size_t)r0 * a.words;
       const uint32_t* sg1 = a.sigT + (size_t)r1 * a.words;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
     // ===================== epilogue (warps 2-5): TMEM -> fp64, combine re/im, scale, scatter =====================
     const double wl[I8_LEV] = {1.0 / 65025.0, 1.0 / 16581375.0, 1.0 / 4228250625.0, 1.0 / 1078203909375.0,
                                1.0 / 274941996890625.0};   // 255^-t, t = 2..6
-    const int zrow = TI * I8_TM + row;
+    const int zrow = RG * 8 + row;
     const int j = zrow >> 1;                              // complex row index; lane parity = re/im part
     const bool isIm = (zrow & 1) != 0;
     const double srow = (j < a.M) ? a.scale[zrow] : 0.0;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         (void)p0;
         const double part = isIm ? (p1 - c0) : (c0 + p1);
         const double other = __shfl_xor_sync(0xffffffffu, part, 1);   // even lane receives Im G
-        if (!lok || j >= a.M || l > j || isIm) continue;
+        if (!lok || j >= a.M || j < tile.z || j >= tile.w || l > j || isIm) continue;
         const double gr = a.alpha * part;
         const double gi = (l == j) ? 0.0 : a.alpha * other;
         const long long a0 = (long long)r0 * a.M + j, b1 = (long long)r1 * a.M + l;
@@ -416,7 +416,9 @@ extern "C" int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long 
   return JVMC_OK;
 }
 
-// tiles: device array of (I, J) int pairs listing the tiles that contain an element l <= j.
+// tiles: device array of int quadruples (rowGroup, J, jlo, jhi): the tile's 128 rows start at real column 8 rowGroup
+// (complex row 4 rowGroup), its 80 columns at real column 80 J; it writes the elements jlo <= j < jhi, l <= j.  The
+// caller's list must cover every (j, l <= j) exactly once (later launches add into A).
 extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale, long long B, int M, int R,
                                   const unsigned int* sigT, const int* tiles, int numTiles, const double* mu,
                                   double alpha, double kappa, double* A, void* stream) {
@@ -425,7 +427,7 @@ extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale
   long long digitBytes;
   jvmc_i8_layout(B, M, &a.numChunks, &a.numZGroups, &digitBytes);
   a.dig = (const int8_t*)digits; a.scale = scale; a.sigT = sigT; a.words = (B + 31) / 32;
-  a.tiles = (const int2*)tiles; a.mu = (const cplx*)mu; a.alpha = alpha; a.kappa = kappa; a.A = (cplx*)A;
+  a.tiles = (const int4*)tiles; a.mu = (const cplx*)mu; a.alpha = alpha; a.kappa = kappa; a.A = (cplx*)A;
   a.M = M; a.R = R;
   size_t smem = (size_t)I8_SLOTS * I8_STAGE_BYTES + 32 * sizeof(uint64_t);
   cudaFuncSetAttribute(gram_s_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -190,13 +190,30 @@ def rbm_gram_S(Y, sigT, mu, alpha, kappa, out=None, tile=0):
 _I8_TILES = {}
 
 
+def i8_tile_list(M):
+    """Tiles (rowGroup, J, jlo, jhi) of 128 x 80 real columns (64 x 40 complex) covering every (j, l <= j) once.
+
+    Full 64-row blocks are anchored at the END of the row range (the block ending at row e needs ceil(e/40) column
+    tiles), so the ragged remainder sits at rows [0, o) where it needs only ceil(o/40) tiles instead of a full
+    tile row: 39 tiles at M = 400 (ideal 31.25; 46 with the remainder at the bottom)."""
+    M4 = (M + 3) // 4 * 4            # row blocks start on 8-real-row (4 complex) boundaries of the digit layout
+    nFull = M4 // 64
+    o = M4 - 64 * nFull
+    tl = []
+    for J in range((min(o, M) + 39) // 40):
+        tl.append((0, J, 0, min(o, M)))
+    for b in range(nFull):
+        lo = o + 64 * b
+        hi = min(lo + 64, M)
+        for J in range((hi + 39) // 40):
+            tl.append((lo // 4, J, lo, hi))
+    return tl
+
+
 def _i8_tiles(M, device):
-    """(I, J) tiles of 128 x 80 real columns (64 x 40 complex) that contain an element l <= j."""
     key = (M, str(device))
     if key not in _I8_TILES:
-        tl = [(I, J) for I in range((2 * M + 127) // 128) for J in range((2 * M + 79) // 80)
-              if 64 * I < M and 40 * J < M and 40 * J <= 64 * I + 63]
-        _I8_TILES[key] = torch.tensor(tl, dtype=I32, device=device).contiguous()
+        _I8_TILES[key] = torch.tensor(i8_tile_list(M), dtype=I32, device=device).contiguous()
     return _I8_TILES[key]
 
 
