@@ -373,8 +373,10 @@ def main():
         # 15 digit-pair products (levels k+k' <= 6) on tcgen05 kind::i8 with exact int32 accumulation.
         ntile = int(K._i8_tiles(M, dev).shape[0])
         stages = (nLocal + 31) // 32
-        launches_i8 = (stages + 511) // 512
+        launches_i8 = (stages + 831) // 832
         exec_ops = 2.0 * (R * (R + 1) / 2) * ntile * stages * (15 * 80) * 128 * 32
+        # minimal work of the method: symmetric half of the 2M x 2M real Gram per site pair, 15 digit-pair products
+        algo_ops = 2.0 * (R * (R + 1) / 2) * (2 * M * (2 * M + 1) / 2) * nLocal * 15
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             with open(peaks_path) as fh:
@@ -383,17 +385,22 @@ def main():
         else:
             bf16, i8_src = 1590.0, "2 x 1.59 PFLOP/s bf16 fallback of B200_PROFILING.md"
         i8_peak = 2.0 * bf16
-        ach = exec_ops / (gram_ms * 1e-3) / 1e12
+        ach = algo_ops / (gram_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "gram_s_i8_kernel (tcgen05.mma kind::i8, UTCIMMA) + i8 slicing",
                     "achieved": ach, "peak": i8_peak, "unit": "TOP/s", "frac": ach / i8_peak, "traffic": None,
                     "peak_source": i8_src, "launch_ms": gram_ms, "launches_per_step": launches_i8,
+                    "algorithmic_int8_op_per_step": algo_ops,
                     "executed_int8_op_per_step": exec_ops,
+                    "executed_tops": exec_ops / (gram_ms * 1e-3) / 1e12,
+                    "executed_frac": exec_ops / (gram_ms * 1e-3) / 1e12 / i8_peak,
                     "algorithmic_flop_per_step": algo_flop,
                     "fp64_equivalent": {"achieved_tflops": achieved, "dgemm_peak_tflops": peak_tf,
                                         "ratio": achieved / peak_tf, "dgemm_peak_source": peak_src},
                     "note": "fp64-equivalent Gram (4*N_s*P_c^2 algorithmic flop, SURVEY 8d) executed as 15 int8 digit-pair "
-                            "products per sample pair; at this tiling the kernel is bound by L2->SM operand traffic "
-                            "(33 KB per 32-sample stage and CTA), see DESIGN.md 4.1"}
+                            "products per sample pair; achieved counts the symmetric half of each site pair's 2M x 2M "
+                            "real Gram, executed also the padding of the 128 x 80 tiles that straddle the diagonal; "
+                            "the tensor pipe waits on shared-memory bandwidth (TMA writes + sign-pass reads + UTCIMMA "
+                            "B reads = 91 KB per 32-sample stage) under the board power cap, see DESIGN.md 4.2"}
     tp = os.path.join(ROOT, "profiles", "gram_traffic.json")
     if os.path.exists(tp):
         try:

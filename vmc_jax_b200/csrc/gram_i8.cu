@@ -15,7 +15,7 @@
 //    tiles into an mbarrier-guarded smem ring; four "sign" warps apply s_n to the A tiles by byte-wise negation;
 //    one thread issues 15 tcgen05.mma kind::i8 (M=128, N=96, K=32; SASS UTCIMMA), digit pair (k,k') accumulating
 //    exactly in int32 into the TMEM accumulator of level t = k+k' (5 levels x 96 columns = 480 TMEM columns).
-//    One launch covers at most 16384 samples (int32 head-room); at its end four epilogue warps read TMEM
+//    One launch covers at most 26624 samples (int32 head-room); at its end four epilogue warps read TMEM
 //    (tcgen05.ld), weight level t by 255^-t in fp64, combine real/imag parts with a lane shuffle, apply scales, alpha
 //    and the mean correction and scatter the Hermitian images (later launches add into A).
 //    Dropped digit pairs (k+k' > 6) are below 4 * 255^-7 = 6e-17 of c_z c_z'; the splitting itself is exact to
@@ -32,7 +32,7 @@ constexpr int I8_SLOTS = 6;
 constexpr int I8_A_BYTES = I8_TM * I8_KS;   // per digit
 constexpr int I8_B_BYTES = I8_TN * I8_KS;
 constexpr int I8_STAGE_BYTES = I8_S * (I8_A_BYTES + I8_B_BYTES);
-constexpr int I8_MAXSTAGES = 512;       // stages per launch: 512*32*5*127^2 < 2^31 (int32 head-room in TMEM)
+constexpr int I8_MAXSTAGES = 832;       // stages per launch: 832*32*5*127^2 < 2^31 (int32 head-room in TMEM)
 constexpr int I8_THREADS = 320;         // warp 0 producer, 1 MMA issuer, 2-9 sign (2-5 also epilogue)
 constexpr int I8_ACOL = I8_LEV * I8_TN;  // first TMEM column of the double-buffered A operand (2 x 5 digits x 8 columns)
 
@@ -63,6 +63,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// multicast variant: the bytes land at the same shared-memory offset of every CTA in ctaMask and complete_tx the
+// mbarrier at the same offset of each of them
+__device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, unsigned bytes, uint64_t* bar, unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 // K-major SWIZZLE_NONE UMMA shared-memory descriptor (canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units)
 __device__ __forceinline__ uint64_t umma_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
@@ -79,6 +97,13 @@ __device__ __forceinline__ void umma_i8_ts(uint32_t tacc, uint32_t ta, uint64_t 
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive (once the preceding MMAs retire) on the mbarrier at this offset in every CTA of ctaMask
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, unsigned short mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tri_decode(long long p, int& hi, int& lo) {
   long long h = (long long)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
@@ -159,6 +184,8 @@ struct I8Args {
   long long stage0, stage1;   // this launch covers sample stages [stage0, stage1), at most I8_MAXSTAGES
   int accumulate;             // 0: A = alpha G - kappa mu^H mu ; 1: A += alpha G
   int dbg;                    // development ablations: 1 = MMA issue only, 2 = TMA + MMA (no sign pass)
+  int cl;                     // thread-block cluster size along the pair axis (operand tiles are TMA-multicast)
+  long long pairs;            // R (R + 1) / 2; CTAs beyond it only pad the last cluster
 };
 
 __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
@@ -173,14 +200,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(accfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // The CTAs of a cluster work on consecutive site pairs of the SAME tile: the raw digit tiles are identical for
+  // all of them (only the signs differ), so every bulk copy is multicast to the whole cluster and the L2 -> SM
+  // operand traffic (the binding resource of the single-CTA version) drops by the cluster size.
+  const unsigned crank = (a.cl > 1) ? cluster_ctarank() : 0u;
+  const unsigned short cmask = (unsigned short)((1u << a.cl) - 1u);
+  const bool padCta = (long long)blockIdx.x >= a.pairs;
   int r1, r0;
-  tri_decode(blockIdx.x, r1, r0);   // r0 <= r1
+  tri_decode(padCta ? 0 : blockIdx.x, r1, r0);   // r0 <= r1
   const int4 tile = a.tiles[blockIdx.y];
   const int RG = tile.x, TJ = tile.y;   // tile rows start at real column 8 RG (any multiple of 8), columns at 80 TJ
   const long long numStages = a.stage1 - a.stage0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < I8_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < I8_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, (unsigned)a.cl); }
     for (int b = 0; b < 2; ++b) { mbar_init(aready + b, 8); mbar_init(afree + b, 1); }
     mbar_init(accfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -191,6 +224,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if (a.cl > 1) cluster_sync_all();   // peers' barriers are initialised before anything is multicast to them
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = *tmem_base_p;
 
@@ -205,9 +239,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       if (lane < 2 * I8_S) {
         const int k = lane >> 1, which = lane & 1;
         const size_t base = ((size_t)(a.stage0 + g) * I8_S + k) * a.numZGroups;
-        if (which == 0) bulk_g2s(st + k * I8_A_BYTES, a.dig + (base + (size_t)RG) * 256, I8_A_BYTES, full + slot);
-        else bulk_g2s(st + I8_S * I8_A_BYTES + k * I8_B_BYTES, a.dig + (base + (size_t)TJ * (I8_TN / 8)) * 256, I8_B_BYTES,
-                      full + slot);
+        unsigned char* dst = which == 0 ? st + k * I8_A_BYTES : st + I8_S * I8_A_BYTES + k * I8_B_BYTES;
+        const int8_t* src = a.dig + (base + (which == 0 ? (size_t)RG : (size_t)TJ * (I8_TN / 8))) * 256;
+        const unsigned bytes = which == 0 ? I8_A_BYTES : I8_B_BYTES;
+        if (a.cl == 1) bulk_g2s(dst, src, bytes, full + slot);
+        else if ((unsigned)lane % (unsigned)a.cl == crank) bulk_g2s_mc(dst, src, bytes, full + slot, cmask);   // my share
       }
     }
   } else if (warp == 1) {
@@ -241,7 +277,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         mma(3, 1, 3, idesc3, 1u);       // levels 4,5,6
         mma(4, 1, 2, idesc2, 1u);       // levels 5,6
         mma(5, 1, 1, idesc1, 1u);       // level 6
-        umma_commit(empty + slot);                       // smem slot reusable once these MMAs retire
+        if (a.cl == 1) umma_commit(empty + slot);        // smem slot reusable once these MMAs retire
+        else umma_commit_mc(empty + slot, cmask);        // ... in every CTA of the cluster (they all write into it)
         umma_commit(afree + b);                          // ... and so is the TMEM A buffer
         if (g + 1 == numStages) umma_commit(accfull);
       }
@@ -268,29 +305,36 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
           const uint32_t nib = (x >> (4 * q)) & 0xFu;
           msk[q] = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;     // nibble bits -> 0x00/0xFF byte masks
         }
-        if (g >= 2) mbar_wait(afree + b, (unsigned)(((g >> 1) - 1) & 1));
+        // The signed digits are prepared in registers BEFORE waiting for the TMEM buffer, so that only the
+        // TMEM store sits on the MMA(g-2) -> sign(g) -> MMA(g) dependency chain.
         mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
         // two warps share a TMEM lane quarter: warps 2-5 take digits 0-2, warps 6-9 digits 3-4
-        const int kbeg = (warp < 6) ? 0 : 3, kend = (warp < 6) ? 3 : I8_S;
+        const int kbeg = (warp < 6) ? 0 : 3, nk = (warp < 6) ? 3 : 2;
+        uint32_t w[3][8];
 #pragma unroll
-        for (int k = 0; k < I8_S; ++k) {
-          if (k < kbeg || k >= kend) continue;
-          uint32_t w[8];
+        for (int k = 0; k < 3; ++k) {
+          if (k >= nk) continue;
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
-            const uint4 v = *reinterpret_cast<const uint4*>(st + k * I8_A_BYTES + ch * 128 + rowOff);
-            w[ch * 4 + 0] = v.x; w[ch * 4 + 1] = v.y; w[ch * 4 + 2] = v.z; w[ch * 4 + 3] = v.w;
+            const uint4 v = *reinterpret_cast<const uint4*>(st + (kbeg + k) * I8_A_BYTES + ch * 128 + rowOff);
+            w[k][ch * 4 + 0] = v.x; w[k][ch * 4 + 1] = v.y; w[k][ch * 4 + 2] = v.z; w[k][ch * 4 + 3] = v.w;
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const uint32_t aa = w[q] ^ msk[q];
-            w[q] = ((aa & 0x7F7F7F7Fu) + (msk[q] & 0x01010101u)) ^ (aa & 0x80808080u);
+            const uint32_t aa = w[k][q] ^ msk[q];
+            w[k][q] = ((aa & 0x7F7F7F7Fu) + (msk[q] & 0x01010101u)) ^ (aa & 0x80808080u);
           }
-          const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(I8_ACOL + b * I8_S * 8 + k * 8);
+        }
+        if (g >= 2) mbar_wait(afree + b, (unsigned)(((g >> 1) - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (k >= nk) continue;
+          const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(I8_ACOL + b * I8_S * 8 + (kbeg + k) * 8);
           asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr),
-                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+                       "r"(w[k][0]), "r"(w[k][1]), "r"(w[k][2]), "r"(w[k][3]), "r"(w[k][4]), "r"(w[k][5]), "r"(w[k][6]),
+                       "r"(w[k][7]) : "memory");
         }
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -340,7 +384,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         (void)p0;
         const double part = isIm ? (p1 - c0) : (c0 + p1);
         const double other = __shfl_xor_sync(0xffffffffu, part, 1);   // even lane receives Im G
-        if (!lok || j >= a.M || j < tile.z || j >= tile.w || l > j || isIm) continue;
+        if (!lok || j >= a.M || j < tile.z || j >= tile.w || l > j || isIm || padCta) continue;
         const double gr = a.alpha * part;
         const double gi = (l == j) ? 0.0 : a.alpha * other;
         const long long a0 = (long long)r0 * a.M + j, b1 = (long long)r1 * a.M + l;
@@ -374,13 +418,21 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if (a.cl > 1) cluster_sync_all();   // no peer may still signal this CTA's barriers when it exits
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem));
 }
 
 }  // namespace
 
 static int g_i8_dbg = 0;
-extern "C" int jvmc_i8_set_debug(int flags) { g_i8_dbg = flags; return JVMC_OK; }   // development ablations (timing only)
+static int g_i8_cluster = 2;
+// development knobs: bits 0-7 ablation flags (timing only, results invalid); bits 8-11, when non-zero, set the cluster size
+extern "C" int jvmc_i8_set_debug(int flags) {
+  g_i8_dbg = flags & 0xFF;
+  const int cl = (flags >> 8) & 0xF;
+  if (cl == 1 || cl == 2 || cl == 4 || cl == 8) g_i8_cluster = cl;
+  return JVMC_OK;
+}
 
 // Sizes of the scratch buffers the caller provides.
 extern "C" int jvmc_i8_layout(long long B, int M, long long* numChunks, int* numZGroups, long long* digitBytes) {
@@ -433,16 +485,30 @@ extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale
   cudaFuncSetAttribute(gram_s_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   long long pairs = (long long)R * (R + 1) / 2;
   if (numTiles > 65535 || pairs > 2147483647LL) return JVMC_ERR_UNSUPPORTED;
-  dim3 grid((unsigned)pairs, (unsigned)numTiles);
+  a.cl = g_i8_cluster; a.pairs = pairs;
+  dim3 grid((unsigned)((pairs + a.cl - 1) / a.cl * a.cl), (unsigned)numTiles);
   const long long numStages = a.numChunks / 2;
-  // one launch per <= 16384 samples (exact int32 accumulation); later launches add into A
-  for (long long s0 = 0; s0 < numStages; s0 += I8_MAXSTAGES) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(I8_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)a.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  // one launch per <= 26624 samples (exact int32 accumulation), evenly split; later launches add into A
+  const long long numLaunches = (numStages + I8_MAXSTAGES - 1) / I8_MAXSTAGES;
+  const long long per = (numStages + numLaunches - 1) / numLaunches;
+  for (long long s0 = 0; s0 < numStages; s0 += per) {
     a.stage0 = s0;
-    a.stage1 = (s0 + I8_MAXSTAGES < numStages) ? s0 + I8_MAXSTAGES : numStages;
+    a.stage1 = (s0 + per < numStages) ? s0 + per : numStages;
     a.accumulate = (s0 > 0) ? 1 : 0;
     a.dbg = g_i8_dbg;
-    gram_s_i8_kernel<<<grid, I8_THREADS, smem, (cudaStream_t)stream>>>(a);
-    JVMC_CHECK_LAUNCH();
+    if (a.cl == 1) {
+      gram_s_i8_kernel<<<grid, I8_THREADS, smem, (cudaStream_t)stream>>>(a);
+      JVMC_CHECK_LAUNCH();
+    } else {
+      cudaError_t le = cudaLaunchKernelEx(&cfg, gram_s_i8_kernel, a);
+      if (le != cudaSuccess) { jvmc_set_last_cuda_error(le); return JVMC_ERR_CUDA; }
+    }
   }
   return JVMC_OK;
 }
