@@ -50,6 +50,7 @@ int jvmc_rbm_mcmc(int32_t* states, long long C, int N, int M, const double* W, c
                   const double* tables, unsigned long long seed, unsigned long long step0, long long chain0,
                   int proposer, double mu, int sweepSteps, long long thermSteps, int numSamplesPerChain,
                   int refreshEvery, int32_t* out, unsigned long long* counters, void* stream);
+int jvmc_mcmc_set_generic(int on);   /* development knob: 1 = always use the generic sampler kernel (A/B timing) */
 
 /* Operator.get_s_primes: jVMC/operator/base.py:91-160 + BranchFreeOperator._get_s_primes
  * jVMC/operator/branch_free.py:443-487.  Phase 1: all matrix elements mAll[B,numOps] (diagonal strings merged),

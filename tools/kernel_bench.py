@@ -21,7 +21,11 @@ ap.add_argument("--chains", type=int, default=2368)
 ap.add_argument("--therm", type=int, default=25)
 ap.add_argument("--g", type=float, default=3.04)
 ap.add_argument("--refresh", type=int, default=8)
+ap.add_argument("--generic", action="store_true", help="force the generic sampler kernel")
 a = ap.parse_args()
+if a.generic:
+    from vmc_jax_b200 import _lib
+    _lib.load().jvmc_mcmc_set_generic(1)
 shape = tuple(a.shape)
 N = int(np.prod(shape))
 M = a.alpha * N

@@ -254,7 +254,238 @@ rbm_mcmc_kernel(McmcArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path for the single-spin-flip proposers (propose_spin_flip, propose_spin_flip_Z2) and M <= 32 JT:
+//  * the row T_a of the NEXT proposal is copied global -> shared with cp.async while the current proposal is
+//    evaluated (the site of step st+1 only depends on the counter RNG, not on the accept decision), so the L2
+//    latency of the weight-row stream is off the per-step critical path;
+//  * the current row lives in registers (JT complex numbers per lane), the loop over hidden units is fully unrolled;
+//  * Philox is evaluated once per 32 steps (lane l computes step base + l) and broadcast by shuffles;
+//  * exp(mu Re lc_a) comes from a per-CTA shared table instead of an exp per proposal.
+// Same RNG counters as the generic kernel: the accept/reject sequence is identical up to floating-point rounding.
+template <int JT>
+__global__ void __launch_bounds__(MC_WPC * 32)
+rbm_mcmc_flip_kernel(McmcArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long chain = (long long)blockIdx.x * MC_WPC + warp;
+  const int N = a.N, M = a.M;
+  cplx* tauAll = reinterpret_cast<cplx*>(smem_raw);
+  cplx* bufAll = tauAll + (size_t)MC_WPC * M;
+  double* elc = reinterpret_cast<double*>(bufAll + (size_t)MC_WPC * JT * 32);
+  uint32_t* sbitsAll = reinterpret_cast<uint32_t*>(elc + N);
+  for (int i = threadIdx.x; i < N; i += MC_WPC * 32) elc[i] = exp(a.mu * a.lc[i].x);
+  __syncthreads();
+  if (chain >= a.C) return;  // whole warp exits together (no further block-wide barriers)
+  cplx* tau = tauAll + (size_t)warp * M;
+  cplx* buf = bufAll + (size_t)warp * JT * 32;
+  uint32_t* sbits = sbitsAll + warp * 32;
+  const bool hasBias = a.bias != nullptr;
+  const unsigned long long gchain = (unsigned long long)(a.chain0 + chain);
+  const Philox rng(a.seed);
+  const uint32_t c2 = (uint32_t)gchain, c3 = (uint32_t)(gchain >> 32) << 8;
+
+  uint32_t valid = 0, bits = 0;
+  {
+    int base = lane * 32;
+    for (int k = 0; k < 32; ++k) {
+      int i = base + k;
+      if (i < N) {
+        valid |= 1u << k;
+        if (a.states[chain * N + i] != 0) bits |= 1u << k;
+      }
+    }
+  }
+  auto refresh = [&]() {
+    sbits[lane] = bits;
+    __syncwarp();
+    for (int j0 = 0; j0 < M; j0 += 32) {
+      int j = j0 + lane;
+      if (j < M) {
+        cplx acc = hasBias ? a.bias[j] : cmk(0.0, 0.0);
+        for (int i = 0; i < N; ++i) {
+          double sg = ((sbits[i >> 5] >> (i & 31)) & 1u) ? 1.0 : -1.0;
+          cplx w = a.W[(size_t)i * M + j];
+          acc.x = fma(sg, w.x, acc.x);
+          acc.y = fma(sg, w.y, acc.y);
+        }
+        cplx l, t;
+        lncosh_tanh(acc, l, t);
+        tau[j] = t;
+      }
+    }
+    __syncwarp();
+  };
+  // stage row T_site into this warp's buffer: lane l copies the elements j = l + 32 k it will read back itself
+  auto prefetch_row = [&](int site) {
+    const cplx* src = a.T + (size_t)site * M + lane;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + lane);
+#pragma unroll
+    for (int k = 0; k < JT; ++k)
+      if (lane + 32 * k < M)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + (unsigned)(k * 32 * sizeof(cplx))),
+                     "l"(src + 32 * k) : "memory");
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  unsigned long long nAcc = 0, nProp = 0;
+  const long long total = a.thermSteps + (long long)a.numSamples * a.K;
+  long long nextEmit = a.thermSteps + a.K;
+  int emitted = 0, sweepCtr = 0, untilSweep = a.K;
+  refresh();
+
+  // RNG batches: q holds the Philox output of step (batch base + lane)
+  uint4 q = make_uint4(0, 0, 0, 0);
+  auto draw = [&](long long st, uint4& r) {   // r of step st (warp-uniform); refills the batch every 32 steps
+    const int idx = (int)(st & 31);
+    if (idx == 0) {
+      const unsigned long long gs = a.step0 + (unsigned long long)st + (unsigned long long)lane;
+      q = rng((uint32_t)gs, (uint32_t)(gs >> 32), c2, c3);
+    }
+    r.x = __shfl_sync(0xffffffffu, q.x, idx);
+    r.y = __shfl_sync(0xffffffffu, q.y, idx);
+    r.z = __shfl_sync(0xffffffffu, q.z, idx);
+    r.w = __shfl_sync(0xffffffffu, q.w, idx);
+  };
+  // Note: a.step0 is a multiple of nothing in particular, so batches are aligned on the LOCAL step index; the
+  // counter of step st is still step0 + st, exactly as in the generic kernel.
+  uint4 rc;
+  if (total > 0) {
+    draw(0, rc);
+    prefetch_row((int)__umulhi(rc.x, (uint32_t)N));
+  }
+  for (long long st = 0; st < total; ++st) {
+    const int sa = (int)__umulhi(rc.x, (uint32_t)N);
+    const bool g = (a.proposer == 1) && (__umulhi(rc.y, 5u) == 0u);
+    const double u = u01_from_bits(rc.z, rc.w);
+    // current row: shared buffer -> registers, then the buffer is free for the next row
+    cplx tv[JT];
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < JT; ++k) tv[k] = (lane + 32 * k < M) ? buf[lane + 32 * k] : cmk(0.0, 0.0);
+    uint4 rn = rc;
+    if (st + 1 < total) {
+      draw(st + 1, rn);
+      prefetch_row((int)__umulhi(rn.x, (uint32_t)N));
+    }
+    const uint32_t wsa = __shfl_sync(0xffffffffu, bits, sa >> 5);
+    const double sga = ((wsa >> (sa & 31)) & 1u) ? -1.0 : 1.0;   // -sigma_a
+    const bool gb = g && hasBias;
+    bool accept;
+    if (!gb) {
+      // |1 + sga tau t|^2 = (1 + sga Re)^2 + Im^2, two independent partial products
+      double p0 = 1.0, p1 = 1.0;
+#pragma unroll
+      for (int k = 0; k < JT; ++k) {
+        const cplx tj = (lane + 32 * k < M) ? tau[lane + 32 * k] : cmk(0.0, 0.0);
+        const double re = fma(tj.x, tv[k].x, -tj.y * tv[k].y);
+        const double im = fma(tj.x, tv[k].y, tj.y * tv[k].x);
+        const double fr = fma(sga, re, 1.0);
+        const double f2 = fma(fr, fr, im * im);
+        if (k & 1) p1 *= f2; else p0 *= f2;
+      }
+      const double prod = warp_prod(p0 * p1);
+      const double P = (a.mu == 2.0) ? elc[sa] * prod : elc[sa] * pow(prod, 0.5 * a.mu);
+      accept = u < P;
+      nProp += 1;
+      if (accept) {
+        nAcc += 1;
+        const double gsn = g ? -1.0 : 1.0;   // Z2 flip without bias: tau -> -tau
+#pragma unroll
+        for (int k = 0; k < JT; ++k) {
+          if (lane + 32 * k < M) {
+            const cplx tj = tau[lane + 32 * k];
+            const cplx n = cscale(tv[k], sga);
+            const cplx tn = cdiv(cadd(tj, n), cadd(cmk(1.0, 0.0), cmul(tj, n)));
+            tau[lane + 32 * k] = cscale(tn, gsn);
+          }
+        }
+      }
+    } else {
+      // global flip with a bias (probability 1/5 of the Z2 proposer's steps): theta -> -theta' + 2b
+      double prod = 1.0;
+#pragma unroll
+      for (int k = 0; k < JT; ++k) {
+        if (lane + 32 * k < M) {
+          const cplx tj = tau[lane + 32 * k];
+          const cplx n = cscale(tv[k], sga);
+          cplx f = cadd(cmk(1.0, 0.0), cmul(tj, n));
+          const cplx t1 = cdiv(cadd(tj, n), f);
+          f = cmul(f, csub(cmk(1.0, 0.0), cmul(t1, a.tb2[lane + 32 * k])));
+          prod *= cabs2(f);
+        }
+      }
+      prod = warp_prod(prod);
+      const double lre = a.lc[sa].x + a.lcb[0].x;
+      const double P = (a.mu == 2.0) ? exp(2.0 * lre) * prod : exp(a.mu * (lre + 0.5 * log(prod)));
+      accept = u < P;
+      nProp += 1;
+      if (accept) {
+        nAcc += 1;
+#pragma unroll
+        for (int k = 0; k < JT; ++k) {
+          if (lane + 32 * k < M) {
+            const cplx tj = tau[lane + 32 * k];
+            const cplx n = cscale(tv[k], sga);
+            cplx tn = cdiv(cadd(tj, n), cadd(cmk(1.0, 0.0), cmul(tj, n)));
+            const cplx b2 = a.tb2[lane + 32 * k];
+            tn = cdiv(csub(b2, tn), csub(cmk(1.0, 0.0), cmul(b2, tn)));
+            tau[lane + 32 * k] = tn;
+          }
+        }
+      }
+    }
+    if (accept) {
+      if ((sa >> 5) == lane) bits ^= 1u << (sa & 31);
+      if (g) bits = (~bits) & valid;
+    }
+    if (st + 1 == nextEmit) {
+      const long long row = (long long)emitted * a.C + chain;  // time-major, chain-minor (sampler.py:323)
+      int32_t* dst = a.out + row * N;
+      for (int w = 0; w * 32 < N; ++w) {
+        uint32_t word = __shfl_sync(0xffffffffu, bits, w);
+        int i = w * 32 + lane;
+        if (i < N) dst[i] = (int32_t)((word >> lane) & 1u);
+      }
+      ++emitted;
+      nextEmit += a.K;
+    }
+    if (--untilSweep == 0) {
+      untilSweep = a.K;
+      if (++sweepCtr >= a.refreshEvery && st + 1 < total) { sweepCtr = 0; refresh(); }
+    }
+    rc = rn;
+  }
+  for (int w = 0; w * 32 < N; ++w) {
+    uint32_t word = __shfl_sync(0xffffffffu, bits, w);
+    int i = w * 32 + lane;
+    if (i < N) a.states[chain * N + i] = (int32_t)((word >> lane) & 1u);
+  }
+  if (lane == 0) {
+    atomicAdd(a.counters + 0, nProp);
+    atomicAdd(a.counters + 1, nAcc);
+  }
+}
+
+template <int JT>
+int launch_flip(const McmcArgs& a, cudaStream_t stream) {
+  size_t smem = (size_t)MC_WPC * a.M * sizeof(cplx) + (size_t)MC_WPC * JT * 32 * sizeof(cplx) + (size_t)a.N * sizeof(double) +
+                MC_WPC * 32 * sizeof(uint32_t);
+  if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(rbm_mcmc_flip_kernel<JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  unsigned grid = (unsigned)((a.C + MC_WPC - 1) / MC_WPC);
+  rbm_mcmc_flip_kernel<JT><<<grid, MC_WPC * 32, smem, stream>>>(a);
+  JVMC_CHECK_LAUNCH();
+  return JVMC_OK;
+}
+
 }  // namespace
+
+static int g_mcmc_generic = 0;
+// development knob: 1 forces the generic kernel (A/B comparisons of the fast single-flip path)
+extern "C" int jvmc_mcmc_set_generic(int on) { g_mcmc_generic = on; return JVMC_OK; }
 
 extern "C" int jvmc_rbm_mcmc(int32_t* states, long long C, int N, int M, const double* W, const double* bias,
                              const double* tables, unsigned long long seed, unsigned long long step0,
@@ -275,6 +506,13 @@ extern "C" int jvmc_rbm_mcmc(int32_t* states, long long C, int N, int M, const d
   a.K = sweepSteps; a.thermSteps = thermSteps; a.numSamples = numSamplesPerChain;
   a.refreshEvery = refreshEvery > 0 ? refreshEvery : 1;
   a.out = out; a.counters = counters;
+  if (proposer != 2 && M <= 512 && !g_mcmc_generic) {
+    const int jt = (M + 31) / 32;
+    if (jt <= 4) return launch_flip<4>(a, (cudaStream_t)stream);
+    if (jt <= 8) return launch_flip<8>(a, (cudaStream_t)stream);
+    if (jt <= 13) return launch_flip<13>(a, (cudaStream_t)stream);
+    return launch_flip<16>(a, (cudaStream_t)stream);
+  }
   size_t smem = (size_t)MC_WPC * M * sizeof(cplx) + MC_WPC * 32 * sizeof(uint32_t);
   if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
