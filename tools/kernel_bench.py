@@ -82,7 +82,12 @@ Wd, bd = psi._cW()
 _, t_l = timed(lambda: K.rbm_logpsi(flat, Wd, bd))
 print("rbm_logpsi: %.3f ms: %.2f TFLOP/s (4NM adds) + %d transcendentals" % (t_l, 4.0 * N * M * B / t_l / 1e9, B * M))
 E, t_e = timed(lambda: H.get_O_loc(s, psi, logPsi))
-print("fused E_loc: %.3f ms: %.2f TFLOP/s (14 N M flop/sample)" % (t_e, 14.0 * N * M * B / t_e / 1e9))
+print("fused E_loc (API call): %.3f ms: %.2f TFLOP/s (14 N M flop/sample)" % (t_e, 14.0 * N * M * B / t_e / 1e9))
+tab = H._ensure_compiled(0)
+tau_d, tables_d, dt_d, pref_d = psi._tau(flat), psi.flip_tables(), tab.device_tables(), tab.eval_prefactors()
+_, t_k = timed(lambda: K.rbm_eloc(flat, tau_d, tables_d, dt_d, pref_d))
+print("fused E_loc (kernel): %.3f ms: %.2f TFLOP/s (14 N M flop/sample), %.2f TB/s of weight rows if unshared"
+      % (t_k, 14.0 * N * M * B / t_k / 1e9, 16.0 * M * B * tab.numOps / t_k / 1e9))
 G = RBMGradientObs(psi, s, p)
 _, t_m = timed(lambda: K.rbm_moments(G._s, G._tau, G._p.to(torch.complex128), False, 0))
 print("rbm_moments: %.3f ms: %.2f TFLOP/s (8 N M flop/sample)" % (t_m, 8.0 * N * M * B / t_m / 1e9))

@@ -132,83 +132,284 @@ __global__ void oloc_reduce_kernel(const cplx* __restrict__ matEl, const cplx* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused RBM local energy.  One warp per sample; tau row in shared memory.  Lanes first walk 32
-// strings in parallel (matrix element, flipped sites), then the warp evaluates the amplitude
-// ratio of every off-diagonal string with lanes striding over hidden units.
-constexpr int EL_WPC = 4;
+// Fused RBM local energy, tiled over samples.  A CTA holds the tau rows of WPC x SPW samples in shared memory;
+// every warp owns SPW samples.  Lanes first walk 32 operator strings in parallel (matrix element, flipped sites),
+// then the warp evaluates the amplitude ratio of every off-diagonal string with lanes striding over the hidden
+// units.  The kernel is bound by the L2 -> SM stream of the weight rows T_a (16 M bytes per string and sample if
+// nothing is shared), so
+//  * a row loaded into registers is applied to the warp's SPW samples whenever they flip the same sites (always
+//    the case for TFIM/Heisenberg-type strings), and
+//  * the warps of a CTA are re-aligned at every block of 32 strings, so that they request the same rows at about
+//    the same time and share them through L1 (ld.global.nc);
+//  * exp(lc_a) is tabulated once per CTA instead of one complex exponential per string and sample.
+constexpr int EL_MAXWPC = 8;
 
-__global__ void __launch_bounds__(EL_WPC * 32)
+template <bool TWO, int SPW>
+__device__ __forceinline__ void flip_ratio(const cplx* __restrict__ T0, const cplx* __restrict__ T1,
+                                           const cplx* const* tau, const double* sg0, const double* sg1, int M,
+                                           int lane, cplx* p) {
+  cplx pa[SPW], pb[SPW];   // two independent product chains per sample
+#pragma unroll
+  for (int q = 0; q < SPW; ++q) { pa[q] = cmk(1.0, 0.0); pb[q] = cmk(1.0, 0.0); }
+  auto step = [&](int j, cplx* acc) {
+    const cplx t0 = __ldg(reinterpret_cast<const double2*>(T0 + j));
+    cplx t1 = cmk(0.0, 0.0);
+    if (TWO) t1 = __ldg(reinterpret_cast<const double2*>(T1 + j));
+#pragma unroll
+    for (int q = 0; q < SPW; ++q) {
+      const cplx tj = tau[q][j];
+      cplx f;
+      if (!TWO) {
+        f = cmk(fma(sg0[q], fma(tj.x, t0.x, -tj.y * t0.y), 1.0), sg0[q] * fma(tj.x, t0.y, tj.y * t0.x));
+      } else {
+        const cplx ta = cscale(t0, sg0[q]), tb = cscale(t1, sg1[q]);
+        f = cadd(cadd(cmk(1.0, 0.0), cmul(ta, tb)), cmul(tj, cadd(ta, tb)));
+      }
+      acc[q] = cmul(acc[q], f);
+    }
+  };
+  int j = lane;
+  for (; j + 32 < M; j += 64) { step(j, pa); step(j + 32, pb); }
+  if (j < M) step(j, pa);
+#pragma unroll
+  for (int q = 0; q < SPW; ++q) p[q] = warp_cprod(cmul(pa[q], pb[q]));
+}
+
+// Same product with the sample's tau row held in registers (lane l owns the hidden units l + 32 k): no shared-memory
+// traffic at all in the inner loop, which otherwise binds before the fp64 pipe does (16 B of tau + 16 B of T per
+// ten DFMA).  JT = ceil(M / 32) exactly, so only the last k can run past the row: its index is clamped (jl) and its
+// tau register is zero, which makes the factor exactly 1 -- no predicates or selects in the unrolled loop.
+template <bool TWO, int JT>
+__device__ __forceinline__ cplx flip_ratio_reg(const cplx* __restrict__ T0, const cplx* __restrict__ T1,
+                                               const cplx (&tr)[JT], double sg0, double sg1, int lane, int jl) {
+  cplx pa = cmk(1.0, 0.0), pb = cmk(1.0, 0.0);
+  const cplx* p0 = T0 + lane;
+  const cplx* p1 = TWO ? T1 + lane : nullptr;
+#pragma unroll
+  for (int k = 0; k < JT; ++k) {
+    const cplx t0 = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? p0 + 32 * k : T0 + jl));
+    const cplx tj = tr[k];
+    cplx f;
+    if (!TWO) {
+      f = cmk(fma(sg0, fma(tj.x, t0.x, -tj.y * t0.y), 1.0), sg0 * fma(tj.x, t0.y, tj.y * t0.x));
+    } else {
+      const cplx t1 = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? p1 + 32 * k : T1 + jl));
+      const cplx ta = cscale(t0, sg0), tb = cscale(t1, sg1);
+      f = cadd(cadd(cmk(1.0, 0.0), cmul(ta, tb)), cmul(tj, cadd(ta, tb)));
+      if (k == JT - 1 && lane + 32 * k != jl) f = cmk(1.0, 0.0);   // padding lane of the ragged tail
+    }
+    if (k & 1) pb = cmul(pb, f); else pa = cmul(pa, f);
+  }
+  return warp_cprod(cmul(pa, pb));
+}
+
+// Two single-flip strings (sites a and b) of the same sample at once: four independent product chains hide the
+// fp64 latency, and the two warp reductions are folded into one butterfly -- after the first exchange lanes 0-15
+// carry string a and lanes 16-31 string b.  Returns, in every lane, the product of the string its half belongs to.
+template <int JT>
+__device__ __forceinline__ cplx flip_ratio_reg_dual(const cplx* __restrict__ Ta, const cplx* __restrict__ Tb,
+                                                    const cplx (&tr)[JT], double sga, double sgb, int lane, int jl) {
+  cplx pa0 = cmk(1.0, 0.0), pa1 = cmk(1.0, 0.0), pb0 = cmk(1.0, 0.0), pb1 = cmk(1.0, 0.0);
+  const cplx* qa = Ta + lane;
+  const cplx* qb = Tb + lane;
+#pragma unroll
+  for (int k = 0; k < JT; ++k) {
+    const cplx ta = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? qa + 32 * k : Ta + jl));
+    const cplx tb = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? qb + 32 * k : Tb + jl));
+    const cplx tj = tr[k];
+    const cplx fa = cmk(fma(sga, fma(tj.x, ta.x, -tj.y * ta.y), 1.0), sga * fma(tj.x, ta.y, tj.y * ta.x));
+    const cplx fb = cmk(fma(sgb, fma(tj.x, tb.x, -tj.y * tb.y), 1.0), sgb * fma(tj.x, tb.y, tj.y * tb.x));
+    if (k & 1) { pa1 = cmul(pa1, fa); pb1 = cmul(pb1, fb); } else { pa0 = cmul(pa0, fa); pb0 = cmul(pb0, fb); }
+  }
+  const cplx A = cmul(pa0, pa1), Bv = cmul(pb0, pb1);
+  const bool hi = lane >= 16;
+  const cplx send = hi ? A : Bv;          // give away the string of the other half ...
+  cplx v = hi ? Bv : A;                   // ... keep the own one
+  v = cmul(v, cmk(__shfl_xor_sync(0xffffffffu, send.x, 16), __shfl_xor_sync(0xffffffffu, send.y, 16)));
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1)
+    v = cmul(v, cmk(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o)));
+  return v;
+}
+
+template <int SPW, int JT>
+__global__ void __launch_bounds__(EL_MAXWPC * 32)
 rbm_eloc_kernel(BfoTables t, const int32_t* __restrict__ s, const cplx* __restrict__ tauG, long long B, int N, int M,
                 const cplx* __restrict__ T, const cplx* __restrict__ lc, const cplx* __restrict__ pref,
                 int numDiag, cplx* __restrict__ out, int* __restrict__ errFlag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long b = (long long)blockIdx.x * EL_WPC + warp;
-  if (b >= B) return;
-  cplx* tau = reinterpret_cast<cplx*>(smem_raw) + (size_t)warp * M;
-  int32_t* cfg = reinterpret_cast<int32_t*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)EL_WPC * M) + (size_t)warp * N;
-  for (int j = lane; j < M; j += 32) tau[j] = tauG[b * M + j];
-  for (int i = lane; i < N; i += 32) cfg[i] = s[b * N + i];
-  __syncwarp();
-
-  cplx diagAcc = cmk(0.0, 0.0);   // merged diagonal strings
-  cplx eloc = cmk(0.0, 0.0);
-  for (int o0 = 0; o0 < t.numOps; o0 += 32) {
-    const int o = o0 + lane;
-    cplx m = cmk(0.0, 0.0);
-    int f0 = -1, f1 = -1;
-    bool isd = true;
-    if (o < t.numOps) {
-      int msite[BFO_MAXLEN], mval[BFO_MAXLEN], nmod;
-      m = walk_string(t, o, cfg, N, pref[o], msite, mval, nmod);
-      isd = t.isDiag[o] != 0;
-      int nf = 0;
-      for (int q = 0; q < nmod; ++q)
-        if (mval[q] != cfg[msite[q]]) { if (nf == 0) f0 = msite[q]; else if (nf == 1) f1 = msite[q]; ++nf; }
-      if (nf > 2) atomicExch(errFlag, 1);
+  const int wpc = blockDim.x >> 5;
+  static_assert(JT == 0 || SPW == 1, "register-resident tau: one sample per warp");
+  cplx* tauAll = reinterpret_cast<cplx*>(smem_raw);                 // [wpc * SPW][M], absent when JT > 0
+  cplx* elc = tauAll + (JT > 0 ? 0 : (size_t)wpc * SPW * M);
+  int32_t* cfgAll = reinterpret_cast<int32_t*>(elc + N);
+  cplx tr[JT > 0 ? JT : 1];
+  const int jl = min(lane + 32 * (JT > 0 ? JT - 1 : 0), M - 1);   // clamped index of the ragged last chunk
+  for (int i = threadIdx.x; i < N; i += blockDim.x) elc[i] = cexp(lc[i]);
+  const long long b0 = ((long long)blockIdx.x * wpc + warp) * SPW;
+  const cplx* tau[SPW];
+  const int32_t* cfg[SPW];
+  bool ok[SPW];
+#pragma unroll
+  for (int q = 0; q < SPW; ++q) {
+    ok[q] = b0 + q < B;
+    const long long b = ok[q] ? b0 + q : B - 1;   // padding samples repeat the last one and are not written
+    cplx* tq = tauAll + (size_t)(warp * SPW + q) * M;
+    int32_t* cq = cfgAll + (size_t)(warp * SPW + q) * N;
+    if (JT > 0) {
+#pragma unroll
+      for (int k = 0; k < (JT > 0 ? JT : 1); ++k) tr[k] = (lane + 32 * k < M) ? tauG[b * M + lane + 32 * k] : cmk(0.0, 0.0);
+    } else {
+      for (int j = lane; j < M; j += 32) tq[j] = tauG[b * M + j];
     }
-    // diagonal strings are merged into one entry (branch_free.py:483-485) ...
-    diagAcc = cadd(diagAcc, warp_csum((isd && o < t.numOps) ? m : cmk(0.0, 0.0)));
-    // off-diagonal strings: warp-cooperative ratio
-    unsigned live = __ballot_sync(0xffffffffu, (o < t.numOps) && !isd && (hypot(m.x, m.y) > 1e-6));
-    while (live) {
-      const int src = __ffs(live) - 1;
-      live &= live - 1;
-      const cplx mm = cmk(__shfl_sync(0xffffffffu, m.x, src), __shfl_sync(0xffffffffu, m.y, src));
-      const int a0 = __shfl_sync(0xffffffffu, f0, src);
-      const int a1 = __shfl_sync(0xffffffffu, f1, src);
-      cplx ratio = cmk(1.0, 0.0);
-      if (a0 >= 0) {
-        const double sg0 = cfg[a0] ? -1.0 : 1.0;   // -sigma
-        const cplx* T0 = T + (size_t)a0 * M;
-        cplx lcs = lc[a0];
-        cplx p = cmk(1.0, 0.0);
-        if (a1 < 0) {
-          for (int j = lane; j < M; j += 32) {
-            cplx tt = T0[j], tj = tau[j];
-            cplx f = cmk(fma(sg0, fma(tj.x, tt.x, -tj.y * tt.y), 1.0), sg0 * fma(tj.x, tt.y, tj.y * tt.x));
-            p = cmul(p, f);
-          }
-        } else {
-          const double sg1 = cfg[a1] ? -1.0 : 1.0;
-          const cplx* T1 = T + (size_t)a1 * M;
-          lcs = cadd(lcs, lc[a1]);
-          for (int j = lane; j < M; j += 32) {
-            cplx ta = cscale(T0[j], sg0), tb = cscale(T1[j], sg1), tj = tau[j];
-            cplx n = cadd(ta, tb);
-            cplx d = cadd(cmk(1.0, 0.0), cmul(ta, tb));
-            p = cmul(p, cadd(d, cmul(tj, n)));
-          }
-        }
-        p = warp_cprod(p);
-        ratio = cmul(cexp(lcs), p);
+    for (int i = lane; i < N; i += 32) cq[i] = s[b * N + i];
+    tau[q] = tq; cfg[q] = cq;
+  }
+  __syncthreads();
+
+  cplx diagAcc[SPW], eloc[SPW];
+  cplx eloc2 = cmk(0.0, 0.0);   // register path: contributions accumulated by lanes 0 and 16 (string pairs)
+#pragma unroll
+  for (int q = 0; q < SPW; ++q) { diagAcc[q] = cmk(0.0, 0.0); eloc[q] = cmk(0.0, 0.0); }
+  for (int o0 = 0; o0 < t.numOps; o0 += 32) {
+    if (o0 > 0) __syncthreads();   // re-align the CTA's warps: same rows at the same time -> L1 sharing
+    const int o = o0 + lane;
+    cplx m[SPW];
+    int f0[SPW], f1[SPW];
+    unsigned live[SPW], any = 0;
+#pragma unroll
+    for (int q = 0; q < SPW; ++q) {
+      m[q] = cmk(0.0, 0.0); f0[q] = -1; f1[q] = -1;
+      bool isd = true;
+      if (o < t.numOps) {
+        int msite[BFO_MAXLEN], mval[BFO_MAXLEN], nmod;
+        m[q] = walk_string(t, o, cfg[q], N, pref[o], msite, mval, nmod);
+        isd = t.isDiag[o] != 0;
+        int nf = 0;
+        for (int k = 0; k < nmod; ++k)
+          if (mval[k] != cfg[q][msite[k]]) { if (nf == 0) f0[q] = msite[k]; else if (nf == 1) f1[q] = msite[k]; ++nf; }
+        if (nf > 2) atomicExch(errFlag, 1);
       }
-      eloc = cadd(eloc, cmul(mm, ratio));
+      // diagonal strings are merged into one entry (branch_free.py:483-485) ...
+      diagAcc[q] = cadd(diagAcc[q], warp_csum((isd && o < t.numOps) ? m[q] : cmk(0.0, 0.0)));
+      live[q] = __ballot_sync(0xffffffffu, (o < t.numOps) && !isd && (hypot(m[q].x, m[q].y) > 1e-6));
+      any |= live[q];
+    }
+    // off-diagonal strings: warp-cooperative ratios
+    while (any) {
+      const int src = __ffs(any) - 1;
+      any &= any - 1;
+      if (JT > 0 && any) {
+        // register path: take two single-flip strings at a time
+        const int src2 = __ffs(any) - 1;
+        const int aa = __shfl_sync(0xffffffffu, f0[0], src), ab = __shfl_sync(0xffffffffu, f0[0], src2);
+        const int a1a = __shfl_sync(0xffffffffu, f1[0], src), a1b = __shfl_sync(0xffffffffu, f1[0], src2);
+        if (aa >= 0 && ab >= 0 && a1a < 0 && a1b < 0) {
+          any &= any - 1;
+          const bool hi = lane >= 16;
+          const int mysrc = hi ? src2 : src;
+          const cplx mmh = cmk(__shfl_sync(0xffffffffu, m[0].x, mysrc), __shfl_sync(0xffffffffu, m[0].y, mysrc));
+          const double sga = cfg[0][aa] ? -1.0 : 1.0, sgb = cfg[0][ab] ? -1.0 : 1.0;
+          const cplx pr = flip_ratio_reg_dual(T + (size_t)aa * M, T + (size_t)ab * M, tr, sga, sgb, lane, jl);
+          // lanes 0 and 16 carry the two contributions; they are summed at the end
+          if ((lane & 15) == 0) eloc2 = cadd(eloc2, cmul(mmh, cmul(elc[hi ? ab : aa], pr)));
+          continue;
+        }
+      }
+      cplx mm[SPW];
+      int a0[SPW], a1[SPW];
+      bool lv[SPW];
+      bool joint = true;
+#pragma unroll
+      for (int q = 0; q < SPW; ++q) {
+        mm[q] = cmk(__shfl_sync(0xffffffffu, m[q].x, src), __shfl_sync(0xffffffffu, m[q].y, src));
+        a0[q] = __shfl_sync(0xffffffffu, f0[q], src);
+        a1[q] = __shfl_sync(0xffffffffu, f1[q], src);
+        lv[q] = (live[q] >> src) & 1u;
+        joint = joint && lv[q] && a0[q] == a0[0] && a1[q] == a1[0];
+      }
+      if (joint && a0[0] >= 0) {
+        // all samples of the warp flip the same sites: one pass over the row(s) serves them all
+        double sg0[SPW], sg1[SPW];
+#pragma unroll
+        for (int q = 0; q < SPW; ++q) {
+          sg0[q] = cfg[q][a0[0]] ? -1.0 : 1.0;   // -sigma
+          sg1[q] = (a1[0] >= 0 && cfg[q][a1[0]]) ? -1.0 : 1.0;
+        }
+        cplx p[SPW];
+        cplx e = elc[a0[0]];
+        if (a1[0] < 0) {
+          if (JT > 0) p[0] = flip_ratio_reg<false>(T + (size_t)a0[0] * M, nullptr, tr, sg0[0], sg1[0], lane, jl);
+          else flip_ratio<false, SPW>(T + (size_t)a0[0] * M, nullptr, tau, sg0, sg1, M, lane, p);
+        } else {
+          if (JT > 0) p[0] = flip_ratio_reg<true>(T + (size_t)a0[0] * M, T + (size_t)a1[0] * M, tr, sg0[0], sg1[0], lane, jl);
+          else flip_ratio<true, SPW>(T + (size_t)a0[0] * M, T + (size_t)a1[0] * M, tau, sg0, sg1, M, lane, p);
+          e = cmul(e, elc[a1[0]]);
+        }
+#pragma unroll
+        for (int q = 0; q < SPW; ++q) eloc[q] = cadd(eloc[q], cmul(mm[q], cmul(e, p[q])));
+      } else {
+#pragma unroll
+        for (int q = 0; q < SPW; ++q) {
+          if (!lv[q]) continue;
+          cplx ratio = cmk(1.0, 0.0);
+          if (a0[q] >= 0) {
+            const double g0 = cfg[q][a0[q]] ? -1.0 : 1.0;
+            const double g1 = (a1[q] >= 0 && cfg[q][a1[q]]) ? -1.0 : 1.0;
+            const cplx* tq = tau[q];
+            cplx p1;
+            cplx e = elc[a0[q]];
+            if (JT > 0) {
+              p1 = cmk(1.0, 0.0);   // unreachable: with one sample per warp a live flipping string takes the joint path
+            } else if (a1[q] < 0) {
+              flip_ratio<false, 1>(T + (size_t)a0[q] * M, nullptr, &tq, &g0, &g1, M, lane, &p1);
+            } else {
+              flip_ratio<true, 1>(T + (size_t)a0[q] * M, T + (size_t)a1[q] * M, &tq, &g0, &g1, M, lane, &p1);
+              e = cmul(e, elc[a1[q]]);
+            }
+            ratio = cmul(e, p1);
+          }
+          eloc[q] = cadd(eloc[q], cmul(mm[q], ratio));
+        }
+      }
     }
   }
-  // ... and that entry passes the same |m| > 1e-6 filter as every other one (base.py:93-103)
-  if (hypot(diagAcc.x, diagAcc.y) <= 1e-6) diagAcc = cmk(0.0, 0.0);
-  if (lane == 0) out[b] = cadd(eloc, diagAcc);
+#pragma unroll
+  for (int q = 0; q < SPW; ++q) {
+    // ... and that entry passes the same |m| > 1e-6 filter as every other one (base.py:93-103)
+    cplx d = diagAcc[q];
+    if (hypot(d.x, d.y) <= 1e-6) d = cmk(0.0, 0.0);
+    if (JT > 0) {
+      const cplx e16 = cmk(__shfl_sync(0xffffffffu, eloc2.x, 16), __shfl_sync(0xffffffffu, eloc2.y, 16));
+      eloc[q] = cadd(eloc[q], cadd(eloc2, e16));
+    }
+    if (lane == 0 && ok[q]) out[b0 + q] = cadd(eloc[q], d);
+  }
+}
+
+template <int SPW, int JT>
+int launch_eloc(BfoTables t, const int32_t* s, const cplx* tau, long long B, int N, int M, const cplx* T, const cplx* lc,
+                const cplx* pref, int numDiag, cplx* out, int* errFlag, cudaStream_t st) {
+  const size_t perSample = (JT > 0 ? 0 : (size_t)M * sizeof(cplx)) + (size_t)N * sizeof(int32_t);
+  const size_t fixed = (size_t)N * sizeof(cplx);
+  // as many samples per CTA as fit ~110 KB (two CTAs per SM); one big CTA when that leaves fewer than 4 warps
+  auto warpsFor = [&](size_t budget) {
+    long long w = ((long long)budget - (long long)fixed) / (long long)(SPW * perSample);
+    return (int)(w < 0 ? 0 : (w > EL_MAXWPC ? EL_MAXWPC : w));
+  };
+  int wpc = warpsFor(110 * 1024);
+  if (wpc < 4) wpc = warpsFor(227 * 1024);
+  if (wpc < 1) return JVMC_ERR_UNSUPPORTED;
+  const long long perCta = (long long)wpc * SPW;
+  if (B < perCta) { wpc = (int)((B + SPW - 1) / SPW); }
+  const size_t smem = fixed + (size_t)wpc * SPW * perSample;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(rbm_eloc_kernel<SPW, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const long long ctas = (B + (long long)wpc * SPW - 1) / ((long long)wpc * SPW);
+  rbm_eloc_kernel<SPW, JT><<<(unsigned)ctas, wpc * 32, smem, st>>>(t, s, tau, B, N, M, T, lc, pref, numDiag, out, errFlag);
+  JVMC_CHECK_LAUNCH();
+  return JVMC_OK;
 }
 
 BfoTables make_tables(int numOps, int len, int lDim, const int32_t* idx, const int32_t* map, const double* matEls,
@@ -279,12 +480,31 @@ extern "C" int jvmc_rbm_eloc_bfo(const int32_t* s, const double* tau, long long 
   BfoTables t = make_tables(numOps, len, lDim, idx, map, matEls, fermi, isDiag);
   const cplx* T = (const cplx*)tables;
   const cplx* lc = T + (size_t)N * M;
-  size_t smem = (size_t)EL_WPC * M * sizeof(cplx) + (size_t)EL_WPC * N * sizeof(int32_t);
-  if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(rbm_eloc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  rbm_eloc_kernel<<<(unsigned)((B + EL_WPC - 1) / EL_WPC), EL_WPC * 32, smem, (cudaStream_t)stream>>>(
-      t, s, (const cplx*)tau, B, N, M, T, lc, (const cplx*)pref, numDiag, (cplx*)out, errFlag);
-  JVMC_CHECK_LAUNCH();
-  return JVMC_OK;
+#define JVMC_ELOC(SPW, JT) launch_eloc<SPW, JT>(t, s, (const cplx*)tau, B, N, M, T, lc, (const cplx*)pref, numDiag, \
+                                               (cplx*)out, errFlag, (cudaStream_t)stream)
+  // M <= 512: tau in registers, one sample per warp (weight rows shared through L1 by the warps of a CTA)
+  switch ((M + 31) / 32) {
+    case 1: return JVMC_ELOC(1, 1);
+    case 2: return JVMC_ELOC(1, 2);
+    case 3: return JVMC_ELOC(1, 3);
+    case 4: return JVMC_ELOC(1, 4);
+    case 5: return JVMC_ELOC(1, 5);
+    case 6: return JVMC_ELOC(1, 6);
+    case 7: return JVMC_ELOC(1, 7);
+    case 8: return JVMC_ELOC(1, 8);
+    case 9: return JVMC_ELOC(1, 9);
+    case 10: return JVMC_ELOC(1, 10);
+    case 11: return JVMC_ELOC(1, 11);
+    case 12: return JVMC_ELOC(1, 12);
+    case 13: return JVMC_ELOC(1, 13);
+    case 14: return JVMC_ELOC(1, 14);
+    case 15: return JVMC_ELOC(1, 15);
+    case 16: return JVMC_ELOC(1, 16);
+    default: break;
+  }
+  // larger M: tau in shared memory, two samples per warp share every weight row in registers
+  int rc = JVMC_ELOC(2, 0);
+  if (rc == JVMC_ERR_UNSUPPORTED) rc = JVMC_ELOC(1, 0);
+  return rc;
+#undef JVMC_ELOC
 }
