@@ -271,14 +271,17 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long chain = (long long)blockIdx.x * MC_WPC + warp;
   const int N = a.N, M = a.M;
+  // tau and the row buffer are padded to 32 JT entries per warp and the padding is kept at zero: the factor of a
+  // padding unit is exactly 1 and its update 0 -> 0, so the unrolled loops need no predicates (JT = ceil(M/32))
   cplx* tauAll = reinterpret_cast<cplx*>(smem_raw);
-  cplx* bufAll = tauAll + (size_t)MC_WPC * M;
+  cplx* bufAll = tauAll + (size_t)MC_WPC * JT * 32;
   double* elc = reinterpret_cast<double*>(bufAll + (size_t)MC_WPC * JT * 32);
   uint32_t* sbitsAll = reinterpret_cast<uint32_t*>(elc + N);
   for (int i = threadIdx.x; i < N; i += MC_WPC * 32) elc[i] = exp(a.mu * a.lc[i].x);
+  for (int i = threadIdx.x; i < 2 * MC_WPC * JT * 32; i += MC_WPC * 32) tauAll[i] = cmk(0.0, 0.0);
   __syncthreads();
   if (chain >= a.C) return;  // whole warp exits together (no further block-wide barriers)
-  cplx* tau = tauAll + (size_t)warp * M;
+  cplx* tau = tauAll + (size_t)warp * JT * 32;
   cplx* buf = bufAll + (size_t)warp * JT * 32;
   uint32_t* sbits = sbitsAll + warp * 32;
   const bool hasBias = a.bias != nullptr;
@@ -323,7 +326,7 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
     const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + lane);
 #pragma unroll
     for (int k = 0; k < JT; ++k)
-      if (lane + 32 * k < M)
+      if (k < JT - 1 || lane + 32 * k < M)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + (unsigned)(k * 32 * sizeof(cplx))),
                      "l"(src + 32 * k) : "memory");
     asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -363,7 +366,7 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
     cplx tv[JT];
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 #pragma unroll
-    for (int k = 0; k < JT; ++k) tv[k] = (lane + 32 * k < M) ? buf[lane + 32 * k] : cmk(0.0, 0.0);
+    for (int k = 0; k < JT; ++k) tv[k] = buf[lane + 32 * k];
     uint4 rn = rc;
     if (st + 1 < total) {
       draw(st + 1, rn);
@@ -378,7 +381,7 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
       double p0 = 1.0, p1 = 1.0;
 #pragma unroll
       for (int k = 0; k < JT; ++k) {
-        const cplx tj = (lane + 32 * k < M) ? tau[lane + 32 * k] : cmk(0.0, 0.0);
+        const cplx tj = tau[lane + 32 * k];
         const double re = fma(tj.x, tv[k].x, -tj.y * tv[k].y);
         const double im = fma(tj.x, tv[k].y, tj.y * tv[k].x);
         const double fr = fma(sga, re, 1.0);
@@ -394,12 +397,10 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
         const double gsn = g ? -1.0 : 1.0;   // Z2 flip without bias: tau -> -tau
 #pragma unroll
         for (int k = 0; k < JT; ++k) {
-          if (lane + 32 * k < M) {
-            const cplx tj = tau[lane + 32 * k];
-            const cplx n = cscale(tv[k], sga);
-            const cplx tn = cdiv(cadd(tj, n), cadd(cmk(1.0, 0.0), cmul(tj, n)));
-            tau[lane + 32 * k] = cscale(tn, gsn);
-          }
+          const cplx tj = tau[lane + 32 * k];
+          const cplx n = cscale(tv[k], sga);
+          const cplx tn = cdiv(cadd(tj, n), cadd(cmk(1.0, 0.0), cmul(tj, n)));
+          tau[lane + 32 * k] = cscale(tn, gsn);
         }
       }
     } else {
@@ -470,8 +471,7 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
 
 template <int JT>
 int launch_flip(const McmcArgs& a, cudaStream_t stream) {
-  size_t smem = (size_t)MC_WPC * a.M * sizeof(cplx) + (size_t)MC_WPC * JT * 32 * sizeof(cplx) + (size_t)a.N * sizeof(double) +
-                MC_WPC * 32 * sizeof(uint32_t);
+  size_t smem = (size_t)2 * MC_WPC * JT * 32 * sizeof(cplx) + (size_t)a.N * sizeof(double) + MC_WPC * 32 * sizeof(uint32_t);
   if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(rbm_mcmc_flip_kernel<JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -507,11 +507,13 @@ extern "C" int jvmc_rbm_mcmc(int32_t* states, long long C, int N, int M, const d
   a.refreshEvery = refreshEvery > 0 ? refreshEvery : 1;
   a.out = out; a.counters = counters;
   if (proposer != 2 && M <= 512 && !g_mcmc_generic) {
-    const int jt = (M + 31) / 32;
-    if (jt <= 4) return launch_flip<4>(a, (cudaStream_t)stream);
-    if (jt <= 8) return launch_flip<8>(a, (cudaStream_t)stream);
-    if (jt <= 13) return launch_flip<13>(a, (cudaStream_t)stream);
-    return launch_flip<16>(a, (cudaStream_t)stream);
+    switch ((M + 31) / 32) {
+#define JVMC_FLIP(J) case J: return launch_flip<J>(a, (cudaStream_t)stream)
+      JVMC_FLIP(1); JVMC_FLIP(2); JVMC_FLIP(3); JVMC_FLIP(4); JVMC_FLIP(5); JVMC_FLIP(6); JVMC_FLIP(7); JVMC_FLIP(8);
+      JVMC_FLIP(9); JVMC_FLIP(10); JVMC_FLIP(11); JVMC_FLIP(12); JVMC_FLIP(13); JVMC_FLIP(14); JVMC_FLIP(15);
+      default: return launch_flip<16>(a, (cudaStream_t)stream);
+#undef JVMC_FLIP
+    }
   }
   size_t smem = (size_t)MC_WPC * M * sizeof(cplx) + MC_WPC * 32 * sizeof(uint32_t);
   if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
