@@ -334,7 +334,11 @@ def main():
         (E, G, *_), phases["moments_F_ms"] = timed(mom)
         _, phases["gram_S_ms"] = timed(lambda: G.gram_A())
         phases["acceptance"] = float(smp.acceptance_ratio())
-        del E, G, Eloc, s, logPsi, p
+        # logpsi alone (it is part of sampling_ms: the sampler re-evaluates logpsi of the emitted configurations)
+        flat_ = s.reshape(s.shape[0] * s.shape[1], -1).contiguous()
+        Wd_, bd_ = psi._cW()
+        _, phases["logpsi_ms"] = timed(lambda: K.rbm_logpsi(flat_, Wd_, bd_))
+        del E, G, Eloc, s, logPsi, p, flat_
     torch.cuda.empty_cache()
 
     # ---- roofline of the dominant kernel (Gram): fp64 tensor pipe
@@ -422,6 +426,42 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
+    # ---- the fp64-pipe kernels (report achieved fp64 flop/s AND achieved HBM bytes/s, from the algorithmic
+    # figures, against the measured peaks; the binding resource of all of them is the fp64 pipe, not HBM)
+    kernels = None
+    if phases:
+        FP64_PEAK = 36.3       # TFLOP/s, DFMA issue-rate probe tools/fp64_probe.cu on this pool's B200 (profiles/README.md)
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                hbm_peak, hbm_src = float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            hbm_peak, hbm_src = 6550.0, "fallback of B200_PROFILING.md"
+        acc = phases["acceptance"]
+        spc = nLocal // chains
+        props = chains * N * (25 + spc)
+        Kmax = N + 1
+
+        def entry(name, ms, flop, hbm_bytes, note):
+            tf, gbs = flop / (ms * 1e-3) / 1e12, hbm_bytes / (ms * 1e-3) / 1e9
+            return {"kernel": name, "ms": ms, "bound": "fp64", "fp64_tflops": tf, "fp64_frac": tf / FP64_PEAK,
+                    "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "algorithmic": note}
+        t_mc = max(phases["sampling_ms"] - phases["logpsi_ms"], 1e-6)
+        kernels = {
+            "fp64_peak_tflops": FP64_PEAK, "fp64_peak_source": "DFMA issue-rate probe (tools/fp64_probe.cu, 36.3 TFLOP/s measured)",
+            "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+            "list": [
+                entry("rbm_mcmc_flip_kernel (sampler sweep incl. %d thermalisation sweeps)" % 25, t_mc,
+                      props * M * (14.0 + 30.0 * acc), nLocal * (4.0 * N + 16.0),
+                      "K M (14 + 30 acc) flop and 4N+16 HBM bytes per emitted sample; %.3g proposals, weight rows "
+                      "stream from L2 (%.1f TB/s)" % (props, props * M * 16.0 / (t_mc * 1e-3) / 1e12)),
+                entry("rbm_logpsi_kernel", phases["logpsi_ms"], nLocal * (4.0 * N * M + 100.0 * M),
+                      nLocal * (4.0 * N + 16.0 * M + 16.0), "4NM + ~100M flop, 4N + 16M + 16 bytes per sample"),
+                entry("rbm_eloc_kernel (fused E_loc)", phases["eloc_ms"], nLocal * 14.0 * N * M,
+                      nLocal * (4.0 * N + 16.0 * M + 16.0), "14 N M flop, 4N + 16M + 16 bytes per sample"),
+                entry("rbm_moments_kernel x2 + reductions (<O>, F)", phases["moments_F_ms"], nLocal * 16.0 * N * M,
+                      2.0 * nLocal * (4.0 * N + 16.0 * M + 24.0), "8 N M flop and 4N + 16M + 24 bytes per sample and pass"),
+            ]}
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t, detail = cpu_reference_step(shape, g, alpha, bias, 64, 32)
         cpu = {"value": 64 / t, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
@@ -441,7 +481,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "note": "parameters H2D from pinned memory; <E>, VarE, F D2H; S stays on device for the solver"},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-                "phases_ms": phases, "energy_mean": [energy.real, energy.imag], "tdvp_step": tdvp_info}
+                "phases_ms": phases, "kernels": kernels, "energy_mean": [energy.real, energy.imag], "tdvp_step": tdvp_info}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -150,3 +150,20 @@ def test_sampler_argument_validation():
         jVMC.sampler.MCSampler(FakeNet(), (4,), 0, updateProposer=None)
     with pytest.raises(NotImplementedError):
         jVMC.sampler.MCSampler(FakeNet(), (4,), 0, updateProposer=lambda k, s, i: s)
+
+
+@pytest.mark.parametrize("rows,cols", [(64, 40), (64, 32), (64, 48)])
+@pytest.mark.parametrize("M", [1, 3, 4, 7, 40, 63, 64, 65, 100, 130, 333, 400])
+def test_i8_gram_tile_list_covers_lower_triangle_once(M, rows, cols):
+    """The INT8 Gram kernel writes (j, l <= j) of every site pair once per tile that covers it and ADDS on later
+    launches, so the host-built tile list must cover the lower triangle exactly once."""
+    from vmc_jax_b200.kernels import i8_tile_list
+    cover = np.zeros((M, M), dtype=np.int32)
+    for rg, J, lo, hi in i8_tile_list(M, rows, cols):
+        assert rg % 1 == 0 and 4 * rg <= lo and hi <= 4 * rg + rows      # written rows lie inside the tile
+        j = np.arange(max(lo, 4 * rg), min(hi, M))
+        l = np.arange(cols * J, min(cols * J + cols, M))
+        jj, ll = np.meshgrid(j, l, indexing="ij")
+        cover[jj[ll <= jj], ll[ll <= jj]] += 1
+    want = np.tril(np.ones((M, M), dtype=np.int32))
+    assert np.array_equal(cover, want)

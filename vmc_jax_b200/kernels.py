@@ -190,22 +190,23 @@ def rbm_gram_S(Y, sigT, mu, alpha, kappa, out=None, tile=0):
 _I8_TILES = {}
 
 
-def i8_tile_list(M):
-    """Tiles (rowGroup, J, jlo, jhi) of 128 x 80 real columns (64 x 40 complex) covering every (j, l <= j) once.
+def i8_tile_list(M, rows=64, cols=40):
+    """Tiles (rowGroup, J, jlo, jhi) of rows x cols complex elements (the kernel's tile is 128 x 80 real columns =
+    64 x 40 complex) covering every (j, l <= j) exactly once.
 
-    Full 64-row blocks are anchored at the END of the row range (the block ending at row e needs ceil(e/40) column
-    tiles), so the ragged remainder sits at rows [0, o) where it needs only ceil(o/40) tiles instead of a full
+    Full row blocks are anchored at the END of the row range (the block ending at row e needs ceil(e/cols) column
+    tiles), so the ragged remainder sits at rows [0, o) where it needs only ceil(o/cols) tiles instead of a full
     tile row: 39 tiles at M = 400 (ideal 31.25; 46 with the remainder at the bottom)."""
     M4 = (M + 3) // 4 * 4            # row blocks start on 8-real-row (4 complex) boundaries of the digit layout
-    nFull = M4 // 64
-    o = M4 - 64 * nFull
+    nFull = M4 // rows
+    o = M4 - rows * nFull
     tl = []
-    for J in range((min(o, M) + 39) // 40):
+    for J in range((min(o, M) + cols - 1) // cols):
         tl.append((0, J, 0, min(o, M)))
     for b in range(nFull):
-        lo = o + 64 * b
-        hi = min(lo + 64, M)
-        for J in range((hi + 39) // 40):
+        lo = o + rows * b
+        hi = min(lo + rows, M)
+        for J in range((hi + cols - 1) // cols):
             tl.append((lo // 4, J, lo, hi))
     return tl
 
