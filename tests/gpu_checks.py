@@ -327,10 +327,14 @@ def run_sampler(W, b, C, numSamples, proposer="spin_flip", mu=2.0, seed=4321, K_
 
 
 def check_sampler_chi2(N=4, M=2, weights=None, proposer="spin_flip", mu=2.0, C=592, numSamples=1_000_000,
-                       bias=False, seed=4321, sector=False, refreshEvery=1):
-    """Sampled distribution vs ExactSampler probabilities, chi-squared p-value > 1e-3 (north_star)."""
+                       bias=False, seed=4321, sector=False, refreshEvery=1, amp=None):
+    """Sampled distribution vs ExactSampler probabilities, chi-squared p-value > 1e-3 (north_star).
+    amp: amplitude of the uniform weight distribution (default 1/sqrt(N))."""
     if weights is None:
         W, b = orbm.init_o1(N, M, bias, 17)
+        if amp is not None:
+            W = W * (amp * np.sqrt(N))
+            b = None if b is None else b * (amp * np.sqrt(N))
     else:
         W, b = orbm.unflatten_params(np.asarray(weights), N, M, bias)
     basis = osamp.basis_states(N)

@@ -76,6 +76,14 @@ def test_eloc_fused_and_generic(name, bias):
     G.check_eloc(G.operator_zoo(N)[name], N=N, M=20, bias=bias)
 
 
+@pytest.mark.parametrize("M,bias", [(33, False), (95, True), (512, False), (600, False), (1100, True), (2500, False),
+                                    (4500, False)])
+@pytest.mark.parametrize("name", ["tfim1d", "heis", "splus"])
+def test_eloc_hidden_unit_splits(name, M, bias):
+    """ragged unrolls (M not a multiple of 32), 2 / 4 / 8 warps per sample (M > 512) and the shared-memory path (M > 4096)."""
+    G.check_eloc(G.operator_zoo(6)[name], N=6, M=M, B=37, bias=bias)
+
+
 def test_eloc_2d_tfim_config2_shape():
     G.check_eloc(obfo.tfim_strings((10, 10), 3.04), N=100, M=400, B=64)
 
@@ -144,6 +152,14 @@ def test_sampler_chi2_z2(bias):
 @pytest.mark.parametrize("bias", [False, True])
 def test_sampler_chi2_zero_mag(bias):
     G.check_sampler_chi2(N=8, M=16, proposer="spin_flip_zeroMag", bias=bias, sector=True, numSamples=1_000_000)
+
+
+@pytest.mark.parametrize("M,proposer,bias", [(70, "spin_flip", False), (600, "spin_flip", False),
+                                             (1100, "spin_flip_Z2", True), (2100, "spin_flip_Z2", False)])
+def test_sampler_chi2_hidden_unit_splits(M, proposer, bias):
+    """ragged unroll and 2 / 4 / 8 warps per chain (M > 512): same chi-squared bar; weights scaled so that
+    theta stays O(1)."""
+    G.check_sampler_chi2(N=6, M=M, proposer=proposer, bias=bias, numSamples=500_000, C=296, amp=(6 * M) ** -0.25)
 
 
 def test_sampler_mu1_and_rare_refresh():

@@ -179,24 +179,26 @@ __device__ __forceinline__ void flip_ratio(const cplx* __restrict__ T0, const cp
 // traffic at all in the inner loop, which otherwise binds before the fp64 pipe does (16 B of tau + 16 B of T per
 // ten DFMA).  JT = ceil(M / 32) exactly, so only the last k can run past the row: its index is clamped (jl) and its
 // tau register is zero, which makes the factor exactly 1 -- no predicates or selects in the unrolled loop.
-template <bool TWO, int JT>
+// With WPS warps per sample the 32-unit chunks are dealt round-robin (chunk c -> warp c % WPS), which keeps the
+// "only the last k can be ragged" property; j0 = 32 sw + lane is the lane's first unit, jl the clamped last one.
+template <bool TWO, int JT, int WPS>
 __device__ __forceinline__ cplx flip_ratio_reg(const cplx* __restrict__ T0, const cplx* __restrict__ T1,
-                                               const cplx (&tr)[JT], double sg0, double sg1, int lane, int jl) {
+                                               const cplx (&tr)[JT], double sg0, double sg1, int lane, int j0, int jl) {
   cplx pa = cmk(1.0, 0.0), pb = cmk(1.0, 0.0);
-  const cplx* p0 = T0 + lane;
-  const cplx* p1 = TWO ? T1 + lane : nullptr;
+  const cplx* p0 = T0 + j0;
+  const cplx* p1 = TWO ? T1 + j0 : nullptr;
 #pragma unroll
   for (int k = 0; k < JT; ++k) {
-    const cplx t0 = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? p0 + 32 * k : T0 + jl));
+    const cplx t0 = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? p0 + 32 * WPS * k : T0 + jl));
     const cplx tj = tr[k];
     cplx f;
     if (!TWO) {
       f = cmk(fma(sg0, fma(tj.x, t0.x, -tj.y * t0.y), 1.0), sg0 * fma(tj.x, t0.y, tj.y * t0.x));
     } else {
-      const cplx t1 = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? p1 + 32 * k : T1 + jl));
+      const cplx t1 = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? p1 + 32 * WPS * k : T1 + jl));
       const cplx ta = cscale(t0, sg0), tb = cscale(t1, sg1);
       f = cadd(cadd(cmk(1.0, 0.0), cmul(ta, tb)), cmul(tj, cadd(ta, tb)));
-      if (k == JT - 1 && lane + 32 * k != jl) f = cmk(1.0, 0.0);   // padding lane of the ragged tail
+      if (k == JT - 1 && j0 + 32 * WPS * k != jl) f = cmk(1.0, 0.0);   // padding lane of the ragged tail
     }
     if (k & 1) pb = cmul(pb, f); else pa = cmul(pa, f);
   }
@@ -206,16 +208,17 @@ __device__ __forceinline__ cplx flip_ratio_reg(const cplx* __restrict__ T0, cons
 // Two single-flip strings (sites a and b) of the same sample at once: four independent product chains hide the
 // fp64 latency, and the two warp reductions are folded into one butterfly -- after the first exchange lanes 0-15
 // carry string a and lanes 16-31 string b.  Returns, in every lane, the product of the string its half belongs to.
-template <int JT>
+template <int JT, int WPS>
 __device__ __forceinline__ cplx flip_ratio_reg_dual(const cplx* __restrict__ Ta, const cplx* __restrict__ Tb,
-                                                    const cplx (&tr)[JT], double sga, double sgb, int lane, int jl) {
+                                                    const cplx (&tr)[JT], double sga, double sgb, int lane, int j0,
+                                                    int jl) {
   cplx pa0 = cmk(1.0, 0.0), pa1 = cmk(1.0, 0.0), pb0 = cmk(1.0, 0.0), pb1 = cmk(1.0, 0.0);
-  const cplx* qa = Ta + lane;
-  const cplx* qb = Tb + lane;
+  const cplx* qa = Ta + j0;
+  const cplx* qb = Tb + j0;
 #pragma unroll
   for (int k = 0; k < JT; ++k) {
-    const cplx ta = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? qa + 32 * k : Ta + jl));
-    const cplx tb = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? qb + 32 * k : Tb + jl));
+    const cplx ta = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? qa + 32 * WPS * k : Ta + jl));
+    const cplx tb = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? qb + 32 * WPS * k : Tb + jl));
     const cplx tj = tr[k];
     const cplx fa = cmk(fma(sga, fma(tj.x, ta.x, -tj.y * ta.y), 1.0), sga * fma(tj.x, ta.y, tj.y * ta.x));
     const cplx fb = cmk(fma(sgb, fma(tj.x, tb.x, -tj.y * tb.y), 1.0), sgb * fma(tj.x, tb.y, tj.y * tb.x));
@@ -232,22 +235,29 @@ __device__ __forceinline__ cplx flip_ratio_reg_dual(const cplx* __restrict__ Ta,
   return v;
 }
 
-template <int SPW, int JT>
-__global__ void __launch_bounds__(EL_MAXWPC * 32)
+template <int SPW, int JT, int WPS>
+__global__ void __launch_bounds__(WPS > 1 ? 512 : EL_MAXWPC * 32)
 rbm_eloc_kernel(BfoTables t, const int32_t* __restrict__ s, const cplx* __restrict__ tauG, long long B, int N, int M,
                 const cplx* __restrict__ T, const cplx* __restrict__ lc, const cplx* __restrict__ pref,
                 int numDiag, cplx* __restrict__ out, int* __restrict__ errFlag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpc = blockDim.x >> 5;
-  static_assert(JT == 0 || SPW == 1, "register-resident tau: one sample per warp");
+  static_assert(JT == 0 || SPW == 1, "register-resident tau: one sample per warp (group)");
+  static_assert(WPS == 1 || JT > 0, "several warps per sample only on the register path");
   cplx* tauAll = reinterpret_cast<cplx*>(smem_raw);                 // [wpc * SPW][M], absent when JT > 0
   cplx* elc = tauAll + (JT > 0 ? 0 : (size_t)wpc * SPW * M);
-  int32_t* cfgAll = reinterpret_cast<int32_t*>(elc + N);
-  cplx tr[JT > 0 ? JT : 1];
-  const int jl = min(lane + 32 * (JT > 0 ? JT - 1 : 0), M - 1);   // clamped index of the ragged last chunk
+  cplx* xch = elc + N;                                              // [wpc / WPS][2][WPS][2] partial products (WPS > 1)
+  int32_t* cfgAll = reinterpret_cast<int32_t*>(xch + (WPS > 1 ? 4 * wpc : 0));
+  constexpr int JR = (JT > 0) ? JT : 1;
+  cplx tr[JR];
+  const int sw = warp % WPS, grp = warp / WPS;                      // slice / sample group of this warp
+  const int j0 = 32 * sw + lane;                                    // first hidden unit of the lane (chunks round-robin)
+  const int jlast = j0 + 32 * WPS * (JT > 0 ? JT - 1 : 0);
+  const int jl = min(jlast, M - 1);                                 // clamped index of the (possibly ragged) last chunk
+  unsigned xpar = 0;                                                // parity of the exchange slots
   for (int i = threadIdx.x; i < N; i += blockDim.x) elc[i] = cexp(lc[i]);
-  const long long b0 = ((long long)blockIdx.x * wpc + warp) * SPW;
+  const long long b0 = ((long long)blockIdx.x * (wpc / WPS) + grp) * SPW;
   const cplx* tau[SPW];
   const int32_t* cfg[SPW];
   bool ok[SPW];
@@ -259,7 +269,8 @@ rbm_eloc_kernel(BfoTables t, const int32_t* __restrict__ s, const cplx* __restri
     int32_t* cq = cfgAll + (size_t)(warp * SPW + q) * N;
     if (JT > 0) {
 #pragma unroll
-      for (int k = 0; k < (JT > 0 ? JT : 1); ++k) tr[k] = (lane + 32 * k < M) ? tauG[b * M + lane + 32 * k] : cmk(0.0, 0.0);
+      for (int k = 0; k < (JT > 0 ? JT : 1); ++k)
+        tr[k] = (j0 + 32 * WPS * k < M) ? tauG[b * M + j0 + 32 * WPS * k] : cmk(0.0, 0.0);
     } else {
       for (int j = lane; j < M; j += 32) tq[j] = tauG[b * M + j];
     }
@@ -268,6 +279,18 @@ rbm_eloc_kernel(BfoTables t, const int32_t* __restrict__ s, const cplx* __restri
   }
   __syncthreads();
 
+  // product over the WPS warps of a sample group: slot [parity][warp][which]; one named barrier per exchange
+  // (all warps of a group follow the same control flow: same sample, same strings)
+  auto group_prod = [&](cplx v, int which) {
+    cplx* slot = xch + ((size_t)(grp * 2 + (xpar & 1)) * WPS) * 2;
+    xpar ^= 1;
+    if ((lane & 15) == 0) slot[sw * 2 + (lane >> 4)] = v;   // lane 0: string a (or the only one), lane 16: string b
+    asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "r"(WPS * 32) : "memory");
+    cplx r = slot[which];
+#pragma unroll
+    for (int w = 1; w < WPS; ++w) r = cmul(r, slot[w * 2 + which]);
+    return r;
+  };
   cplx diagAcc[SPW], eloc[SPW];
   cplx eloc2 = cmk(0.0, 0.0);   // register path: contributions accumulated by lanes 0 and 16 (string pairs)
 #pragma unroll
@@ -311,9 +334,11 @@ rbm_eloc_kernel(BfoTables t, const int32_t* __restrict__ s, const cplx* __restri
           const int mysrc = hi ? src2 : src;
           const cplx mmh = cmk(__shfl_sync(0xffffffffu, m[0].x, mysrc), __shfl_sync(0xffffffffu, m[0].y, mysrc));
           const double sga = cfg[0][aa] ? -1.0 : 1.0, sgb = cfg[0][ab] ? -1.0 : 1.0;
-          const cplx pr = flip_ratio_reg_dual(T + (size_t)aa * M, T + (size_t)ab * M, tr, sga, sgb, lane, jl);
-          // lanes 0 and 16 carry the two contributions; they are summed at the end
-          if ((lane & 15) == 0) eloc2 = cadd(eloc2, cmul(mmh, cmul(elc[hi ? ab : aa], pr)));
+          cplx pr = flip_ratio_reg_dual<JR, WPS>(T + (size_t)aa * M, T + (size_t)ab * M, tr, sga, sgb, lane,
+                                                              j0, jl);
+          if (WPS > 1) pr = group_prod(pr, hi ? 1 : 0);
+          // lanes 0 and 16 (of the group's first warp) carry the two contributions; they are summed at the end
+          if ((lane & 15) == 0 && sw == 0) eloc2 = cadd(eloc2, cmul(mmh, cmul(elc[hi ? ab : aa], pr)));
           continue;
         }
       }
@@ -340,10 +365,17 @@ rbm_eloc_kernel(BfoTables t, const int32_t* __restrict__ s, const cplx* __restri
         cplx p[SPW];
         cplx e = elc[a0[0]];
         if (a1[0] < 0) {
-          if (JT > 0) p[0] = flip_ratio_reg<false>(T + (size_t)a0[0] * M, nullptr, tr, sg0[0], sg1[0], lane, jl);
+          if (JT > 0) {
+            p[0] = flip_ratio_reg<false, JR, WPS>(T + (size_t)a0[0] * M, nullptr, tr, sg0[0], sg1[0], lane, j0, jl);
+            if (WPS > 1) p[0] = group_prod(p[0], 0);
+          }
           else flip_ratio<false, SPW>(T + (size_t)a0[0] * M, nullptr, tau, sg0, sg1, M, lane, p);
         } else {
-          if (JT > 0) p[0] = flip_ratio_reg<true>(T + (size_t)a0[0] * M, T + (size_t)a1[0] * M, tr, sg0[0], sg1[0], lane, jl);
+          if (JT > 0) {
+            p[0] = flip_ratio_reg<true, JR, WPS>(T + (size_t)a0[0] * M, T + (size_t)a1[0] * M, tr, sg0[0], sg1[0],
+                                                         lane, j0, jl);
+            if (WPS > 1) p[0] = group_prod(p[0], 0);
+          }
           else flip_ratio<true, SPW>(T + (size_t)a0[0] * M, T + (size_t)a1[0] * M, tau, sg0, sg1, M, lane, p);
           e = cmul(e, elc[a1[0]]);
         }
@@ -384,30 +416,43 @@ rbm_eloc_kernel(BfoTables t, const int32_t* __restrict__ s, const cplx* __restri
       const cplx e16 = cmk(__shfl_sync(0xffffffffu, eloc2.x, 16), __shfl_sync(0xffffffffu, eloc2.y, 16));
       eloc[q] = cadd(eloc[q], cadd(eloc2, e16));
     }
-    if (lane == 0 && ok[q]) out[b0 + q] = cadd(eloc[q], d);
+    if (lane == 0 && sw == 0 && ok[q]) out[b0 + q] = cadd(eloc[q], d);
   }
 }
 
-template <int SPW, int JT>
+template <int SPW, int JT, int WPS>
 int launch_eloc(BfoTables t, const int32_t* s, const cplx* tau, long long B, int N, int M, const cplx* T, const cplx* lc,
                 const cplx* pref, int numDiag, cplx* out, int* errFlag, cudaStream_t st) {
-  const size_t perSample = (JT > 0 ? 0 : (size_t)M * sizeof(cplx)) + (size_t)N * sizeof(int32_t);
-  const size_t fixed = (size_t)N * sizeof(cplx);
-  // as many samples per CTA as fit ~110 KB (two CTAs per SM); one big CTA when that leaves fewer than 4 warps
-  auto warpsFor = [&](size_t budget) {
-    long long w = ((long long)budget - (long long)fixed) / (long long)(SPW * perSample);
-    return (int)(w < 0 ? 0 : (w > EL_MAXWPC ? EL_MAXWPC : w));
-  };
-  int wpc = warpsFor(110 * 1024);
-  if (wpc < 4) wpc = warpsFor(227 * 1024);
-  if (wpc < 1) return JVMC_ERR_UNSUPPORTED;
-  const long long perCta = (long long)wpc * SPW;
-  if (B < perCta) { wpc = (int)((B + SPW - 1) / SPW); }
-  const size_t smem = fixed + (size_t)wpc * SPW * perSample;
+  int wpc;
+  size_t smem;
+  if (JT > 0) {
+    // register path: shared memory only holds the configurations (per warp), exp(lc) and the exchange slots
+    const int maxw = WPS > 1 ? 16 : EL_MAXWPC;
+    long long groups = maxw / WPS;
+    if (B < groups) groups = B;
+    wpc = (int)groups * WPS;
+    smem = (size_t)N * sizeof(cplx) + (WPS > 1 ? (size_t)4 * wpc * sizeof(cplx) : 0) + (size_t)wpc * N * sizeof(int32_t);
+    if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
+  } else {
+    const size_t perSample = (size_t)M * sizeof(cplx) + (size_t)N * sizeof(int32_t);
+    const size_t fixed = (size_t)N * sizeof(cplx);
+    // as many samples per CTA as fit ~110 KB (two CTAs per SM); one big CTA when that leaves fewer than 4 warps
+    auto warpsFor = [&](size_t budget) {
+      long long w = ((long long)budget - (long long)fixed) / (long long)(SPW * perSample);
+      return (int)(w < 0 ? 0 : (w > EL_MAXWPC ? EL_MAXWPC : w));
+    };
+    wpc = warpsFor(110 * 1024);
+    if (wpc < 4) wpc = warpsFor(227 * 1024);
+    if (wpc < 1) return JVMC_ERR_UNSUPPORTED;
+    if (B < (long long)wpc * SPW) wpc = (int)((B + SPW - 1) / SPW);
+    smem = fixed + (size_t)wpc * SPW * perSample;
+  }
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(rbm_eloc_kernel<SPW, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const long long ctas = (B + (long long)wpc * SPW - 1) / ((long long)wpc * SPW);
-  rbm_eloc_kernel<SPW, JT><<<(unsigned)ctas, wpc * 32, smem, st>>>(t, s, tau, B, N, M, T, lc, pref, numDiag, out, errFlag);
+    cudaFuncSetAttribute(rbm_eloc_kernel<SPW, JT, WPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const long long perCta = (long long)(wpc / WPS) * SPW;
+  const long long ctas = (B + perCta - 1) / perCta;
+  rbm_eloc_kernel<SPW, JT, WPS><<<(unsigned)ctas, wpc * 32, smem, st>>>(t, s, tau, B, N, M, T, lc, pref, numDiag, out,
+                                                                     errFlag);
   JVMC_CHECK_LAUNCH();
   return JVMC_OK;
 }
@@ -480,31 +525,28 @@ extern "C" int jvmc_rbm_eloc_bfo(const int32_t* s, const double* tau, long long 
   BfoTables t = make_tables(numOps, len, lDim, idx, map, matEls, fermi, isDiag);
   const cplx* T = (const cplx*)tables;
   const cplx* lc = T + (size_t)N * M;
-#define JVMC_ELOC(SPW, JT) launch_eloc<SPW, JT>(t, s, (const cplx*)tau, B, N, M, T, lc, (const cplx*)pref, numDiag, \
-                                               (cplx*)out, errFlag, (cudaStream_t)stream)
-  // M <= 512: tau in registers, one sample per warp (weight rows shared through L1 by the warps of a CTA)
-  switch ((M + 31) / 32) {
-    case 1: return JVMC_ELOC(1, 1);
-    case 2: return JVMC_ELOC(1, 2);
-    case 3: return JVMC_ELOC(1, 3);
-    case 4: return JVMC_ELOC(1, 4);
-    case 5: return JVMC_ELOC(1, 5);
-    case 6: return JVMC_ELOC(1, 6);
-    case 7: return JVMC_ELOC(1, 7);
-    case 8: return JVMC_ELOC(1, 8);
-    case 9: return JVMC_ELOC(1, 9);
-    case 10: return JVMC_ELOC(1, 10);
-    case 11: return JVMC_ELOC(1, 11);
-    case 12: return JVMC_ELOC(1, 12);
-    case 13: return JVMC_ELOC(1, 13);
-    case 14: return JVMC_ELOC(1, 14);
-    case 15: return JVMC_ELOC(1, 15);
-    case 16: return JVMC_ELOC(1, 16);
-    default: break;
+#define JVMC_ELOC(SPW, JT, WPS) launch_eloc<SPW, JT, WPS>(t, s, (const cplx*)tau, B, N, M, T, lc, (const cplx*)pref, \
+                                                         numDiag, (cplx*)out, errFlag, (cudaStream_t)stream)
+#define JVMC_ELOC_JT(WPS)                                                                                          \
+  switch ((M + 32 * WPS - 1) / (32 * WPS)) {                                                                       \
+    case 1: return JVMC_ELOC(1, 1, WPS);   case 2: return JVMC_ELOC(1, 2, WPS);   case 3: return JVMC_ELOC(1, 3, WPS);   \
+    case 4: return JVMC_ELOC(1, 4, WPS);   case 5: return JVMC_ELOC(1, 5, WPS);   case 6: return JVMC_ELOC(1, 6, WPS);   \
+    case 7: return JVMC_ELOC(1, 7, WPS);   case 8: return JVMC_ELOC(1, 8, WPS);   case 9: return JVMC_ELOC(1, 9, WPS);   \
+    case 10: return JVMC_ELOC(1, 10, WPS); case 11: return JVMC_ELOC(1, 11, WPS); case 12: return JVMC_ELOC(1, 12, WPS); \
+    case 13: return JVMC_ELOC(1, 13, WPS); case 14: return JVMC_ELOC(1, 14, WPS); case 15: return JVMC_ELOC(1, 15, WPS); \
+    case 16: return JVMC_ELOC(1, 16, WPS);                                                                         \
+    default: break;                                                                                                \
   }
+  // tau in registers: one warp per sample up to M = 512, then 2 / 4 / 8 warps per sample (M <= 4096); the weight
+  // rows are shared through L1 by the warps of a CTA
+  if (M <= 512) { JVMC_ELOC_JT(1) }
+  else if (M <= 1024) { JVMC_ELOC_JT(2) }
+  else if (M <= 2048) { JVMC_ELOC_JT(4) }
+  else if (M <= 4096) { JVMC_ELOC_JT(8) }
   // larger M: tau in shared memory, two samples per warp share every weight row in registers
-  int rc = JVMC_ELOC(2, 0);
-  if (rc == JVMC_ERR_UNSUPPORTED) rc = JVMC_ELOC(1, 0);
+  int rc = JVMC_ELOC(2, 0, 1);
+  if (rc == JVMC_ERR_UNSUPPORTED) rc = JVMC_ELOC(1, 0, 1);
   return rc;
+#undef JVMC_ELOC_JT
 #undef JVMC_ELOC
 }

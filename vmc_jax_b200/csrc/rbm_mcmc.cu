@@ -264,23 +264,32 @@ rbm_mcmc_kernel(McmcArgs a) {
 //  * Philox is evaluated once per 32 steps (lane l computes step base + l) and broadcast by shuffles;
 //  * exp(mu Re lc_a) comes from a per-CTA shared table instead of an exp per proposal.
 // Same RNG counters as the generic kernel: the accept/reject sequence is identical up to floating-point rounding.
-template <int JT>
-__global__ void __launch_bounds__(MC_WPC * 32)
+// WPCH > 1 (large M): one chain per CTA, its hidden units split over WPCH warps (slices of 32 JT units); the
+// partial products meet in shared memory (one __syncthreads per Metropolis step, double-buffered slots) and every
+// warp takes the same accept decision from the same RNG counters.
+template <int JT, int WPCH>
+__global__ void __launch_bounds__(WPCH == 1 ? MC_WPC * 32 : WPCH * 32)
 rbm_mcmc_flip_kernel(McmcArgs a) {
+  constexpr int CPB = (WPCH == 1) ? MC_WPC : 1;    // chains per CTA
+  constexpr int NW = CPB * WPCH;                   // warps per CTA
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long chain = (long long)blockIdx.x * MC_WPC + warp;
+  const int cw = (WPCH == 1) ? warp : 0;           // chain of this warp within the CTA
+  const int sw = (WPCH == 1) ? 0 : warp;           // slice of the hidden units this warp owns
+  const long long chain = (long long)blockIdx.x * CPB + cw;
   const int N = a.N, M = a.M;
+  const int jbase = sw * 32 * JT;                  // first hidden unit of the slice
   // tau and the row buffer are padded to 32 JT entries per warp and the padding is kept at zero: the factor of a
-  // padding unit is exactly 1 and its update 0 -> 0, so the unrolled loops need no predicates (JT = ceil(M/32))
+  // padding unit is exactly 1 and its update 0 -> 0, so the unrolled loops need no predicates
   cplx* tauAll = reinterpret_cast<cplx*>(smem_raw);
-  cplx* bufAll = tauAll + (size_t)MC_WPC * JT * 32;
-  double* elc = reinterpret_cast<double*>(bufAll + (size_t)MC_WPC * JT * 32);
-  uint32_t* sbitsAll = reinterpret_cast<uint32_t*>(elc + N);
-  for (int i = threadIdx.x; i < N; i += MC_WPC * 32) elc[i] = exp(a.mu * a.lc[i].x);
-  for (int i = threadIdx.x; i < 2 * MC_WPC * JT * 32; i += MC_WPC * 32) tauAll[i] = cmk(0.0, 0.0);
+  cplx* bufAll = tauAll + (size_t)NW * JT * 32;
+  double* elc = reinterpret_cast<double*>(bufAll + (size_t)NW * JT * 32);
+  double* part = elc + N;                          // [2][WPCH] partial products (WPCH > 1)
+  uint32_t* sbitsAll = reinterpret_cast<uint32_t*>(part + 2 * WPCH);
+  for (int i = threadIdx.x; i < N; i += NW * 32) elc[i] = exp(a.mu * a.lc[i].x);
+  for (int i = threadIdx.x; i < 2 * NW * JT * 32; i += NW * 32) tauAll[i] = cmk(0.0, 0.0);
   __syncthreads();
-  if (chain >= a.C) return;  // whole warp exits together (no further block-wide barriers)
+  if (chain >= a.C) return;  // WPCH == 1 only (whole warp exits together; no further block-wide barriers there)
   cplx* tau = tauAll + (size_t)warp * JT * 32;
   cplx* buf = bufAll + (size_t)warp * JT * 32;
   uint32_t* sbits = sbitsAll + warp * 32;
@@ -303,8 +312,8 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
   auto refresh = [&]() {
     sbits[lane] = bits;
     __syncwarp();
-    for (int j0 = 0; j0 < M; j0 += 32) {
-      int j = j0 + lane;
+    for (int k = 0; k < JT; ++k) {
+      const int j = jbase + lane + 32 * k;
       if (j < M) {
         cplx acc = hasBias ? a.bias[j] : cmk(0.0, 0.0);
         for (int i = 0; i < N; ++i) {
@@ -315,21 +324,34 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
         }
         cplx l, t;
         lncosh_tanh(acc, l, t);
-        tau[j] = t;
+        tau[lane + 32 * k] = t;
       }
     }
     __syncwarp();
   };
-  // stage row T_site into this warp's buffer: lane l copies the elements j = l + 32 k it will read back itself
+  // stage this warp's slice of row T_site into its buffer: a lane copies the elements it will read back itself
   auto prefetch_row = [&](int site) {
-    const cplx* src = a.T + (size_t)site * M + lane;
+    const cplx* src = a.T + (size_t)site * M + jbase + lane;
     const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + lane);
 #pragma unroll
     for (int k = 0; k < JT; ++k)
-      if (k < JT - 1 || lane + 32 * k < M)
+      if (jbase + lane + 32 * k < M)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + (unsigned)(k * 32 * sizeof(cplx))),
                      "l"(src + 32 * k) : "memory");
     asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  // product over all hidden units of the chain from this warp's partial product
+  auto chain_prod = [&](double p, long long st) {
+    p = warp_prod(p);
+    if (WPCH > 1) {
+      double* slot = part + (st & 1) * WPCH;
+      if (lane == 0) slot[sw] = p;
+      __syncthreads();
+      p = 1.0;
+#pragma unroll
+      for (int w = 0; w < WPCH; ++w) p *= slot[w];   // same order in every warp: bitwise identical decisions
+    }
+    return p;
   };
 
   unsigned long long nAcc = 0, nProp = 0;
@@ -338,7 +360,8 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
   int emitted = 0, sweepCtr = 0, untilSweep = a.K;
   refresh();
 
-  // RNG batches: q holds the Philox output of step (batch base + lane)
+  // RNG batches: q holds the Philox output of step (batch base + lane); batches are aligned on the LOCAL step
+  // index, the counter of step st is step0 + st exactly as in the generic kernel.
   uint4 q = make_uint4(0, 0, 0, 0);
   auto draw = [&](long long st, uint4& r) {   // r of step st (warp-uniform); refills the batch every 32 steps
     const int idx = (int)(st & 31);
@@ -351,8 +374,6 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
     r.z = __shfl_sync(0xffffffffu, q.z, idx);
     r.w = __shfl_sync(0xffffffffu, q.w, idx);
   };
-  // Note: a.step0 is a multiple of nothing in particular, so batches are aligned on the LOCAL step index; the
-  // counter of step st is still step0 + st, exactly as in the generic kernel.
   uint4 rc;
   if (total > 0) {
     draw(0, rc);
@@ -388,7 +409,7 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
         const double f2 = fma(fr, fr, im * im);
         if (k & 1) p1 *= f2; else p0 *= f2;
       }
-      const double prod = warp_prod(p0 * p1);
+      const double prod = chain_prod(p0 * p1, st);
       const double P = (a.mu == 2.0) ? elc[sa] * prod : elc[sa] * pow(prod, 0.5 * a.mu);
       accept = u < P;
       nProp += 1;
@@ -408,16 +429,17 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
       double prod = 1.0;
 #pragma unroll
       for (int k = 0; k < JT; ++k) {
-        if (lane + 32 * k < M) {
+        const int j = jbase + lane + 32 * k;
+        if (j < M) {
           const cplx tj = tau[lane + 32 * k];
           const cplx n = cscale(tv[k], sga);
           cplx f = cadd(cmk(1.0, 0.0), cmul(tj, n));
           const cplx t1 = cdiv(cadd(tj, n), f);
-          f = cmul(f, csub(cmk(1.0, 0.0), cmul(t1, a.tb2[lane + 32 * k])));
+          f = cmul(f, csub(cmk(1.0, 0.0), cmul(t1, a.tb2[j])));
           prod *= cabs2(f);
         }
       }
-      prod = warp_prod(prod);
+      prod = chain_prod(prod, st);
       const double lre = a.lc[sa].x + a.lcb[0].x;
       const double P = (a.mu == 2.0) ? exp(2.0 * lre) * prod : exp(a.mu * (lre + 0.5 * log(prod)));
       accept = u < P;
@@ -426,11 +448,12 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
         nAcc += 1;
 #pragma unroll
         for (int k = 0; k < JT; ++k) {
-          if (lane + 32 * k < M) {
+          const int j = jbase + lane + 32 * k;
+          if (j < M) {
             const cplx tj = tau[lane + 32 * k];
             const cplx n = cscale(tv[k], sga);
             cplx tn = cdiv(cadd(tj, n), cadd(cmk(1.0, 0.0), cmul(tj, n)));
-            const cplx b2 = a.tb2[lane + 32 * k];
+            const cplx b2 = a.tb2[j];
             tn = cdiv(csub(b2, tn), csub(cmk(1.0, 0.0), cmul(b2, tn)));
             tau[lane + 32 * k] = tn;
           }
@@ -442,12 +465,14 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
       if (g) bits = (~bits) & valid;
     }
     if (st + 1 == nextEmit) {
-      const long long row = (long long)emitted * a.C + chain;  // time-major, chain-minor (sampler.py:323)
-      int32_t* dst = a.out + row * N;
-      for (int w = 0; w * 32 < N; ++w) {
-        uint32_t word = __shfl_sync(0xffffffffu, bits, w);
-        int i = w * 32 + lane;
-        if (i < N) dst[i] = (int32_t)((word >> lane) & 1u);
+      if (sw == 0) {
+        const long long row = (long long)emitted * a.C + chain;  // time-major, chain-minor (sampler.py:323)
+        int32_t* dst = a.out + row * N;
+        for (int w = 0; w * 32 < N; ++w) {
+          uint32_t word = __shfl_sync(0xffffffffu, bits, w);
+          int i = w * 32 + lane;
+          if (i < N) dst[i] = (int32_t)((word >> lane) & 1u);
+        }
       }
       ++emitted;
       nextEmit += a.K;
@@ -458,27 +483,43 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
     }
     rc = rn;
   }
-  for (int w = 0; w * 32 < N; ++w) {
-    uint32_t word = __shfl_sync(0xffffffffu, bits, w);
-    int i = w * 32 + lane;
-    if (i < N) a.states[chain * N + i] = (int32_t)((word >> lane) & 1u);
-  }
-  if (lane == 0) {
-    atomicAdd(a.counters + 0, nProp);
-    atomicAdd(a.counters + 1, nAcc);
+  if (sw == 0) {
+    for (int w = 0; w * 32 < N; ++w) {
+      uint32_t word = __shfl_sync(0xffffffffu, bits, w);
+      int i = w * 32 + lane;
+      if (i < N) a.states[chain * N + i] = (int32_t)((word >> lane) & 1u);
+    }
+    if (lane == 0) {
+      atomicAdd(a.counters + 0, nProp);
+      atomicAdd(a.counters + 1, nAcc);
+    }
   }
 }
 
-template <int JT>
+template <int JT, int WPCH>
 int launch_flip(const McmcArgs& a, cudaStream_t stream) {
-  size_t smem = (size_t)2 * MC_WPC * JT * 32 * sizeof(cplx) + (size_t)a.N * sizeof(double) + MC_WPC * 32 * sizeof(uint32_t);
+  constexpr int CPB = (WPCH == 1) ? MC_WPC : 1;
+  constexpr int NW = CPB * WPCH;
+  size_t smem = (size_t)2 * NW * JT * 32 * sizeof(cplx) + (size_t)(a.N + 2 * WPCH) * sizeof(double) + NW * 32 * sizeof(uint32_t);
   if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(rbm_mcmc_flip_kernel<JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  unsigned grid = (unsigned)((a.C + MC_WPC - 1) / MC_WPC);
-  rbm_mcmc_flip_kernel<JT><<<grid, MC_WPC * 32, smem, stream>>>(a);
+    cudaFuncSetAttribute(rbm_mcmc_flip_kernel<JT, WPCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  unsigned grid = (unsigned)((a.C + CPB - 1) / CPB);
+  rbm_mcmc_flip_kernel<JT, WPCH><<<grid, NW * 32, smem, stream>>>(a);
   JVMC_CHECK_LAUNCH();
   return JVMC_OK;
+}
+
+// JT = ceil(M / (32 WPCH)) in 1..16
+template <int WPCH>
+int dispatch_flip(const McmcArgs& a, cudaStream_t stream) {
+  switch ((a.M + 32 * WPCH - 1) / (32 * WPCH)) {
+#define JVMC_FLIP(J) case J: return launch_flip<J, WPCH>(a, stream)
+    JVMC_FLIP(1); JVMC_FLIP(2); JVMC_FLIP(3); JVMC_FLIP(4); JVMC_FLIP(5); JVMC_FLIP(6); JVMC_FLIP(7); JVMC_FLIP(8);
+    JVMC_FLIP(9); JVMC_FLIP(10); JVMC_FLIP(11); JVMC_FLIP(12); JVMC_FLIP(13); JVMC_FLIP(14); JVMC_FLIP(15); JVMC_FLIP(16);
+#undef JVMC_FLIP
+    default: return JVMC_ERR_UNSUPPORTED;
+  }
 }
 
 }  // namespace
@@ -506,14 +547,14 @@ extern "C" int jvmc_rbm_mcmc(int32_t* states, long long C, int N, int M, const d
   a.K = sweepSteps; a.thermSteps = thermSteps; a.numSamples = numSamplesPerChain;
   a.refreshEvery = refreshEvery > 0 ? refreshEvery : 1;
   a.out = out; a.counters = counters;
-  if (proposer != 2 && M <= 512 && !g_mcmc_generic) {
-    switch ((M + 31) / 32) {
-#define JVMC_FLIP(J) case J: return launch_flip<J>(a, (cudaStream_t)stream)
-      JVMC_FLIP(1); JVMC_FLIP(2); JVMC_FLIP(3); JVMC_FLIP(4); JVMC_FLIP(5); JVMC_FLIP(6); JVMC_FLIP(7); JVMC_FLIP(8);
-      JVMC_FLIP(9); JVMC_FLIP(10); JVMC_FLIP(11); JVMC_FLIP(12); JVMC_FLIP(13); JVMC_FLIP(14); JVMC_FLIP(15);
-      default: return launch_flip<16>(a, (cudaStream_t)stream);
-#undef JVMC_FLIP
-    }
+  if (proposer != 2 && !g_mcmc_generic) {
+    // single-flip fast path: one warp per chain up to M = 512, then 2 / 4 / 8 warps per chain (M <= 4096)
+    int rc = JVMC_ERR_UNSUPPORTED;
+    if (M <= 512) rc = dispatch_flip<1>(a, (cudaStream_t)stream);
+    else if (M <= 1024) rc = dispatch_flip<2>(a, (cudaStream_t)stream);
+    else if (M <= 2048) rc = dispatch_flip<4>(a, (cudaStream_t)stream);
+    else if (M <= 4096) rc = dispatch_flip<8>(a, (cudaStream_t)stream);
+    if (rc != JVMC_ERR_UNSUPPORTED) return rc;
   }
   size_t smem = (size_t)MC_WPC * M * sizeof(cplx) + MC_WPC * 32 * sizeof(uint32_t);
   if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
