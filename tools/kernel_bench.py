@@ -22,6 +22,7 @@ ap.add_argument("--therm", type=int, default=25)
 ap.add_argument("--g", type=float, default=3.04)
 ap.add_argument("--refresh", type=int, default=8)
 ap.add_argument("--generic", action="store_true", help="force the generic sampler kernel")
+ap.add_argument("--minsr", type=int, default=0, help="also time the MinSR tangent kernel T on the first N_T samples")
 a = ap.parse_args()
 if a.generic:
     from vmc_jax_b200 import _lib
@@ -91,3 +92,11 @@ print("fused E_loc (kernel): %.3f ms: %.2f TFLOP/s (14 N M flop/sample), %.2f TB
 G = RBMGradientObs(psi, s, p)
 _, t_m = timed(lambda: K.rbm_moments(G._s, G._tau, G._p.to(torch.complex128), False, 0))
 print("rbm_moments: %.3f ms: %.2f TFLOP/s (8 N M flop/sample)" % (t_m, 8.0 * N * M * B / t_m / 1e9))
+
+if a.minsr > 0:
+    NT = min(a.minsr, B)
+    Gs = RBMGradientObs(psi, s[:, :NT], (p[:, :NT] / p[:, :NT].sum()))
+    mu = Gs.kr_mean()
+    _, t_t = timed(lambda: K.rbm_gram_T(Gs._s, Gs._tau, Gs._p, mu, False, 2.0), reps=2)
+    print("MinSR tangent kernel T (N_T = %d, %0.1f GB): %.2f ms: %.2f TFLOP/s (4 N_T^2 M, Hermitian half), dense O O^dagger would be "
+          "%.1f PFLOP" % (NT, NT * NT * 16 / 1e9, t_t, 4.0 * NT * NT * M / t_t / 1e9, 4.0 * NT * NT * N * M / 1e15))

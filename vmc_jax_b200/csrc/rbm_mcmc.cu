@@ -279,19 +279,20 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
   const long long chain = (long long)blockIdx.x * CPB + cw;
   const int N = a.N, M = a.M;
   const int jbase = sw * 32 * JT;                  // first hidden unit of the slice
-  // tau and the row buffer are padded to 32 JT entries per warp and the padding is kept at zero: the factor of a
-  // padding unit is exactly 1 and its update 0 -> 0, so the unrolled loops need no predicates
-  cplx* tauAll = reinterpret_cast<cplx*>(smem_raw);
-  cplx* bufAll = tauAll + (size_t)NW * JT * 32;
-  double* elc = reinterpret_cast<double*>(bufAll + (size_t)NW * JT * 32);
+  // tau lives in REGISTERS (lane l owns the units jbase + l + 32 k); the weight rows are staged in two shared
+  // buffers per warp (ping-pong: the row of step st+1 lands while step st is evaluated).  Buffers are padded to
+  // 32 JT entries and the padding is kept at zero, tau of a padding unit is zero as well: its factor is exactly 1
+  // and its update 0 -> 0, so the unrolled loops need no predicates.  Shared-memory traffic per hidden unit and
+  // proposal: 16 B written by cp.async + 16 B read -- the L1/shared pipe is what binds this kernel.
+  cplx* bufAll = reinterpret_cast<cplx*>(smem_raw);            // [NW][2][32 JT]
+  double* elc = reinterpret_cast<double*>(bufAll + (size_t)NW * 2 * JT * 32);
   double* part = elc + N;                          // [2][WPCH] partial products (WPCH > 1)
   uint32_t* sbitsAll = reinterpret_cast<uint32_t*>(part + 2 * WPCH);
   for (int i = threadIdx.x; i < N; i += NW * 32) elc[i] = exp(a.mu * a.lc[i].x);
-  for (int i = threadIdx.x; i < 2 * NW * JT * 32; i += NW * 32) tauAll[i] = cmk(0.0, 0.0);
+  for (int i = threadIdx.x; i < 2 * NW * JT * 32; i += NW * 32) bufAll[i] = cmk(0.0, 0.0);
   __syncthreads();
   if (chain >= a.C) return;  // WPCH == 1 only (whole warp exits together; no further block-wide barriers there)
-  cplx* tau = tauAll + (size_t)warp * JT * 32;
-  cplx* buf = bufAll + (size_t)warp * JT * 32;
+  cplx* buf0 = bufAll + (size_t)warp * 2 * JT * 32;
   uint32_t* sbits = sbitsAll + warp * 32;
   const bool hasBias = a.bias != nullptr;
   const unsigned long long gchain = (unsigned long long)(a.chain0 + chain);
@@ -309,11 +310,14 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
       }
     }
   }
+  cplx tau[JT];
   auto refresh = [&]() {
     sbits[lane] = bits;
     __syncwarp();
+#pragma unroll
     for (int k = 0; k < JT; ++k) {
       const int j = jbase + lane + 32 * k;
+      cplx t = cmk(0.0, 0.0);
       if (j < M) {
         cplx acc = hasBias ? a.bias[j] : cmk(0.0, 0.0);
         for (int i = 0; i < N; ++i) {
@@ -322,17 +326,17 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
           acc.x = fma(sg, w.x, acc.x);
           acc.y = fma(sg, w.y, acc.y);
         }
-        cplx l, t;
+        cplx l;
         lncosh_tanh(acc, l, t);
-        tau[lane + 32 * k] = t;
       }
+      tau[k] = t;
     }
     __syncwarp();
   };
-  // stage this warp's slice of row T_site into its buffer: a lane copies the elements it will read back itself
-  auto prefetch_row = [&](int site) {
+  // stage this warp's slice of row T_site into buffer `which`: a lane copies the elements it will read back itself
+  auto prefetch_row = [&](int site, int which) {
     const cplx* src = a.T + (size_t)site * M + jbase + lane;
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + lane);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(buf0 + which * JT * 32 + lane);
 #pragma unroll
     for (int k = 0; k < JT; ++k)
       if (jbase + lane + 32 * k < M)
@@ -377,21 +381,18 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
   uint4 rc;
   if (total > 0) {
     draw(0, rc);
-    prefetch_row((int)__umulhi(rc.x, (uint32_t)N));
+    prefetch_row((int)__umulhi(rc.x, (uint32_t)N), 0);
   }
   for (long long st = 0; st < total; ++st) {
     const int sa = (int)__umulhi(rc.x, (uint32_t)N);
     const bool g = (a.proposer == 1) && (__umulhi(rc.y, 5u) == 0u);
     const double u = u01_from_bits(rc.z, rc.w);
-    // current row: shared buffer -> registers, then the buffer is free for the next row
-    cplx tv[JT];
+    const cplx* tv = buf0 + (int)(st & 1) * JT * 32 + lane;   // row of this step; the other buffer receives the next one
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < JT; ++k) tv[k] = buf[lane + 32 * k];
     uint4 rn = rc;
     if (st + 1 < total) {
       draw(st + 1, rn);
-      prefetch_row((int)__umulhi(rn.x, (uint32_t)N));
+      prefetch_row((int)__umulhi(rn.x, (uint32_t)N), (int)((st + 1) & 1));
     }
     const uint32_t wsa = __shfl_sync(0xffffffffu, bits, sa >> 5);
     const double sga = ((wsa >> (sa & 31)) & 1u) ? -1.0 : 1.0;   // -sigma_a
@@ -402,9 +403,10 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
       double p0 = 1.0, p1 = 1.0;
 #pragma unroll
       for (int k = 0; k < JT; ++k) {
-        const cplx tj = tau[lane + 32 * k];
-        const double re = fma(tj.x, tv[k].x, -tj.y * tv[k].y);
-        const double im = fma(tj.x, tv[k].y, tj.y * tv[k].x);
+        const cplx tj = tau[k];
+        const cplx t = tv[32 * k];
+        const double re = fma(tj.x, t.x, -tj.y * t.y);
+        const double im = fma(tj.x, t.y, tj.y * t.x);
         const double fr = fma(sga, re, 1.0);
         const double f2 = fma(fr, fr, im * im);
         if (k & 1) p1 *= f2; else p0 *= f2;
@@ -418,10 +420,10 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
         const double gsn = g ? -1.0 : 1.0;   // Z2 flip without bias: tau -> -tau
 #pragma unroll
         for (int k = 0; k < JT; ++k) {
-          const cplx tj = tau[lane + 32 * k];
-          const cplx n = cscale(tv[k], sga);
+          const cplx tj = tau[k];
+          const cplx n = cscale(tv[32 * k], sga);
           const cplx tn = cdiv(cadd(tj, n), cadd(cmk(1.0, 0.0), cmul(tj, n)));
-          tau[lane + 32 * k] = cscale(tn, gsn);
+          tau[k] = cscale(tn, gsn);
         }
       }
     } else {
@@ -431,8 +433,8 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
       for (int k = 0; k < JT; ++k) {
         const int j = jbase + lane + 32 * k;
         if (j < M) {
-          const cplx tj = tau[lane + 32 * k];
-          const cplx n = cscale(tv[k], sga);
+          const cplx tj = tau[k];
+          const cplx n = cscale(tv[32 * k], sga);
           cplx f = cadd(cmk(1.0, 0.0), cmul(tj, n));
           const cplx t1 = cdiv(cadd(tj, n), f);
           f = cmul(f, csub(cmk(1.0, 0.0), cmul(t1, a.tb2[j])));
@@ -450,12 +452,12 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
         for (int k = 0; k < JT; ++k) {
           const int j = jbase + lane + 32 * k;
           if (j < M) {
-            const cplx tj = tau[lane + 32 * k];
-            const cplx n = cscale(tv[k], sga);
+            const cplx tj = tau[k];
+            const cplx n = cscale(tv[32 * k], sga);
             cplx tn = cdiv(cadd(tj, n), cadd(cmk(1.0, 0.0), cmul(tj, n)));
             const cplx b2 = a.tb2[j];
             tn = cdiv(csub(b2, tn), csub(cmk(1.0, 0.0), cmul(b2, tn)));
-            tau[lane + 32 * k] = tn;
+            tau[k] = tn;
           }
         }
       }
