@@ -34,6 +34,7 @@ WORKLOADS = {
     "tfim2d_6x6_cpxrbm_a4_2p14": ((6, 6), 3.04, 4, False, 2 ** 14, 1184),
 }
 DEFAULT_WORKLOAD = "tfim2d_10x10_cpxrbm_a4_2p16"
+_REAL_STDOUT = 1
 METRIC = "VMC step samples/sec (sample + E_loc + S/F)"
 UNIT = "samples/s"
 
@@ -192,8 +193,12 @@ def main():
         return
 
     os.environ["JVMC_GRAM_BACKEND"] = args.gram
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line
+    # stdout carries exactly ONE JSON line: everything libraries print to fd 1 (e.g. "NCCL version ..." at communicator
+    # creation) is diverted to stderr, the JSON line is written to the saved descriptor at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import vmc_jax_b200 as jVMC
@@ -482,7 +487,8 @@ def main():
                         "steps": e2e_steps, "note": "parameters H2D from pinned memory; <E>, VarE, F D2H; S stays on device for the solver"},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
                 "phases_ms": phases, "kernels": kernels, "energy_mean": [energy.real, energy.imag], "tdvp_step": tdvp_info}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
