@@ -139,6 +139,26 @@ int jvmc_tdvp_regularize(int n, const double* ev, const double* VtF, const doubl
                          double pinvTol, double pinvCutoff, double snrTol, double* pinvEv, double* scal,
                          void* stream);
 
+/* Orbit-averaged (Cpx)RBM = SymNet(orbit, RBM, avgFun_Coefficients_Exp) (jVMC/nets/sym_wrapper.py:8-66, orbits from
+ * jVMC/util/symmetries.py): log Psi(s) = log sum_g fac_g exp(logpsi_RBM(O_g s)), O_g signed permutations given as
+ * x^g_i = esgn[g,i] * sigma[pmap[g,i]] (int32 [G,N] each; sigma = 2s-1), qmap[g,k] = the row i with pmap[g,i] = k.
+ * jvmc_symrbm_logpsi: logpsi complex128[B]; weights (optional) complex128[B,G] = fac_g psi_g / sum   <- NQS.__call__
+ * jvmc_symrbm_grad:   d log Psi / d theta, reference flat layout (layout 0: holomorphic [g, ig] per leaf; 1: plain)
+ *                     from the weights of jvmc_symrbm_logpsi                                          <- NQS.gradients
+ * jvmc_symrbm_mcmc:   Metropolis sampler with propose_spin_flip; same state / RNG / output conventions as
+ *                     jvmc_rbm_mcmc; tanh(theta^g) of every group element is updated incrementally     <- MCSampler */
+int jvmc_symrbm_logpsi(const int32_t* s, long long B, int N, int M, int G, const double* W, const double* bias,
+                       const int32_t* pmap, const int32_t* esgn, const double* fac, double* logpsi, double* weights,
+                       void* stream);
+int jvmc_symrbm_grad(const int32_t* s, long long B, int N, int M, int G, const double* W, const double* bias,
+                     const int32_t* pmap, const int32_t* esgn, const double* fac, const double* weights, int layout,
+                     double* out, void* stream);
+int jvmc_symrbm_mcmc(int32_t* states, long long C, int N, int M, int G, const double* W, const double* bias,
+                     const int32_t* pmap, const int32_t* esgn, const int32_t* qmap, const double* fac,
+                     const double* tables, unsigned long long seed, unsigned long long step0, long long chain0,
+                     double mu, int sweepSteps, long long thermSteps, int numSamplesPerChain, int refreshEvery,
+                     int32_t* out, unsigned long long* counters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,7 +3,7 @@ Used by tests/test_gpu_kernels.py (-m gpu) and by __graft_entry__.smoke()."""
 import numpy as np
 import torch
 
-from oracle import rbm as orbm, bfo as obfo, stats as ostats, solve as osolve, sampling as osamp
+from oracle import rbm as orbm, bfo as obfo, stats as ostats, solve as osolve, sampling as osamp, symmetries as osym
 from vmc_jax_b200 import kernels as K
 
 DEV = "cuda:0"
@@ -358,6 +358,73 @@ def check_sampler_chi2(N=4, M=2, weights=None, proposer="spin_flip", mu=2.0, C=5
     # chains are autocorrelated between emitted samples only weakly (K=N steps per sweep); allow p > 1e-3
     assert pval > 1e-3, (pval, stat)
     assert counters[0] > 0 and 0 < counters[1] <= counters[0]
+    return pval
+
+
+# ---------------------------------------------------------------- orbit-averaged RBM (SymNet)
+def _orbit(kind, L, args, **fac):
+    import warnings
+    from vmc_jax_b200.util import symmetries as psym
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if kind == "1d":
+            return psym.get_orbit_1D(L, *args, **fac), osym.orbit_1d(L, *args, **fac)
+        return psym.get_orbit_2D_square(L, *args, **fac), osym.orbit_2d_square(L, *args, **fac)
+
+
+def check_symrbm(kind="1d", L=4, M=3, args=("translation", "reflection", "spinflip"), bias=False, B=77, seed=5, **fac):
+    """SymNet(orbit, CpxRBM): log Psi and gradients (reference flat layout) vs the oracle restatement."""
+    ls, (orb, f) = _orbit(kind, L, args, **fac)
+    N = orb.shape[1]
+    W, b = orbm.init_o1(N, M, bias, seed)
+    s = rand_configs(B, N, seed + 1)
+    st = K.SymTables(ls, DEV)
+    dW, db, ds = dev(W), (None if b is None else dev(b)), dev(s)
+    lp, wts = K.symrbm_logpsi(ds, dW, db, st, want_weights=True)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ref = osym.symnet_logpsi(s, W, b, orb, f)
+        # amplitudes (Im log Psi is defined modulo 2 pi); with non-trivial quantum numbers the symmetrised amplitude
+        # of a configuration can vanish identically (log = -inf): compare amplitudes on the scale of the largest one
+        aref, agpu = np.exp(ref - np.max(ref.real)), np.exp(host(lp) - np.max(ref.real))
+    aref, agpu = np.nan_to_num(aref), np.nan_to_num(agpu)
+    e1 = np.max(np.abs(agpu - aref))
+    assert e1 < RTOL, e1
+    ok = np.abs(aref) > 1e-3            # gradients of log Psi are only defined away from the nodes
+    assert ok.sum() >= 3
+    assert np.max(np.abs(host(wts)[ok].sum(1) - 1.0)) < 1e-10
+    g = host(K.symrbm_grad(ds, dW, db, st, wts, 0))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gb, gW = osym.symnet_gradients(s, W, b, orb, f)
+    parts = ([gb, 1j * gb] if bias else []) + [gW.reshape(B, -1), 1j * gW.reshape(B, -1)]
+    e2 = relerr(g[ok], np.concatenate(parts, axis=1)[ok])
+    assert e2 < 1e-8, e2
+    return e1, e2
+
+
+def check_symrbm_sampler(L=4, M=2, args=("translation", "reflection", "spinflip"), weights=None, C=592,
+                         numSamples=600_000, mu=2.0, seed=4321, **fac):
+    """jvmc_symrbm_mcmc vs exact probabilities of the orbit-averaged RBM, chi-squared p > 1e-3."""
+    ls, (orb, f) = _orbit("1d", L, args, **fac)
+    if weights is None:
+        W, b = orbm.init_o1(L, M, False, 17)
+    else:
+        W, b = orbm.unflatten_params(np.asarray(weights), L, M, False)
+    basis = osamp.basis_states(L)
+    pex = np.exp(mu * np.real(osym.symnet_logpsi(basis, W, b, orb, f)))
+    pex /= pex.sum()
+    st = K.SymTables(ls, DEV)
+    dW = dev(W)
+    tables = K.rbm_tables(dW, None)
+    states = torch.zeros((C, L), dtype=torch.int32, device=DEV)
+    counters = torch.zeros(2, dtype=torch.int64, device=DEV)
+    spc = (numSamples + C - 1) // C
+    cfg = host(K.symrbm_mcmc(states, dW, None, st, tables, seed, 0, 0, mu, 8 * L, 20 * 8 * L, spc, counters, 1))
+    ints = (cfg.astype(np.int64) * (2 ** np.arange(L))[None, :]).sum(1)
+    counts = np.bincount(ints, minlength=2 ** L).astype(np.float64)
+    pval, stat = chi2_pvalue(counts, pex)
+    assert pval > 1e-3, (pval, stat)
+    c = host(counters)
+    assert c[0] > 0 and 0 < c[1] <= c[0]
     return pval
 
 

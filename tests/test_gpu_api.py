@@ -196,6 +196,62 @@ def test_MCMC_sampling(mu, kappa):
     assert float(torch.max(torch.abs((psi_s - psi_s1) / psi_s))) < 1e-14
 
 
+@pytest.mark.parametrize("mu,kappa", [(2, 0.5), (1, 0.5), (1, 1.0)])
+def test_MCMC_sampling_symnet(mu, kappa):
+    """reference tests/sampler_test.py:32-182 as written there: the RBM wrapped into SymNet with the
+    (translation, reflection, spinflip) orbit of the chain."""
+    import warnings
+    L = 4
+    rbm = nets.CpxRBM(numHidden=2, bias=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        orbit = jVMC.util.symmetries.get_orbit_1D(L, "translation", "reflection", "spinflip")
+    net = nets.sym_wrapper.SymNet(net=rbm, orbit=orbit)
+    psi = NQS(net)
+    exactSampler = sampler.ExactSampler(psi, L, logProbFactor=kappa)
+    mcSampler = sampler.MCSampler(psi, (L,), 0, updateProposer=sampler.propose_spin_flip, numChains=777, mu=mu,
+                                  logProbFactor=kappa)
+    p0 = psi.get_parameters()
+    psi.set_parameters(WEIGHTS)
+    _, _, pex = exactSampler.sample()
+    numSamples = 500000
+    smc, _, p = mcSampler.sample(numSamples=numSamples)
+    assert smc.shape[1] >= numSamples
+    ints = state_to_int(smc.reshape(-1, L))
+    pmc = torch.zeros(16, dtype=torch.float64, device=ints.device).index_add_(0, ints, p[0])
+    pmc = pmc / pmc.sum()
+    assert float(torch.max(torch.abs(pmc - pex.reshape(-1)[:16]))) < 2e-3
+    # the symmetrised amplitude is invariant under the orbit
+    s = smc[:, :64]
+    assert torch.allclose(psi(s), psi(torch.roll(s, 1, dims=-1)), atol=1e-12)
+    assert torch.allclose(psi(s).real, psi(1 - s).real, atol=1e-12)
+    s, psi_s, _ = mcSampler.sample(parameters=p0, numSamples=100)
+    psi.set_parameters(p0)
+    psi_s1 = psi(s)
+    assert float(torch.max(torch.abs((psi_s - psi_s1) / psi_s))) < 1e-14
+
+
+def test_symnet_ground_state_search():
+    """reference tests/tdvp_test.py:27-56 with the RBM wrapped into SymNet (generic gradient path: dense O from
+    jvmc_symrbm_grad, E_loc through s' enumeration): the ground state of the periodic TFIM lies in the fully
+    symmetric sector, so the symmetrised ansatz must reach the same golden energies."""
+    import warnings
+    L, J = 4, -1.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        orbit = jVMC.util.symmetries.get_orbit_1D(L, "translation", "reflection", "spinflip")
+    for k in (0, 1):
+        hx, exE = REFG["gs_hx"][k], REFG["gs_energies"][k]
+        psi = NQS(nets.sym_wrapper.SymNet(net=nets.CpxRBM(numHidden=6, bias=False), orbit=orbit))
+        H = tfim(L, J, hx)
+        exactSampler = sampler.ExactSampler(psi, L)
+        tdvpEquation = jVMC.util.TDVP(exactSampler, snrTol=1, pinvTol=0.0, pinvCutoff=1e-8, rhsPrefactor=1.,
+                                      diagonalShift=2, makeReal='real')
+        ground_state_search(psi, H, tdvpEquation, exactSampler, numSteps=100, stepSize=5e-2)
+        obs = measure({"energy": H}, psi, exactSampler)
+        assert float(torch.max(torch.abs((obs['energy']['mean'] - exE) / exE))) < 1e-3
+
+
 def test_sampler_output_contract():
     """time-major / chain-minor order, rounding up per chain, persistent chains."""
     L = 6

@@ -187,3 +187,28 @@ def test_sampler_stream_independent_of_chain_partition():
     bb, cb = run(C // 2, C // 2)
     assert np.array_equal(full, np.concatenate([a, bb], axis=1))
     assert np.array_equal(cf, ca + cb)
+
+
+# ---------------------------------------------------------------- orbit-averaged RBM (SymNet around CpxRBM)
+@pytest.mark.parametrize("kind,L,M,args,bias,fac", [
+    ("1d", 4, 2, ("translation", "reflection", "spinflip"), False, {}),
+    ("1d", 6, 5, ("translation",), True, {"translation_factor": -1.0}),
+    ("1d", 5, 3, ("reflection", "spinflip"), True, {"reflection_factor": -1.0, "spinflip_factor": -1.0}),
+    ("1d", 7, 4, (), False, {}),
+    ("2d", 3, 4, ("translation", "reflection", "rotation"), True, {}),
+    ("2d", 2, 3, ("rotation", "spinflip"), False, {"rotation_factor": 1j}),
+    ("1d", 20, 6, ("translation", "reflection", "spinflip"), False, {})])
+def test_symnet_logpsi_and_gradients(kind, L, M, args, bias, fac):
+    G.check_symrbm(kind, L, M, args, bias, **fac)
+
+
+def test_symnet_sampler_reference_weights():
+    """the reference's own sampler test case: SymNet(translation, reflection, spinflip) around CpxRBM(2), L = 4,
+    fixed weight vector (tests/sampler_test.py:32-45)."""
+    G.check_symrbm_sampler(L=4, M=2, weights=REFG["rbm_weights"])
+
+
+@pytest.mark.parametrize("L,M,args,mu", [(6, 4, ("translation",), 2.0), (8, 3, ("translation", "reflection", "spinflip"), 2.0),
+                                        (5, 2, ("reflection",), 1.0)])
+def test_symnet_sampler_chi2(L, M, args, mu):
+    G.check_symrbm_sampler(L=L, M=M, args=args, mu=mu)

@@ -167,3 +167,28 @@ def test_i8_gram_tile_list_covers_lower_triangle_once(M, rows, cols):
         cover[jj[ll <= jj], ll[ll <= jj]] += 1
     want = np.tril(np.ones((M, M), dtype=np.int32))
     assert np.array_equal(cover, want)
+
+
+@pytest.mark.parametrize("kind,L,args,fac", [
+    ("1d", 4, ("translation", "reflection", "spinflip"), {}),
+    ("1d", 6, ("translation",), {"translation_factor": -1.0}),
+    ("1d", 5, ("reflection", "spinflip"), {"reflection_factor": -1.0, "spinflip_factor": -1.0}),
+    ("2d", 3, ("translation", "reflection", "rotation"), {"rotation_factor": 1j}),
+    ("2d", 2, ("rotation", "spinflip"), {})])
+def test_symmetry_orbits_match_oracle(kind, L, args, fac):
+    """jVMC.util.symmetries mirror (index form used by the kernels) vs the dense restatement of the reference."""
+    import warnings
+    from oracle import symmetries as osym
+    from vmc_jax_b200.util import symmetries as psym
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if kind == "1d":
+            ls, (o, f) = psym.get_orbit_1D(L, *args, **fac), osym.orbit_1d(L, *args, **fac)
+        else:
+            ls, (o, f) = psym.get_orbit_2D_square(L, *args, **fac), osym.orbit_2d_square(L, *args, **fac)
+    assert np.array_equal(ls.orbit, o) and np.allclose(ls.factor, f)
+    n = o.shape[1]
+    x = np.random.default_rng(0).normal(size=n)
+    for g in range(o.shape[0]):
+        assert np.allclose(o[g] @ x, ls.sign[g] * x[ls.perm[g]])
+        assert np.array_equal(ls.perm[g][ls.inv[g]], np.arange(n))

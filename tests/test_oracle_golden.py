@@ -294,3 +294,31 @@ def test_adaptive_heun_linear_ode():
         y, dt = st.step(lambda y, t, intStep=0: A @ y, y, t)
         t += dt
     assert np.linalg.norm(y - expm(A * t) @ y0) < 1e-5
+
+
+def test_symnet_oracle_properties():
+    """SymNet restatement (jVMC/nets/sym_wrapper.py:8-66): orbit sizes of the reference's test case, invariance of
+    the symmetrised amplitude under every orbit element, analytic gradients vs finite differences."""
+    from oracle import symmetries as osym
+    o, f = osym.orbit_1d(4, "translation", "reflection", "spinflip")
+    assert o.shape == (16, 4, 4) and np.all(f == 1.0)          # 4 translations x reflection x spin flip
+    o2, _ = osym.orbit_2d_square(3, "translation", "reflection", "rotation")
+    assert o2.shape == (72, 9, 9)                                # |Z3 x Z3| x |D4|
+    W, b = rbm.init_o1(4, 3, True, 3)
+    s = np.random.default_rng(0).integers(0, 2, (9, 4))
+    lp = osym.symnet_logpsi(s, W, b, o, f)
+    x = 2 * s - 1
+    for O in o:
+        sp = ((x @ O.T) + 1) // 2
+        assert np.max(np.abs(np.exp(osym.symnet_logpsi(sp, W, b, o, f) - lp) - 1)) < 1e-12
+    gb, gW = osym.symnet_gradients(s, W, b, o, f)
+    eps = 1e-6
+    for (i, j) in [(0, 0), (1, 2), (3, 1)]:
+        Wp = W.copy(); Wp[i, j] += eps
+        Wm = W.copy(); Wm[i, j] -= eps
+        fd = (osym.symnet_logpsi(s, Wp, b, o, f) - osym.symnet_logpsi(s, Wm, b, o, f)) / (2 * eps)
+        assert np.max(np.abs(fd - gW[:, i, j])) < 1e-8
+    bp = b.copy(); bp[1] += eps
+    bm = b.copy(); bm[1] -= eps
+    fd = (osym.symnet_logpsi(s, W, bp, o, f) - osym.symnet_logpsi(s, W, bm, o, f)) / (2 * eps)
+    assert np.max(np.abs(fd - gb[:, 1])) < 1e-8

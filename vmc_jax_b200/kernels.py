@@ -4,6 +4,7 @@ torch is used for device memory and streams only; all arithmetic of the hot path
 kernels of libjvmc_b200.so.  Complex tensors are complex128, configurations int32."""
 import ctypes
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -110,6 +111,59 @@ def oloc_reduce(matEl, logPsiS, logPsiSP):
     B, K = matEl.shape
     out = torch.empty(B, dtype=CPX, device=matEl.device)
     call("jvmc_oloc_reduce", ptr(matEl), ptr(logPsiS), ptr(logPsiSP), B, K, ptr(out))
+    return out
+
+
+class SymTables:
+    """Device copies of a LatticeSymmetry in index form (perm, sign, inverse map, factors)."""
+
+    def __init__(self, sym, device):
+        self.G, self.N = sym.perm.shape
+        self.pmap = torch.as_tensor(np.ascontiguousarray(sym.perm), dtype=I32).to(device).contiguous()
+        self.esgn = torch.as_tensor(np.ascontiguousarray(sym.sign), dtype=I32).to(device).contiguous()
+        self.qmap = torch.as_tensor(np.ascontiguousarray(sym.inv), dtype=I32).to(device).contiguous()
+        self.fac = torch.as_tensor(np.asarray(sym.factor).astype(np.complex128)).to(device).contiguous()
+
+
+def symrbm_logpsi(s, W, b, st, want_weights=False):
+    """log Psi of the orbit-averaged RBM; optionally the normalised group weights f_g psi_g / sum [B, G]."""
+    s = _c(s, I32)
+    W = _c(W, CPX)
+    b = _c(b, CPX)
+    B, N = s.shape
+    M = W.shape[1]
+    out = torch.empty(B, dtype=CPX, device=s.device)
+    wts = torch.empty((B, st.G), dtype=CPX, device=s.device) if want_weights else None
+    call("jvmc_symrbm_logpsi", ptr(s), B, N, M, st.G, ptr(W), ptr(b), ptr(st.pmap), ptr(st.esgn), ptr(st.fac), ptr(out),
+         ptr(wts))
+    return (out, wts) if want_weights else out
+
+
+def symrbm_grad(s, W, b, st, wts, layout):
+    s = _c(s, I32)
+    W = _c(W, CPX)
+    b = _c(b, CPX)
+    B, N = s.shape
+    M = W.shape[1]
+    Pc = (M if b is not None else 0) + N * M
+    out = torch.empty((B, 2 * Pc if layout == 0 else Pc), dtype=CPX, device=s.device)
+    call("jvmc_symrbm_grad", ptr(s), B, N, M, st.G, ptr(W), ptr(b), ptr(st.pmap), ptr(st.esgn), ptr(st.fac), ptr(wts),
+         int(layout), ptr(out))
+    return out
+
+
+def symrbm_mcmc(states, W, b, st, tables, seed, step0, chain0, mu, sweepSteps, thermSteps, numSamplesPerChain, counters,
+                refreshEvery=1):
+    """states int32[C,N] updated in place; returns configs int32[numSamplesPerChain*C, N] (propose_spin_flip)."""
+    assert states.dtype == I32 and states.is_contiguous()
+    C, N = states.shape
+    W = _c(W, CPX)
+    b = _c(b, CPX)
+    M = W.shape[1]
+    out = torch.empty((numSamplesPerChain * C, N), dtype=I32, device=states.device)
+    call("jvmc_symrbm_mcmc", ptr(states), C, N, M, st.G, ptr(W), ptr(b), ptr(st.pmap), ptr(st.esgn), ptr(st.qmap),
+         ptr(st.fac), ptr(tables), ctypes.c_ulonglong(seed), ctypes.c_ulonglong(step0), chain0, float(mu),
+         int(sweepSteps), int(thermSteps), int(numSamplesPerChain), int(refreshEvery), ptr(out), ptr(counters))
     return out
 
 

@@ -184,7 +184,7 @@ class CompiledTables:
 
     def fused_ok(self, psi):
         """The fused (Cpx)RBM local-energy kernel covers lDim=2, non-fermionic strings flipping <= 2 sites."""
-        return (hasattr(psi, "_tau") and hasattr(psi, "flip_tables") and getattr(psi, "logarithmic", False)
+        return (getattr(psi, "khatri_rao", False) and hasattr(psi, "flip_tables") and getattr(psi, "logarithmic", False)
                 and self.lDim == 2 and self.maxOpStrLength <= 16 and not self.fermionic.any()
                 and all(len(t) <= 2 for t in self.nondiag_sites))
 

@@ -141,9 +141,15 @@ class MCSampler:
             states = self.states.reshape(C, -1)
             K_ = int(self.sweepSteps)
             therm = int(self.thermalizationSweeps) * K_               # thermalise on every call (:309-310)
-            cfg = K.rbm_mcmc(states, W, b, tables, self.key, self._stepCounter, mpi.rank * C,
-                             self.updateProposer.kernel_id, float(self.mu), K_, therm, spc, self._counters,
-                             self.refreshEvery)
+            if getattr(psi, "sym", None) is not None:
+                if self.updateProposer.kernel_id != 0:
+                    raise NotImplementedError("SymNet sampling runs on the device with propose_spin_flip only")
+                cfg = K.symrbm_mcmc(states, W, b, psi.sym_tables(), tables, self.key, self._stepCounter, mpi.rank * C,
+                                    float(self.mu), K_, therm, spc, self._counters, self.refreshEvery)
+            else:
+                cfg = K.rbm_mcmc(states, W, b, tables, self.key, self._stepCounter, mpi.rank * C,
+                                 self.updateProposer.kernel_id, float(self.mu), K_, therm, spc, self._counters,
+                                 self.refreshEvery)
             self._stepCounter += therm + spc * K_
             configs = cfg.reshape((1, spc * C) + self.sampleShape)
             coeffs = psi(configs)                                     # re-evaluation, reference :293-296

@@ -3,4 +3,4 @@ from .minsr import MinSR  # noqa: F401
 from .stepper import Euler, Heun, AdaptiveHeun  # noqa: F401
 from .util import measure, ground_state_search, get_iterable  # noqa: F401
 from .output_manager import OutputManager  # noqa: F401
-from . import tdvp, minsr, stepper, util, output_manager  # noqa: F401
+from . import tdvp, minsr, stepper, util, output_manager, symmetries  # noqa: F401

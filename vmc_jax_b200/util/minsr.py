@@ -89,7 +89,7 @@ class MinSR:
         stop_timing("compute Eloc")
         Eloc = SampledObs(Eloc, p)
         start_timing("compute gradients")
-        if hasattr(psi, "_tau"):
+        if getattr(psi, "khatri_rao", False):
             sampleGradients = RBMGradientObs(psi, sampleConfigs, p)
         else:
             sampleGradients = SampledObs(psi.gradients(sampleConfigs), p)

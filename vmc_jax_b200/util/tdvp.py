@@ -193,7 +193,7 @@ class TDVP:
         Eloc = SampledObs(Eloc, p)
 
         start_timing("compute gradients")
-        if hasattr(psi, "_tau"):
+        if getattr(psi, "khatri_rao", False):
             sampleGradients = RBMGradientObs(psi, sampleConfigs, p)      # factorised: O is never formed
         else:
             sampleGradients = SampledObs(psi.gradients(sampleConfigs), p)

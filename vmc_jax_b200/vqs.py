@@ -8,6 +8,7 @@ import torch
 from . import global_defs
 from . import kernels as K
 from .nets.rbm import CpxRBM, RBM, _RBMBase
+from .nets.sym_wrapper import SymNet
 
 
 def _to_dev(x, dtype=None):
@@ -30,9 +31,11 @@ class NQS:
         if isinstance(net, (tuple, list)):
             raise NotImplementedError("two-network ansatz (TwoNets) is outside the B200 hot path (SURVEY 2a-16)")
         if orbit is not None:
-            raise NotImplementedError("symmetrised nets (SymNet) are outside the B200 hot path (SURVEY 2a-15)")
-        if not isinstance(net, _RBMBase):
-            raise NotImplementedError("only jVMC.nets.CpxRBM / RBM have B200 kernels; got %r" % (net,))
+            # reference :170-173: NQS(net, orbit=...) wraps the net into SymNet itself
+            net = SymNet(orbit=orbit, net=net) if avgFun is None else SymNet(orbit=orbit, net=net, avgFun=avgFun)
+        if not isinstance(net, (_RBMBase, SymNet)):
+            raise NotImplementedError("only jVMC.nets.CpxRBM / RBM (optionally inside SymNet) have B200 kernels; "
+                                      "got %r" % (net,))
         if not logarithmic:
             raise NotImplementedError("non-logarithmic networks are not supported")
         self.net = net
@@ -49,6 +52,20 @@ class NQS:
         self._cache = None
         self._tables = None
         self.sampleShape = None
+        self.sym = net.orbit if isinstance(net, SymNet) else None     # LatticeSymmetry of an orbit-averaged RBM
+        self._symTables = None
+
+    @property
+    def khatri_rao(self):
+        """True when per-sample gradients factorise as sigma (x) tau (bare RBM): the fused E_loc / Gram kernels apply."""
+        return self.sym is None
+
+    def sym_tables(self):
+        if self._symTables is None:
+            if self.sym.perm.shape[1] != self.N:
+                raise ValueError("orbit acts on %d sites, the configurations have %d" % (self.sym.perm.shape[1], self.N))
+            self._symTables = K.SymTables(self.sym, global_defs.myDevice)
+        return self._symTables
 
     # ------------------------------------------------------------------ initialisation
     def init_net(self, s):
@@ -99,6 +116,8 @@ class NQS:
         self.init_net(s)
         flat, lead = self._flat_configs(s)
         W, b = self._cW()
+        if self.sym is not None:
+            return K.symrbm_logpsi(flat, W, b, self.sym_tables()).reshape(lead)
         logpsi, tau = K.rbm_logpsi(flat, W, b)
         self._remember(flat, tau)
         return logpsi.reshape(lead)
@@ -130,7 +149,12 @@ class NQS:
         s = _to_dev(s, torch.int32)
         self.init_net(s)
         flat, lead = self._flat_configs(s)
-        g = K.rbm_grad(flat, self._tau(flat), self.b is not None, 0 if self.holomorphic else 1)
+        if self.sym is not None:
+            W, b = self._cW()
+            _, wts = K.symrbm_logpsi(flat, W, b, self.sym_tables(), want_weights=True)
+            g = K.symrbm_grad(flat, W, b, self.sym_tables(), wts, 0 if self.holomorphic else 1)
+        else:
+            g = K.rbm_grad(flat, self._tau(flat), self.b is not None, 0 if self.holomorphic else 1)
         return g.reshape(lead + (g.shape[-1],))
 
     def gradients_dict(self, s):
