@@ -159,6 +159,24 @@ int jvmc_symrbm_mcmc(int32_t* states, long long C, int N, int M, int G, const do
                      double mu, int sweepSteps, long long thermSteps, int numSamplesPerChain, int refreshEvery,
                      int32_t* out, unsigned long long* counters, void* stream);
 
+/* Real-parameter CNN ansatz (jVMC/nets/cnn.py:18-81): wrap padding, strided cross-correlation, activation per layer,
+ * sum / sqrt(size).  desc: HOST int array [nl, Lx, Ly, Fx, Fy, sx, sy, firstLayerBias, bias, ch_1..ch_nl, act_1..act_nl]
+ * (act: 0 elu, 1 relu, 2 tanh, 3 poly5, 4 poly6, 5 square; Ly = Fy = sy = 1 for chains); theta: device float64[P], the
+ * flat parameter vector in the reference's order (per layer: bias if present, kernel [Fx, Fy, Cin, Cout]).
+ * jvmc_cnn_logpsi: complex128[B] (imaginary part 0)                                           <- NQS.__call__
+ * jvmc_cnn_grad:   complex128[B, P], d log psi / d theta by per-sample back-propagation        <- NQS.gradients
+ * jvmc_cnn_mcmc:   Metropolis sampler, full forward pass per proposal; state / RNG / output conventions and proposer
+ *                  ids of jvmc_rbm_mcmc                                                        <- MCSampler */
+int jvmc_cnn_num_parameters(const int* desc, int ndesc, int* P);
+int jvmc_cnn_logpsi(const int* desc, int ndesc, const double* theta, const int32_t* s, long long B, double* logpsi,
+                    void* stream);
+int jvmc_cnn_grad(const int* desc, int ndesc, const double* theta, const int32_t* s, long long B, double* out,
+                  void* stream);
+int jvmc_cnn_mcmc(const int* desc, int ndesc, const double* theta, int32_t* states, long long C,
+                  unsigned long long seed, unsigned long long step0, long long chain0, int proposer, double mu,
+                  int sweepSteps, long long thermSteps, int numSamplesPerChain, int32_t* out,
+                  unsigned long long* counters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

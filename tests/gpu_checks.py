@@ -3,7 +3,7 @@ Used by tests/test_gpu_kernels.py (-m gpu) and by __graft_entry__.smoke()."""
 import numpy as np
 import torch
 
-from oracle import rbm as orbm, bfo as obfo, stats as ostats, solve as osolve, sampling as osamp, symmetries as osym
+from oracle import rbm as orbm, bfo as obfo, stats as ostats, solve as osolve, sampling as osamp, symmetries as osym, cnn as ocnn
 from vmc_jax_b200 import kernels as K
 
 DEV = "cuda:0"
@@ -425,6 +425,68 @@ def check_symrbm_sampler(L=4, M=2, args=("translation", "reflection", "spinflip"
     assert pval > 1e-3, (pval, stat)
     c = host(counters)
     assert c[0] > 0 and 0 < c[1] <= c[0]
+    return pval
+
+
+# ---------------------------------------------------------------- CNN (real parameters)
+def _cnn(shape, F, channels, strides, act, bias, firstLayerBias, seed):
+    from vmc_jax_b200.nets.cnn import CNN
+    net = CNN(F=F, channels=channels, strides=strides, actFun=act, bias=bias, firstLayerBias=firstLayerBias)
+    cd = K.CnnDesc(net, shape)
+    P = ocnn.num_parameters(F, channels, bias, firstLayerBias)
+    assert cd.P == P
+    theta = np.random.default_rng(seed).normal(size=P) * 0.4
+    kw = dict(F=F, channels=channels, strides=strides, actFun=act, bias=bias, firstLayerBias=firstLayerBias)
+    return cd, theta, kw
+
+
+def check_cnn(shape=(6,), F=(3,), channels=(3, 2), strides=(1,), act=("elu",), bias=True, firstLayerBias=False, B=23,
+              seed=3):
+    """CNN log psi vs the oracle restatement; per-sample gradients vs central finite differences of the oracle."""
+    cd, theta, kw = _cnn(shape, F, channels, strides, act, bias, firstLayerBias, seed)
+    s = np.random.default_rng(seed + 1).integers(0, 2, (B,) + tuple(shape)).astype(np.int32)
+    flat = dev(s.reshape(B, -1))
+    dth = dev(theta)
+    lp = host(K.cnn_logpsi(flat, dth, cd))
+    ref = ocnn.cnn_logpsi(s, theta, **kw)
+    e1 = np.max(np.abs(lp.real - ref) / np.maximum(np.abs(ref), 1e-3))
+    assert e1 < RTOL and np.all(lp.imag == 0), e1
+    g = host(K.cnn_grad(flat, dth, cd))
+    assert np.all(g.imag == 0)
+    eps, fd = 1e-6, np.zeros((B, cd.P))
+    for k in range(cd.P):
+        tp, tm = theta.copy(), theta.copy()
+        tp[k] += eps
+        tm[k] -= eps
+        fd[:, k] = (ocnn.cnn_logpsi(s, tp, **kw) - ocnn.cnn_logpsi(s, tm, **kw)) / (2 * eps)
+    e2 = np.max(np.abs(g.real - fd)) / max(np.max(np.abs(fd)), 1e-3)
+    assert e2 < 1e-7, e2       # finite-difference truncation, not kernel accuracy
+    return e1, e2
+
+
+def check_cnn_sampler(shape=(6,), F=(3,), channels=(2,), proposer="spin_flip", C=296, numSamples=400_000, mu=2.0,
+                      sector=False, seed=4321):
+    cd, theta, kw = _cnn(shape, F, channels, (1,) * len(shape), ("elu",), True, False, 11)
+    N = int(np.prod(shape))
+    basis = osamp.basis_states(N)
+    pex = np.exp(mu * ocnn.cnn_logpsi(basis.reshape((-1,) + tuple(shape)), theta, **kw))
+    init = None
+    if sector:
+        pex = np.where(basis.sum(1) == N // 2, pex, 0.0)
+        init = np.array([1] * (N // 2) + [0] * (N - N // 2), np.int32)
+    pex /= pex.sum()
+    states = torch.zeros((C, N), dtype=torch.int32, device=DEV)
+    if init is not None:
+        states[:] = dev(init)
+    counters = torch.zeros(2, dtype=torch.int64, device=DEV)
+    spc = (numSamples + C - 1) // C
+    cfg = host(K.cnn_mcmc(states, dev(theta), cd, seed, 0, 0, proposer, mu, 8 * N, 20 * 8 * N, spc, counters))
+    ints = (cfg.astype(np.int64) * (2 ** np.arange(N))[None, :]).sum(1)
+    counts = np.bincount(ints, minlength=2 ** N).astype(np.float64)
+    if sector:
+        assert counts[pex == 0].sum() == 0
+    pval, stat = chi2_pvalue(counts, pex)
+    assert pval > 1e-3, (pval, stat)
     return pval
 
 

@@ -252,6 +252,67 @@ def test_symnet_ground_state_search():
         assert float(torch.max(torch.abs((obs['energy']['mean'] - exE) / exE))) < 1e-3
 
 
+def test_cnn_ground_state_search_and_sampling():
+    """nets.CNN through the public API: SR ground-state search with exact sampling reaches the golden TFIM energy
+    (positive ground state, so a real log-amplitude suffices), then MCMC with the same net reproduces the exact
+    distribution (reference tests/sampler_test.py style, 2e-3 on the histogram)."""
+    L, J, hx, exE = 4, -1.0, REFG["gs_hx"][1], REFG["gs_energies"][1]
+    psi = NQS(nets.CNN(F=(4,), channels=(3, 2), strides=(1,), bias=True, firstLayerBias=True), seed=3)
+    H = tfim(L, J, hx)
+    exactSampler = sampler.ExactSampler(psi, L)
+    assert not psi.holomorphic and psi.realParams and psi.numParameters == 3 + 4 * 3 + 2 + 4 * 3 * 2
+    tdvpEquation = jVMC.util.TDVP(exactSampler, snrTol=1, pinvTol=0.0, pinvCutoff=1e-8, rhsPrefactor=1.,
+                                  diagonalShift=1., makeReal='real')
+    e_start = float(measure({"energy": H}, psi, exactSampler)["energy"]["mean"][0])
+    ground_state_search(psi, H, tdvpEquation, exactSampler, numSteps=200, stepSize=5e-2)
+    e = float(measure({"energy": H}, psi, exactSampler)["energy"]["mean"][0])
+    assert e < e_start and abs((e - exE) / exE) < 5e-3, (e_start, e, exE)
+    # parameter round trip and dict/flat gradient consistency (reference tests/vqs_test.py:272-289)
+    p = psi.get_parameters()
+    psi.set_parameters(p)
+    assert torch.equal(psi.get_parameters(), p)
+    s = exactSampler.basis
+    g, gd, mp = psi.gradients(s), psi.gradients_dict(s), psi.grad_dict_to_vec_map()
+    for m in gd:
+        for k in gd[m]:
+            assert torch.equal(g[..., mp[m][k]], gd[m][k])
+    # MCMC vs exact
+    mcSampler = sampler.MCSampler(psi, (L,), 0, updateProposer=sampler.propose_spin_flip, numChains=777)
+    _, _, pex = exactSampler.sample()
+    smc, lp, pw = mcSampler.sample(numSamples=300000)
+    ints = state_to_int(smc.reshape(-1, L))
+    pmc = torch.zeros(16, dtype=torch.float64, device=ints.device).index_add_(0, ints, pw[0])
+    assert float(torch.max(torch.abs(pmc / pmc.sum() - pex.reshape(-1)[:16]))) < 3e-3
+    assert torch.allclose(lp, psi(smc))
+
+
+def test_cnn_heisenberg_exchange_sampling_config4_style():
+    """Config-4-shaped run at small size: 2-D Heisenberg (Marshall-rotated so that the ground state is positive),
+    CNN ansatz, magnetisation-conserving exchange proposer, SR steps with MC sampling and batched local energies."""
+    L = 4
+    H = op.BranchFreeOperator(ElocBatchSize=500)
+    for x in range(L):
+        for y in range(L):
+            i = x * L + y
+            for j in (x * L + (y + 1) % L, ((x + 1) % L) * L + y):
+                H.add(op.scal_opstr(-0.25, (op.Sx(i), op.Sx(j))))
+                H.add(op.scal_opstr(-0.25, (op.Sy(i), op.Sy(j))))
+                H.add(op.scal_opstr(0.25, (op.Sz(i), op.Sz(j))))
+    psi = NQS(nets.CNN(F=(2, 2), channels=(4, 2), strides=(1, 1), bias=True, firstLayerBias=False), seed=5)
+    neel = np.indices((L, L)).sum(0) % 2
+    mc = sampler.MCSampler(psi, (L, L), 123, updateProposer=sampler.propose_spin_flip_zeroMag, numChains=200,
+                           numSamples=4000, thermalizationSweeps=10, sweepSteps=L * L, initState=neel)
+    tdvpEquation = jVMC.util.TDVP(mc, snrTol=1, pinvTol=1e-8, pinvCutoff=1e-8, rhsPrefactor=1., diagonalShift=0.1,
+                                  makeReal='real')
+    s, lp, p = mc.sample()
+    assert s.shape[2:] == (L, L) and bool((s.reshape(s.shape[1], -1).sum(1) == L * L // 2).all())   # sector conserved
+    e0 = float(measure({"energy": H}, psi, mc)["energy"]["mean"][0])
+    ground_state_search(psi, H, tdvpEquation, mc, numSteps=40, stepSize=2e-2)
+    e1 = float(measure({"energy": H}, psi, mc)["energy"]["mean"][0])
+    # exact ground-state energy of the 4x4 periodic Heisenberg model: -0.70178 per site (= -11.2285)
+    assert e1 < e0 - 0.5 and e1 > -11.2285 - 0.3, (e0, e1)
+
+
 def test_sampler_output_contract():
     """time-major / chain-minor order, rounding up per chain, persistent chains."""
     L = 6

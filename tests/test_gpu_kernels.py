@@ -212,3 +212,21 @@ def test_symnet_sampler_reference_weights():
                                         (5, 2, ("reflection",), 1.0)])
 def test_symnet_sampler_chi2(L, M, args, mu):
     G.check_symrbm_sampler(L=L, M=M, args=args, mu=mu)
+
+
+# ---------------------------------------------------------------- real-parameter CNN (reference nets/cnn.py)
+@pytest.mark.parametrize("shape,F,channels,strides,act,bias,flb", [
+    ((6,), (3,), (3, 2), (1,), ("elu",), True, False),
+    ((8,), (4,), (2,), (2,), ("tanh",), False, True),
+    ((5,), (8,), (2, 2), (1,), ("poly5", "elu"), True, True),          # filter wider than the lattice (multiple wraps)
+    ((4, 4), (2, 2), (3, 2), (1, 1), ("elu",), True, False),
+    ((4, 6), (3, 2), (2, 3, 2), (2, 1), ("poly6", "relu", "square"), True, False),
+    ((3, 3), (2, 2), (4,), (1, 1), ("elu",), False, False)])
+def test_cnn_logpsi_and_gradients(shape, F, channels, strides, act, bias, flb):
+    G.check_cnn(shape, F, channels, strides, act, bias, flb)
+
+
+@pytest.mark.parametrize("shape,F,proposer,sector", [((6,), (3,), "spin_flip", False), ((2, 3), (2, 2), "spin_flip_Z2", False),
+                                                   ((6,), (4,), "spin_flip_zeroMag", True)])
+def test_cnn_sampler_chi2(shape, F, proposer, sector):
+    G.check_cnn_sampler(shape=shape, F=F, proposer=proposer, sector=sector)

@@ -42,6 +42,11 @@ _SIGS = {
     "jvmc_i8_layout": (c_int, [c_ll, c_int, ctypes.POINTER(c_ll), ctypes.POINTER(c_int), ctypes.POINTER(c_ll)]),
     "jvmc_i8_set_debug": (c_int, [c_int]),
     "jvmc_mcmc_set_generic": (c_int, [c_int]),
+    "jvmc_cnn_num_parameters": (c_int, [c_ptr, c_int, ctypes.POINTER(c_int)]),
+    "jvmc_cnn_logpsi": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ll, c_ptr, c_ptr]),
+    "jvmc_cnn_grad": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ll, c_ptr, c_ptr]),
+    "jvmc_cnn_mcmc": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ll, c_ull, c_ull, c_ll, c_int, c_dbl, c_int, c_ll, c_int,
+                              c_ptr, c_ptr, c_ptr]),
     "jvmc_symrbm_logpsi": (c_int, [c_ptr, c_ll, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "jvmc_symrbm_grad": (c_int, [c_ptr, c_ll, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr,
                                  c_ptr]),

@@ -114,6 +114,48 @@ def oloc_reduce(matEl, logPsiS, logPsiSP):
     return out
 
 
+class CnnDesc:
+    """Host int descriptor of a CNN on a given lattice (see include/jvmc_b200.h) + its parameter count."""
+
+    def __init__(self, net, sampleShape):
+        d = net.descriptor(tuple(sampleShape))
+        self.n = len(d)
+        self.arr = (ctypes.c_int * self.n)(*d)
+        P = ctypes.c_int(0)
+        _lib.check(_lib.load().jvmc_cnn_num_parameters(self.arr, self.n, ctypes.byref(P)), "jvmc_cnn_num_parameters")
+        self.P = P.value
+        self.N = int(np.prod(sampleShape))
+
+
+def cnn_logpsi(s, theta, cd):
+    s = _c(s, I32)
+    theta = _c(theta, F64)
+    B = s.shape[0]
+    out = torch.empty(B, dtype=CPX, device=s.device)
+    call("jvmc_cnn_logpsi", cd.arr, cd.n, ptr(theta), ptr(s), B, ptr(out))
+    return out
+
+
+def cnn_grad(s, theta, cd):
+    s = _c(s, I32)
+    theta = _c(theta, F64)
+    B = s.shape[0]
+    out = torch.empty((B, cd.P), dtype=CPX, device=s.device)
+    call("jvmc_cnn_grad", cd.arr, cd.n, ptr(theta), ptr(s), B, ptr(out))
+    return out
+
+
+def cnn_mcmc(states, theta, cd, seed, step0, chain0, proposer, mu, sweepSteps, thermSteps, numSamplesPerChain, counters):
+    assert states.dtype == I32 and states.is_contiguous()
+    C, N = states.shape
+    theta = _c(theta, F64)
+    out = torch.empty((numSamplesPerChain * C, N), dtype=I32, device=states.device)
+    pid = PROPOSER_IDS[proposer] if isinstance(proposer, str) else int(proposer)
+    call("jvmc_cnn_mcmc", cd.arr, cd.n, ptr(theta), ptr(states), C, ctypes.c_ulonglong(seed), ctypes.c_ulonglong(step0),
+         chain0, pid, float(mu), int(sweepSteps), int(thermSteps), int(numSamplesPerChain), ptr(out), ptr(counters))
+    return out
+
+
 class SymTables:
     """Device copies of a LatticeSymmetry in index form (perm, sign, inverse map, factors)."""
 

@@ -132,8 +132,10 @@ class MCSampler:
             tmpP = psi.params
             psi.set_parameters(params)
         try:
-            W, b = psi._cW()
-            tables = psi.flip_tables()
+            isCnn = getattr(psi, "kind", "rbm") == "cnn"
+            if not isCnn:
+                W, b = psi._cW()
+                tables = psi.flip_tables()
             C = self.numChains
             spc, self.globNumSamples = mpi.distribute_sampling(
                 numSamples, localDevices=global_defs.device_count(), numChainsPerDevice=math.lcm(C, multipleOf))
@@ -141,7 +143,10 @@ class MCSampler:
             states = self.states.reshape(C, -1)
             K_ = int(self.sweepSteps)
             therm = int(self.thermalizationSweeps) * K_               # thermalise on every call (:309-310)
-            if getattr(psi, "sym", None) is not None:
+            if isCnn:
+                cfg = K.cnn_mcmc(states, psi.get_parameters(), psi._cnnDesc, self.key, self._stepCounter, mpi.rank * C,
+                                 self.updateProposer.kernel_id, float(self.mu), K_, therm, spc, self._counters)
+            elif getattr(psi, "sym", None) is not None:
                 if self.updateProposer.kernel_id != 0:
                     raise NotImplementedError("SymNet sampling runs on the device with propose_spin_flip only")
                 cfg = K.symrbm_mcmc(states, W, b, psi.sym_tables(), tables, self.key, self._stepCounter, mpi.rank * C,

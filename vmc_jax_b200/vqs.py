@@ -9,6 +9,7 @@ from . import global_defs
 from . import kernels as K
 from .nets.rbm import CpxRBM, RBM, _RBMBase
 from .nets.sym_wrapper import SymNet
+from .nets.cnn import CNN
 
 
 def _to_dev(x, dtype=None):
@@ -33,8 +34,8 @@ class NQS:
         if orbit is not None:
             # reference :170-173: NQS(net, orbit=...) wraps the net into SymNet itself
             net = SymNet(orbit=orbit, net=net) if avgFun is None else SymNet(orbit=orbit, net=net, avgFun=avgFun)
-        if not isinstance(net, (_RBMBase, SymNet)):
-            raise NotImplementedError("only jVMC.nets.CpxRBM / RBM (optionally inside SymNet) have B200 kernels; "
+        if not isinstance(net, (_RBMBase, SymNet, CNN)):
+            raise NotImplementedError("only jVMC.nets.CpxRBM / RBM (optionally inside SymNet) and CNN have B200 kernels; "
                                       "got %r" % (net,))
         if not logarithmic:
             raise NotImplementedError("non-logarithmic networks are not supported")
@@ -54,11 +55,13 @@ class NQS:
         self.sampleShape = None
         self.sym = net.orbit if isinstance(net, SymNet) else None     # LatticeSymmetry of an orbit-averaged RBM
         self._symTables = None
+        self.kind = "cnn" if isinstance(net, CNN) else ("symrbm" if self.sym is not None else "rbm")
+        self._cnnDesc = None
 
     @property
     def khatri_rao(self):
         """True when per-sample gradients factorise as sigma (x) tau (bare RBM): the fused E_loc / Gram kernels apply."""
-        return self.sym is None
+        return self.kind == "rbm"
 
     def sym_tables(self):
         if self._symTables is None:
@@ -73,10 +76,13 @@ class NQS:
         if self.initialized:
             return
         self.sampleShape = tuple(s.shape[2:])
-        if not self.net.cpx and len(self.sampleShape) != 1:
-            raise NotImplementedError("real RBM acts on the last axis only (rbm.py:88); use 1-d sampleShape")
         self.N = int(np.prod(self.sampleShape))
-        self.M = self.net.numHidden
+        if self.kind == "cnn":
+            self._cnnDesc = K.CnnDesc(self.net, self.sampleShape)
+        else:
+            if not self.net.cpx and len(self.sampleShape) != 1:
+                raise NotImplementedError("real RBM acts on the last axis only (rbm.py:88); use 1-d sampleShape")
+            self.M = self.net.numHidden
         self.parameters = {"params": self.net.init(self.seed, self.sampleShape, global_defs.myDevice)}
         self.holomorphic = bool(self.net.cpx)
         leaves = self._leaves()
@@ -84,9 +90,15 @@ class NQS:
         self.numParameters = int(sum(p.numel() for p in leaves))
         self.initialized = True
 
+    def _leaf_keys(self, tree=None):
+        """(module, leaf) pairs in Flax's flattening order (sorted keys at both levels: Dense_0/bias, Dense_0/kernel;
+        Conv_0/bias, Conv_0/kernel, Conv_1/...)."""
+        t = self.parameters["params"] if tree is None else tree
+        return [(m, k) for m in sorted(t.keys()) for k in sorted(t[m].keys())]
+
     def _leaves(self, tree=None):
-        d = (self.parameters["params"] if tree is None else tree)["Dense_0"]
-        return [d[k] for k in sorted(d.keys())]      # Flax sorted-key order: bias, kernel
+        t = self.parameters["params"] if tree is None else tree
+        return [t[m][k] for m, k in self._leaf_keys(t)]
 
     @property
     def W(self):
@@ -115,6 +127,8 @@ class NQS:
         s = _to_dev(s, torch.int32)
         self.init_net(s)
         flat, lead = self._flat_configs(s)
+        if self.kind == "cnn":
+            return K.cnn_logpsi(flat, self.get_parameters(), self._cnnDesc).reshape(lead)
         W, b = self._cW()
         if self.sym is not None:
             return K.symrbm_logpsi(flat, W, b, self.sym_tables()).reshape(lead)
@@ -149,7 +163,9 @@ class NQS:
         s = _to_dev(s, torch.int32)
         self.init_net(s)
         flat, lead = self._flat_configs(s)
-        if self.sym is not None:
+        if self.kind == "cnn":
+            g = K.cnn_grad(flat, self.get_parameters(), self._cnnDesc)
+        elif self.sym is not None:
             W, b = self._cW()
             _, wts = K.symrbm_logpsi(flat, W, b, self.sym_tables(), want_weights=True)
             g = K.symrbm_grad(flat, W, b, self.sym_tables(), wts, 0 if self.holomorphic else 1)
@@ -157,24 +173,28 @@ class NQS:
             g = K.rbm_grad(flat, self._tau(flat), self.b is not None, 0 if self.holomorphic else 1)
         return g.reshape(lead + (g.shape[-1],))
 
+    def _leaf_slices(self):
+        out, start = [], 0
+        for (m, k), (size, _) in zip(self._leaf_keys(), self.paramShapes):
+            n = 2 * size if self.holomorphic else size
+            out.append((m, k, start, start + n))
+            start += n
+        return out
+
     def gradients_dict(self, s):
         """reference :292-314."""
         g = self.gradients(s)
-        out, start = {}, 0
-        for name, (size, _) in zip(sorted(self.parameters["params"]["Dense_0"].keys()), self.paramShapes):
-            n = 2 * size if self.holomorphic else size
-            out[name] = g[..., start:start + n]
-            start += n
-        return {"Dense_0": out}
+        out = {}
+        for m, k, lo, hi in self._leaf_slices():
+            out.setdefault(m, {})[k] = g[..., lo:hi]
+        return out
 
     def grad_dict_to_vec_map(self):
         """reference :319-334."""
-        out, start = {}, 0
-        for name, (size, _) in zip(sorted(self.parameters["params"]["Dense_0"].keys()), self.paramShapes):
-            n = 2 * size if self.holomorphic else size
-            out[name] = torch.arange(start, start + n)
-            start += n
-        return {"Dense_0": out}
+        out = {}
+        for m, k, lo, hi in self._leaf_slices():
+            out.setdefault(m, {})[k] = torch.arange(lo, hi)
+        return out
 
     def get_sampler_net(self):
         """reference :337-352: (function evaluating Re log psi, current parameters)."""
@@ -198,8 +218,8 @@ class NQS:
         if not self.initialized:
             self.set_parameters(deltaP)
         new = self._param_unflatten(deltaP)
-        cur = self.parameters["params"]["Dense_0"]
-        self.parameters = {"params": {"Dense_0": {k: cur[k] + new["Dense_0"][k] for k in cur}}}
+        cur = self.parameters["params"]
+        self.parameters = {"params": {m: {k: cur[m][k] + new[m][k] for k in cur[m]} for m in cur}}
         self._bump()
 
     def set_parameters(self, P):
@@ -215,17 +235,17 @@ class NQS:
     def _param_unflatten(self, P):
         """reference :430-444."""
         P = _to_dev(P)
-        names = sorted(self.parameters["params"]["Dense_0"].keys())
         out, start = {}, 0
-        for name, (size, shape) in zip(names, self.paramShapes):
+        for (m, name), (size, shape) in zip(self._leaf_keys(), self.paramShapes):
             if not self.realParams:
-                out[name] = (P[start:start + size] + 1j * P[start + size:start + 2 * size]).reshape(shape) \
-                    .to(torch.complex128)
+                leaf = (P[start:start + size] + 1j * P[start + size:start + 2 * size]).reshape(shape).to(torch.complex128)
                 start += 2 * size
             else:
-                out[name] = P[start:start + size].reshape(shape)
+                leaf = P[start:start + size].reshape(shape)
+                leaf = leaf.real.to(torch.float64) if leaf.is_complex() else leaf.to(torch.float64)
                 start += size
-        return {"Dense_0": out}
+            out.setdefault(m, {})[name] = leaf
+        return out
 
     def get_parameters(self):
         """reference :449-466: per leaf [Re ravel, Im ravel] (complex) or ravel (real)."""
@@ -248,7 +268,7 @@ class NQS:
 
     @params.setter
     def params(self, val):
-        if "params" in val and "Dense_0" not in val:
+        if "params" in val and len(val) == 1:
             val = val["params"]
-        self.parameters = {"params": {"Dense_0": {k: _to_dev(v) for k, v in val["Dense_0"].items()}}}
+        self.parameters = {"params": {m: {k: _to_dev(v) for k, v in val[m].items()} for m in val}}
         self._bump()
