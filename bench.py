@@ -428,6 +428,10 @@ def main():
             tdvp_info = tdvp_step_ms(jVMC, op, torch)
         except Exception as ex:  # pragma: no cover
             tdvp_info = {"error": repr(ex)}
+        try:
+            tdvp_info["config3"] = tdvp_step_ms_config3(jVMC, op, torch)
+        except Exception as ex:  # pragma: no cover
+            tdvp_info["config3"] = {"error": repr(ex)}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
@@ -518,6 +522,43 @@ def tdvp_step_ms(jVMC, op, torch, L=20, alpha=2, nsamp=4096, chains=500, steps=5
     return {"config": "1D TFIM L=%d, CpxRBM alpha=%d (P=%d), %d chains, %d samples, SR (makeReal=real, diagonalShift=10)"
                       % (L, alpha, 2 * L * alpha * L, chains, smp.get_last_number_of_samples()),
             "ms_per_step": float(np.median(times[2:])), "energy_per_site": float(tdvp.ElocMean0.real) / L}
+
+
+def tdvp_step_ms_config3(jVMC, op, torch, L=40, alpha=2, nsamp=2 ** 16, chains=2368, steps=2):
+    """One real-time TDVP right-hand side (TDVP.__call__ with rhsPrefactor=1j, makeReal='imag', SNR-regularised solve)
+    on BASELINE configs[2]: 1D TFIM L=40 quench, CpxRBM alpha=2 with bias (P = 6560), 2^16 samples.  An AdaptiveHeun
+    step costs 5 of these per attempt (stepper.py:146-158)."""
+    dev = jVMC.global_defs.myDevice
+    psi = jVMC.vqs.NQS(jVMC.nets.CpxRBM(numHidden=alpha * L, bias=True), seed=1234)
+    psi(torch.zeros((1, 1, L), dtype=torch.int32, device=dev))
+    W, b = o1_weights(L, alpha * L, True)
+    psi.set_parameters(torch.as_tensor(flat_params(0.3 * W, 0.3 * b)))
+    H = op.BranchFreeOperator()
+    for l in range(L):
+        H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz((l + 1) % L))))
+        H.add(op.scal_opstr(-0.3, (op.Sx(l),)))
+    smp = jVMC.sampler.MCSampler(psi, (L,), 4321, updateProposer=jVMC.sampler.propose_spin_flip, numChains=chains,
+                                 sweepSteps=L, numSamples=nsamp, thermalizationSweeps=25)
+    tdvp = jVMC.util.TDVP(smp, snrTol=2, pinvTol=1e-8, rhsPrefactor=1.j, makeReal='imag')
+    times = []
+    for k in range(steps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tdvp(psi.get_parameters(), 0.0, hamiltonian=H, psi=psi, numSamples=None)
+        torch.cuda.synchronize()
+        times.append((time.perf_counter() - t0) * 1e3)
+    P = 2 * (alpha * L + L * alpha * L)
+    return {"config": "1D TFIM L=%d quench, CpxRBM alpha=%d with bias (P=%d), %d chains, %d samples, real-time TDVP "
+                      "(rhsPrefactor=1j, makeReal=imag, snrTol=2)" % (L, alpha, P, chains, smp.get_last_number_of_samples()),
+            "ms_per_rhs": float(np.median(times[1:])), "rhs_per_adaptive_heun_attempt": 5,
+            "solver_residual": _maybe_float(lambda: tdvp.get_residuals()[1])}
+
+
+def _maybe_float(f):
+    try:
+        return float(f())
+    except Exception:
+        return None
 
 
 if __name__ == "__main__":
