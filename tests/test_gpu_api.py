@@ -530,3 +530,92 @@ def test_gradient_dict_and_param_roundtrip():
     psi2 = NQS(nets.CpxRBM(numHidden=8))
     with pytest.raises(RuntimeError):
         psi2.set_parameters(P)
+
+
+# ------------------------------------------------------------------ tests/nets_test.py, vqs_test.py, tdvp_test.py with wrappers
+def _orbit_1d(L, *args):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return jVMC.util.symmetries.get_orbit_1D(L, *args)
+
+
+def test_cnn_translation_invariance_1d_2d():
+    """reference tests/nets_test.py:16-46: a periodic CNN gives the same output on all translates."""
+    cnn = NQS(nets.CNN(F=(4,), channels=[3, 2, 5]), seed=0)
+    S0 = np.pad(np.array([1, 0, 1, 1, 0]), (0, 4), 'wrap')
+    S = torch.tensor(np.array([S0[i:i + 5] for i in range(5)]), dtype=torch.int32)[None]
+    psiS = cnn(S)
+    assert float(torch.max(torch.abs(psiS - psiS[0, 0]))) < 1e-12
+    cnn = NQS(nets.CNN(F=(3, 3), channels=[3, 2, 5], strides=[1, 1]), seed=0)
+    S0 = np.pad(np.array([[1, 0, 1, 1], [0, 1, 1, 1], [0, 0, 1, 0], [1, 0, 0, 1]]), [(0, 3), (0, 3)], 'wrap')
+    S = torch.tensor(np.array([S0[i:i + 4, j:j + 4] for i in range(4) for j in range(4)]), dtype=torch.int32)[None]
+    psiS = cnn(S)
+    assert float(torch.max(torch.abs(psiS - psiS[0, 0]))) < 1e-12
+
+
+def test_sym_net_translation_invariance():
+    """reference tests/nets_test.py:51-65: real RBM wrapped into SymNet with the translation orbit."""
+    L = 5
+    psi = NQS(nets.SymNet(net=nets.RBM(numHidden=5), orbit=_orbit_1d(L, "translation")), seed=0)
+    S0 = np.pad(np.array([1, 0, 1, 1, 0]), (0, 4), 'wrap')
+    S = torch.tensor(np.array([S0[i:i + 5] for i in range(5)]), dtype=torch.int32)[None]
+    psiS = psi(S)
+    assert not psi.holomorphic
+    assert float(torch.max(torch.abs(psiS - psiS[0, 0]))) < 1e-12
+
+
+def test_holomorphicity_recognition_and_gradients_symnet():
+    """reference tests/vqs_test.py:86-131 as written there (the RBM sits inside SymNet with the trivial orbit)."""
+    L = 3
+    for k in range(6):
+        net = nets.sym_wrapper.SymNet(net=nets.CpxRBM(numHidden=2 ** k, bias=True), orbit=_orbit_1d(L))
+        psiC = NQS(net)
+        psiC(torch.zeros((1, 4, 3), dtype=torch.int32))
+        assert psiC.holomorphic
+    psiC = NQS(nets.sym_wrapper.SymNet(net=nets.CpxRBM(numHidden=2, bias=True), orbit=_orbit_1d(L, "translation")))
+    s = torch.zeros((1, 4, L), dtype=torch.int32, device="cuda")
+    s[..., 0, 1] = 1
+    s[..., 2, 2] = 1
+    psi0 = psiC(s)
+    G = psiC.gradients(s)
+    delta = 1e-6
+    params = psiC.get_parameters()
+    assert G.shape[-1] == params.shape[0]
+    for j in range(G.shape[-1]):
+        u = torch.zeros(G.shape[-1], dtype=torch.float64, device="cuda")
+        u[j] = 1
+        psiC.update_parameters(delta * u)
+        psi1 = psiC(s)
+        psiC.set_parameters(params)
+        assert float(torch.max(torch.abs((psi1 - psi0) / delta - G[..., j]))) < 1e-4
+
+
+def test_snr_consistency_symnet():
+    """reference tests/tdvp_test.py:201-263: legacy SNR formula vs SampledObs.covar_data().transform().var() for the
+    translation-symmetrised RBM sampled by MCMC."""
+    L = 4
+    psi = NQS(nets.sym_wrapper.SymNet(net=nets.CpxRBM(numHidden=2, bias=False), orbit=_orbit_1d(L, "translation")),
+              batchSize=5000)
+    psi(torch.tensor([[[1, 1, 1, 1]]], dtype=torch.int32))
+    psi.set_parameters(WEIGHTS)
+    H = tfim(L, -1.0, -0.3)
+    smp = sampler.MCSampler(psi, (L,), 0, numSamples=10, updateProposer=sampler.propose_spin_flip, mu=2, numChains=500)
+    s, logPsi, p = smp.sample()
+    Eloc_old = H.get_O_loc(s, psi, logPsi, 0.0)
+    Eloc = SampledObs(Eloc_old, p)
+    grads_old = psi.gradients(s)
+    grads = SampledObs(grads_old, p)
+    S = jVMC.util.imagFun(grads.covar())
+    ev, V = torch.linalg.eigh(S)
+    # legacy formula
+    E0 = Eloc_old - mpi.global_mean(Eloc_old, p)
+    G0 = grads_old - mpi.global_mean(grads_old, p)
+    EOdata = (p * E0)[..., None] * torch.conj(G0) * mpi.globNumSamples
+    EOdata = jVMC.util.imagFun(EOdata).to(V.dtype) @ torch.conj(V)
+    rhoVar_old = mpi.global_variance(EOdata, torch.ones(EOdata.shape[:2], dtype=torch.float64, device=EOdata.device)
+                                     / mpi.globNumSamples)
+    EO = grads.covar_data(Eloc).transform(linearFun=torch.conj(V).T, nonLinearFun=lambda x: jVMC.util.imagFun(x))
+    rhoVar_new = EO.var().ravel()
+    assert torch.allclose(rhoVar_old.ravel().real.to(torch.float64), rhoVar_new.real.to(torch.float64), rtol=1e-8,
+                          atol=1e-12 * float(rhoVar_new.abs().max()))
