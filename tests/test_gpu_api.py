@@ -619,3 +619,39 @@ def test_snr_consistency_symnet():
     rhoVar_new = EO.var().ravel()
     assert torch.allclose(rhoVar_old.ravel().real.to(torch.float64), rhoVar_new.real.to(torch.float64), rtol=1e-8,
                           atol=1e-12 * float(rhoVar_new.abs().max()))
+
+
+def test_two_nets_gradients_and_sampling():
+    """reference tests/vqs_test.py:133-164 (finite-difference gradients of NQS((rbm1, rbm2))) and
+    tests/sampler_test.py:184-228 (MCMC with the two-network ansatz: the amplitude network alone is sampled)."""
+    L = 3
+    psi = NQS((nets.RBM(numHidden=2, bias=True), nets.RBM(numHidden=3, bias=True)))
+    s = torch.zeros((1, 4, L), dtype=torch.int32, device="cuda")
+    s[..., 0, 1] = 1
+    s[..., 2, 2] = 1
+    psi0 = psi(s)
+    assert not psi.holomorphic and psi.realParams
+    G = psi.gradients(s)
+    delta = 1e-5
+    params = psi.get_parameters()
+    assert G.shape[-1] == params.shape[0] == (2 + 3 * 2) + (3 + 3 * 3)
+    for j in range(G.shape[-1]):
+        u = torch.zeros(G.shape[-1], dtype=torch.float64, device="cuda")
+        u[j] = 1
+        psi.update_parameters(delta * u)
+        psi1 = psi(s)
+        psi.set_parameters(params)
+        assert float(torch.max(torch.abs((psi1 - psi0) / delta - G[..., j]))) < 1e-3
+    # sampler
+    L = 4
+    psi = NQS(nets.two_nets_wrapper.TwoNets((nets.RBM(numHidden=2, bias=False), nets.RBM(numHidden=2, bias=False))))
+    exactSampler = sampler.ExactSampler(psi, L)
+    mcSampler = sampler.MCSampler(psi, (L,), 0, updateProposer=sampler.propose_spin_flip, numChains=777)
+    psi.set_parameters(torch.cat([WEIGHTS[:8], WEIGHTS[:8]]))
+    _, _, pex = exactSampler.sample()
+    smc, lp, p = mcSampler.sample(numSamples=500000)
+    assert smc.shape[1] >= 500000
+    ints = state_to_int(smc.reshape(-1, L))
+    pmc = torch.zeros(16, dtype=torch.float64, device=ints.device).index_add_(0, ints, p[0])
+    assert float(torch.max(torch.abs(pmc / pmc.sum() - pex.reshape(-1)[:16]))) < 2e-3
+    assert float(lp.imag.abs().max()) > 0        # the phase network contributes

@@ -41,7 +41,12 @@ def test_unsupported_components_raise():
     with pytest.raises(NotImplementedError):
         jVMC.vqs.NQS(object())
     with pytest.raises(NotImplementedError):
-        jVMC.vqs.NQS((jVMC.nets.RBM(), jVMC.nets.RBM()))
+        jVMC.vqs.NQS((jVMC.nets.CpxRBM(), jVMC.nets.RBM()))        # two-network ansatz: pair of real RBMs only
+    with pytest.raises(NotImplementedError):
+        jVMC.nets.CNN(F=(3,), channels=(2,), periodicBoundary=False)
+    with pytest.raises(NotImplementedError):
+        jVMC.nets.CNN(F=(3,), channels=(2,), actFun=(abs,))
+    assert jVMC.vqs.NQS((jVMC.nets.RBM(), jVMC.nets.RBM())).kind == "tworbm"
 
 
 def test_opstr_algebra():

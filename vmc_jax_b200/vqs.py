@@ -10,6 +10,7 @@ from . import kernels as K
 from .nets.rbm import CpxRBM, RBM, _RBMBase
 from .nets.sym_wrapper import SymNet
 from .nets.cnn import CNN
+from .nets.two_nets_wrapper import TwoNets
 
 
 def _to_dev(x, dtype=None):
@@ -30,11 +31,13 @@ class NQS:
 
     def __init__(self, net, logarithmic=True, batchSize=1000, seed=1234, orbit=None, avgFun=None):
         if isinstance(net, (tuple, list)):
-            raise NotImplementedError("two-network ansatz (TwoNets) is outside the B200 hot path (SURVEY 2a-16)")
+            net = TwoNets(net)                     # reference :166-167
         if orbit is not None:
             # reference :170-173: NQS(net, orbit=...) wraps the net into SymNet itself
             net = SymNet(orbit=orbit, net=net) if avgFun is None else SymNet(orbit=orbit, net=net, avgFun=avgFun)
-        if not isinstance(net, (_RBMBase, SymNet, CNN)):
+        if isinstance(net, SymNet) and isinstance(net.net, TwoNets):
+            raise NotImplementedError("SymNet around TwoNets has no device kernel (use NQS((rbm1, rbm2)))")
+        if not isinstance(net, (_RBMBase, SymNet, CNN, TwoNets)):
             raise NotImplementedError("only jVMC.nets.CpxRBM / RBM (optionally inside SymNet) and CNN have B200 kernels; "
                                       "got %r" % (net,))
         if not logarithmic:
@@ -55,7 +58,8 @@ class NQS:
         self.sampleShape = None
         self.sym = net.orbit if isinstance(net, SymNet) else None     # LatticeSymmetry of an orbit-averaged RBM
         self._symTables = None
-        self.kind = "cnn" if isinstance(net, CNN) else ("symrbm" if self.sym is not None else "rbm")
+        self.kind = "cnn" if isinstance(net, CNN) else ("tworbm" if isinstance(net, TwoNets) else
+                                                        ("symrbm" if self.sym is not None else "rbm"))
         self._cnnDesc = None
 
     @property
@@ -82,7 +86,7 @@ class NQS:
         else:
             if not self.net.cpx and len(self.sampleShape) != 1:
                 raise NotImplementedError("real RBM acts on the last axis only (rbm.py:88); use 1-d sampleShape")
-            self.M = self.net.numHidden
+            self.M = self.net.nets[0].numHidden if self.kind == "tworbm" else self.net.numHidden
         self.parameters = {"params": self.net.init(self.seed, self.sampleShape, global_defs.myDevice)}
         self.holomorphic = bool(self.net.cpx)
         leaves = self._leaves()
@@ -100,16 +104,22 @@ class NQS:
         t = self.parameters["params"] if tree is None else tree
         return [t[m][k] for m, k in self._leaf_keys(t)]
 
+    def _dense(self, which=0):
+        """parameter group of the (which-th) RBM: the amplitude network for the two-network ansatz"""
+        return self.parameters["params"]["nets_%d/Dense_0" % which if self.kind == "tworbm" else "Dense_0"]
+
     @property
     def W(self):
-        return self.parameters["params"]["Dense_0"]["kernel"]
+        return self._dense()["kernel"]
 
     @property
     def b(self):
-        return self.parameters["params"]["Dense_0"].get("bias", None)
+        return self._dense().get("bias", None)
 
-    def _cW(self):
-        return self.W.to(torch.complex128), (None if self.b is None else self.b.to(torch.complex128))
+    def _cW(self, which=0):
+        d = self._dense(which)
+        b = d.get("bias", None)
+        return d["kernel"].to(torch.complex128), (None if b is None else b.to(torch.complex128))
 
     def _bump(self):
         self._version += 1
@@ -129,6 +139,10 @@ class NQS:
         flat, lead = self._flat_configs(s)
         if self.kind == "cnn":
             return K.cnn_logpsi(flat, self.get_parameters(), self._cnnDesc).reshape(lead)
+        if self.kind == "tworbm":
+            r, _ = K.rbm_logpsi(flat, *self._cW(0))
+            phi, _ = K.rbm_logpsi(flat, *self._cW(1))
+            return (r.real + 1j * phi.real).reshape(lead)      # reference two_nets_wrapper.py:19-21
         W, b = self._cW()
         if self.sym is not None:
             return K.symrbm_logpsi(flat, W, b, self.sym_tables()).reshape(lead)
@@ -165,6 +179,14 @@ class NQS:
         flat, lead = self._flat_configs(s)
         if self.kind == "cnn":
             g = K.cnn_grad(flat, self.get_parameters(), self._cnnDesc)
+        elif self.kind == "tworbm":
+            # real parameters: d Re log psi + i d Im log psi (reference :46-51) = [d r / d theta_r, i d phi / d theta_phi]
+            gs = []
+            for which in (0, 1):
+                W, b = self._cW(which)
+                _, tau = K.rbm_logpsi(flat, W, b)
+                gs.append(K.rbm_grad(flat, tau, b is not None, 1))
+            g = torch.cat([gs[0], 1j * gs[1]], dim=1)
         elif self.sym is not None:
             W, b = self._cW()
             _, wts = K.symrbm_logpsi(flat, W, b, self.sym_tables(), want_weights=True)
