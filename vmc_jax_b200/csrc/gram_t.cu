@@ -12,6 +12,7 @@
 // i.e. N (= number of sites) times fewer tensor flops than the dense product and no O in memory.
 // Pipeline as in gram.cu: TMA-engine bulk copies by a producer warp into an mbarrier-guarded smem ring, 16
 // DMMA consumer warps (CTA tile 64 x 64), Hermitian: only tile pairs nb >= mb, both images written.
+#include <type_traits>
 #include "common.cuh"
 
 namespace {
@@ -135,31 +136,36 @@ gram_t_kernel(const cplx* __restrict__ Y, long long B, int M, int R, const uint3
     const cplx* As = tiles + (size_t)slot * 2 * T_TS * T_LD;
     const cplx* Bs = As + (size_t)T_TS * T_LD;
     mbar_wait(full + slot, (unsigned)((kt / T_STAGES) & 1));
-    // hidden units beyond M in the last stage hold stale data from earlier stages -> mask them
+    // hidden units beyond M in the last stage hold stale data from earlier stages -> mask them there (only there:
+    // the selects cost issue slots the DMMA stream needs)
     const int kvalid = min(T_KC, M - kt * T_KC);
+    auto stage = [&](auto masked) {
+      constexpr bool MASK = decltype(masked)::value;
 #pragma unroll
-    for (int ks = 0; ks < T_KC / 4; ++ks) {
-      const int kk = ks * 4 + q4;
-      const bool ok = kk < kvalid;
-      cplx av = As[(size_t)(wm * 8 + q8) * T_LD + kk];
-      double ar = ok ? av.x : 0.0, ai = ok ? av.y : 0.0;
-      double nar = -ar;
-      double br[4], bi[4];
+      for (int ks = 0; ks < T_KC / 4; ++ks) {
+        const int kk = ks * 4 + q4;
+        const bool ok = !MASK || kk < kvalid;
+        cplx av = As[(size_t)(wm * 8 + q8) * T_LD + kk];
+        double ar = ok ? av.x : 0.0, ai = ok ? av.y : 0.0;
+        double nar = -ar;
+        double br[4], bi[4];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        cplx bv = Bs[(size_t)(wn * 32 + b * 8 + q8) * T_LD + kk];
-        br[b] = ok ? bv.x : 0.0;
-        bi[b] = ok ? bv.y : 0.0;
+        for (int b = 0; b < 4; ++b) {
+          cplx bv = Bs[(size_t)(wn * 32 + b * 8 + q8) * T_LD + kk];
+          br[b] = ok ? bv.x : 0.0;
+          bi[b] = ok ? bv.y : 0.0;
+        }
+        // a conj(b) = (ar br + ai bi) + i (ai br - ar bi)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          dmma884(cre[b][0], cre[b][1], ar, br[b]);
+          dmma884(cim[b][0], cim[b][1], ai, br[b]);
+          dmma884(cre[b][0], cre[b][1], ai, bi[b]);
+          dmma884(cim[b][0], cim[b][1], nar, bi[b]);
+        }
       }
-      // a conj(b) = (ar br + ai bi) + i (ai br - ar bi)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        dmma884(cre[b][0], cre[b][1], ar, br[b]);
-        dmma884(cim[b][0], cim[b][1], ai, br[b]);
-        dmma884(cre[b][0], cre[b][1], ai, bi[b]);
-        dmma884(cim[b][0], cim[b][1], nar, bi[b]);
-      }
-    }
+    };
+    if (kvalid == T_KC) stage(std::false_type{}); else stage(std::true_type{});
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + slot);
   }
