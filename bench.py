@@ -423,6 +423,7 @@ def main():
 
     # ---- TDVP step (sample + E_loc + O_k + S/F + SNR + solve) on the CPU-runnable config 1, for the "TDVP step ms" half
     tdvp_info = None
+    other_configs = {}
     if not args.no_tdvp and world == 1:
         try:
             tdvp_info = tdvp_step_ms(jVMC, op, torch)
@@ -432,6 +433,15 @@ def main():
             tdvp_info["config3"] = tdvp_step_ms_config3(jVMC, op, torch)
         except Exception as ex:  # pragma: no cover
             tdvp_info["config3"] = {"error": repr(ex)}
+        torch.cuda.empty_cache()
+        # the remaining BASELINE configs, bounded (auxiliary: not part of the headline metric)
+        for name, fn in (("config4_cnn_heisenberg", lambda: aux_config4_cnn(jVMC, op, torch)),
+                         ("config5_minsr_20x20", lambda: aux_config5_minsr(jVMC, op, torch, K))):
+            try:
+                other_configs[name] = fn()
+            except Exception as ex:  # pragma: no cover
+                other_configs[name] = {"error": repr(ex)}
+            torch.cuda.empty_cache()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
@@ -490,7 +500,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "note": "parameters H2D from pinned memory; <E>, VarE, F D2H; S stays on device for the solver"},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-                "phases_ms": phases, "kernels": kernels, "energy_mean": [energy.real, energy.imag], "tdvp_step": tdvp_info}
+                "phases_ms": phases, "kernels": kernels, "energy_mean": [energy.real, energy.imag], "tdvp_step": tdvp_info, "other_configs": other_configs}
         sys.stdout.flush()
         os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -552,6 +562,95 @@ def tdvp_step_ms_config3(jVMC, op, torch, L=40, alpha=2, nsamp=2 ** 16, chains=2
                       "(rhsPrefactor=1j, makeReal=imag, snrTol=2)" % (L, alpha, P, chains, smp.get_last_number_of_samples()),
             "ms_per_rhs": float(np.median(times[1:])), "rhs_per_adaptive_heun_attempt": 5,
             "solver_residual": _maybe_float(lambda: tdvp.get_residuals()[1])}
+
+
+def aux_config5_minsr(jVMC, op, torch, K, L=20, alpha=4, nsamp=2 ** 14, chains=1184):
+    """BASELINE configs[4] lattice on ONE GPU, bounded: 2D TFIM 20x20, CpxRBM alpha=4 (P_c = 640 000), sample + E_loc +
+    the MinSR tangent kernel T on N_T samples + (for N_T <= 4096) the full MinSR.__call__ incl. the pseudo-inverse."""
+    dev = jVMC.global_defs.myDevice
+    N, M = L * L, alpha * L * L
+    psi = jVMC.vqs.NQS(jVMC.nets.CpxRBM(numHidden=M, bias=False), seed=1234)
+    psi(torch.zeros((1, 1, L, L), dtype=torch.int32, device=dev))
+    W, _ = o1_weights(N, M, False)
+    psi.set_parameters(torch.as_tensor(flat_params(W, None)))
+    H = op.BranchFreeOperator()
+    for x in range(L):
+        for y in range(L):
+            l = x * L + y
+            H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz(x * L + (y + 1) % L))))
+            H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz(((x + 1) % L) * L + y))))
+            H.add(op.scal_opstr(3.04, (op.Sx(l),)))
+    smp = jVMC.sampler.MCSampler(psi, (L, L), 4321, updateProposer=jVMC.sampler.propose_spin_flip, numChains=chains,
+                                 sweepSteps=N, numSamples=nsamp, thermalizationSweeps=25)
+    smp.refreshEvery = 8
+
+    def timed(fn):
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); r = fn(); b_.record(); torch.cuda.synchronize()
+        return r, a.elapsed_time(b_)
+    smp.sample()
+    (s, logPsi, p), t_s = timed(lambda: smp.sample())
+    H.get_O_loc(s, psi, logPsi)
+    Eloc, t_e = timed(lambda: H.get_O_loc(s, psi, logPsi))
+    from vmc_jax_b200.stats import RBMGradientObs
+    G = RBMGradientObs(psi, s, p)
+    G.tangent_kernel()
+    T, t_t = timed(lambda: G.tangent_kernel())
+    B = s.shape[1]
+    out = {"config": "2D TFIM %dx%d, CpxRBM alpha=%d (P_c=%d), %d chains, %d samples on one GPU" % (L, L, alpha, N * M, chains, B),
+           "sampling_ms": t_s, "eloc_ms": t_e, "tangent_kernel_ms": t_t,
+           "tangent_kernel_tflops_dmma": 4.0 * B * B * M / (t_t * 1e-3) / 1e12,
+           "samples_per_s_sample_eloc_T": B / ((t_s + t_e + t_t) * 1e-3),
+           "note": "2^20 samples make the dense N_s x N_s tangent kernel (17.6 TB) infeasible on any number of B200s; "
+                   "T is formed on N_T = %d samples per step" % B}
+    del T, G
+    minsr = jVMC.util.MinSR(smp, pinvTol=1e-8)
+    nsmall = 4096
+    minsr(psi.get_parameters(), 0.0, psi=psi, hamiltonian=H, numSamples=nsmall)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    minsr(psi.get_parameters(), 0.0, psi=psi, hamiltonian=H, numSamples=nsmall)
+    torch.cuda.synchronize()
+    out["minsr_step_ms_4096_samples"] = (time.perf_counter() - t0) * 1e3
+    return out
+
+
+def aux_config4_cnn(jVMC, op, torch, L=12, nsamp=2 ** 12, chains=296):
+    """BASELINE configs[3] on ONE GPU, bounded: 2D Heisenberg J1 12x12 (Marshall-rotated), real CNN, exchange proposer:
+    sample + E_loc (s' enumeration + forward passes) + dense gradients + S, F.  Correctness-level kernels."""
+    dev = jVMC.global_defs.myDevice
+    H = op.BranchFreeOperator(ElocBatchSize=256)
+    for x in range(L):
+        for y in range(L):
+            i = x * L + y
+            for j in (x * L + (y + 1) % L, ((x + 1) % L) * L + y):
+                H.add(op.scal_opstr(-0.25, (op.Sx(i), op.Sx(j))))
+                H.add(op.scal_opstr(-0.25, (op.Sy(i), op.Sy(j))))
+                H.add(op.scal_opstr(0.25, (op.Sz(i), op.Sz(j))))
+    psi = jVMC.vqs.NQS(jVMC.nets.CNN(F=(3, 3), channels=(6, 4), strides=(1, 1), bias=True, firstLayerBias=False), seed=7)
+    neel = np.indices((L, L)).sum(0) % 2
+    smp = jVMC.sampler.MCSampler(psi, (L, L), 99, updateProposer=jVMC.sampler.propose_spin_flip_zeroMag, numChains=chains,
+                                 numSamples=nsamp, thermalizationSweeps=10, sweepSteps=L * L, initState=neel)
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
+        return r, (time.perf_counter() - t0) * 1e3
+    (s, logPsi, p), t_s = timed(lambda: smp.sample())
+    Eloc, t_e = timed(lambda: H.get_O_loc(s, psi, logPsi))
+    from vmc_jax_b200.stats import SampledObs
+
+    def stats():
+        E = SampledObs(Eloc, p)
+        G = SampledObs(psi.gradients(s), p)
+        return E.mean(), G.covar(E), G.covar()
+    (Em, F, S), t_g = timed(stats)
+    B = s.shape[1]
+    return {"config": "2D Heisenberg %dx%d, CNN F=(3,3) channels=(6,4) (P=%d real), exchange proposer, %d chains, %d "
+                      "samples on one GPU" % (L, L, psi.numParameters, chains, B),
+            "sampling_ms": t_s, "eloc_ms": t_e, "gradients_S_F_ms": t_g,
+            "samples_per_s": B / ((t_s + t_e + t_g) * 1e-3), "energy_per_site": float(Em.real.reshape(-1)[0]) / (L * L),
+            "acceptance": float(smp.acceptance_ratio())}
 
 
 def _maybe_float(f):
