@@ -527,11 +527,16 @@ extern "C" int jvmc_rbm_eloc_bfo(const int32_t* s, const double* tau, long long 
   const cplx* lc = T + (size_t)N * M;
 #define JVMC_ELOC(SPW, JT, WPS) launch_eloc<SPW, JT, WPS>(t, s, (const cplx*)tau, B, N, M, T, lc, (const cplx*)pref, \
                                                          numDiag, (cplx*)out, errFlag, (cudaStream_t)stream)
-#define JVMC_ELOC_JT(WPS)                                                                                          \
+#define JVMC_ELOC_LO(WPS)                                                                                          \
   switch ((M + 32 * WPS - 1) / (32 * WPS)) {                                                                       \
     case 1: return JVMC_ELOC(1, 1, WPS);   case 2: return JVMC_ELOC(1, 2, WPS);   case 3: return JVMC_ELOC(1, 3, WPS);   \
     case 4: return JVMC_ELOC(1, 4, WPS);   case 5: return JVMC_ELOC(1, 5, WPS);   case 6: return JVMC_ELOC(1, 6, WPS);   \
-    case 7: return JVMC_ELOC(1, 7, WPS);   case 8: return JVMC_ELOC(1, 8, WPS);   case 9: return JVMC_ELOC(1, 9, WPS);   \
+    case 7: return JVMC_ELOC(1, 7, WPS);   case 8: return JVMC_ELOC(1, 8, WPS);                                          \
+    default: break;                                                                                                \
+  }
+#define JVMC_ELOC_JT(WPS)                                                                                          \
+  switch ((M + 32 * WPS - 1) / (32 * WPS)) {                                                                       \
+    case 9: return JVMC_ELOC(1, 9, WPS);                                                                           \
     case 10: return JVMC_ELOC(1, 10, WPS); case 11: return JVMC_ELOC(1, 11, WPS); case 12: return JVMC_ELOC(1, 12, WPS); \
     case 13: return JVMC_ELOC(1, 13, WPS); case 14: return JVMC_ELOC(1, 14, WPS); case 15: return JVMC_ELOC(1, 15, WPS); \
     case 16: return JVMC_ELOC(1, 16, WPS);                                                                         \
@@ -539,7 +544,8 @@ extern "C" int jvmc_rbm_eloc_bfo(const int32_t* s, const double* tau, long long 
   }
   // tau in registers: one warp per sample up to M = 512, then 2 / 4 / 8 warps per sample (M <= 4096); the weight
   // rows are shared through L1 by the warps of a CTA
-  if (M <= 512) { JVMC_ELOC_JT(1) }
+  if (M <= 256) { JVMC_ELOC_LO(1) }
+  else if (M <= 512) { JVMC_ELOC_JT(1) }
   else if (M <= 1024) { JVMC_ELOC_JT(2) }
   else if (M <= 2048) { JVMC_ELOC_JT(4) }
   else if (M <= 4096) { JVMC_ELOC_JT(8) }
@@ -548,5 +554,6 @@ extern "C" int jvmc_rbm_eloc_bfo(const int32_t* s, const double* tau, long long 
   if (rc == JVMC_ERR_UNSUPPORTED) rc = JVMC_ELOC(1, 0, 1);
   return rc;
 #undef JVMC_ELOC_JT
+#undef JVMC_ELOC_LO
 #undef JVMC_ELOC
 }

@@ -512,16 +512,22 @@ int launch_flip(const McmcArgs& a, cudaStream_t stream) {
   return JVMC_OK;
 }
 
-// JT = ceil(M / (32 WPCH)) in 1..16
+// JT = ceil(M / (32 WPCH)) in 1..16; with several warps per chain only 9..16 occur (M > 256 WPCH)
 template <int WPCH>
 int dispatch_flip(const McmcArgs& a, cudaStream_t stream) {
-  switch ((a.M + 32 * WPCH - 1) / (32 * WPCH)) {
+  const int jt = (a.M + 32 * WPCH - 1) / (32 * WPCH);
 #define JVMC_FLIP(J) case J: return launch_flip<J, WPCH>(a, stream)
-    JVMC_FLIP(1); JVMC_FLIP(2); JVMC_FLIP(3); JVMC_FLIP(4); JVMC_FLIP(5); JVMC_FLIP(6); JVMC_FLIP(7); JVMC_FLIP(8);
+  if constexpr (WPCH == 1) {
+    switch (jt) {
+      JVMC_FLIP(1); JVMC_FLIP(2); JVMC_FLIP(3); JVMC_FLIP(4); JVMC_FLIP(5); JVMC_FLIP(6); JVMC_FLIP(7); JVMC_FLIP(8);
+      default: break;
+    }
+  }
+  switch (jt) {
     JVMC_FLIP(9); JVMC_FLIP(10); JVMC_FLIP(11); JVMC_FLIP(12); JVMC_FLIP(13); JVMC_FLIP(14); JVMC_FLIP(15); JVMC_FLIP(16);
-#undef JVMC_FLIP
     default: return JVMC_ERR_UNSUPPORTED;
   }
+#undef JVMC_FLIP
 }
 
 }  // namespace
