@@ -108,6 +108,7 @@ int jvmc_rbm_gram_S(const double* Y, long long B, int M, int R, const unsigned i
  * column 40 J, and the tile writes the elements jlo <= j < jhi, l <= j (plus their Hermitian images); the list must
  * cover every (j, l <= j) exactly once (vmc_jax_b200/kernels.py:i8_tile_list). */
 int jvmc_i8_layout(long long B, int M, long long* numChunks, int* numZGroups, long long* digitBytes);
+int jvmc_i8_tile_shape(int* rows, int* cols);   /* tile of jvmc_rbm_gram_S_i8 in real columns */
 int jvmc_i8_set_debug(int flags);   /* development ablations of the int8 Gram pipeline (timing only; results invalid) */
 int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long long* colmax, double* scale,
                   signed char* digits, void* stream);

@@ -9,7 +9,7 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjvmc_b200.so")
+LIB_PATH = os.environ.get("JVMC_B200_LIB") or os.path.join(_HERE, "libjvmc_b200.so")   # override: kernel variants (tools/)
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "jvmc_b200.h")
 
 _lib = None
@@ -41,6 +41,7 @@ _SIGS = {
     "jvmc_rbm_krmatvec": (c_int, [c_ptr, c_ptr, c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "jvmc_i8_layout": (c_int, [c_ll, c_int, ctypes.POINTER(c_ll), ctypes.POINTER(c_int), ctypes.POINTER(c_ll)]),
     "jvmc_i8_set_debug": (c_int, [c_int]),
+    "jvmc_i8_tile_shape": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "jvmc_mcmc_set_generic": (c_int, [c_int]),
     "jvmc_cnn_num_parameters": (c_int, [c_ptr, c_int, ctypes.POINTER(c_int)]),
     "jvmc_cnn_logpsi": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ll, c_ptr, c_ptr]),

@@ -26,7 +26,14 @@ namespace {
 
 constexpr int I8_S = 5;                 // digits
 constexpr int I8_LEV = 5;               // levels t = 2..6
-constexpr int I8_TM = 128, I8_TN = 80;  // tile in real columns (5 levels x 80 + 2 x 40 A-operand columns = 480 of 512 TMEM columns)
+#ifndef JVMC_I8_TN
+#define JVMC_I8_TN 80
+#endif
+#ifndef JVMC_I8_NB
+#define JVMC_I8_NB 2
+#endif
+constexpr int I8_NB = JVMC_I8_NB;       // TMEM A-operand buffers
+constexpr int I8_TM = 128, I8_TN = JVMC_I8_TN;  // tile in real columns (5 levels x 80 + 2 x 40 A-operand columns = 480 of 512 TMEM columns)
 constexpr int I8_KS = 32;               // samples per stage (one MMA K)
 constexpr int I8_SLOTS = 6;
 constexpr int I8_A_BYTES = I8_TM * I8_KS;   // per digit
@@ -34,7 +41,8 @@ constexpr int I8_B_BYTES = I8_TN * I8_KS;
 constexpr int I8_STAGE_BYTES = I8_S * (I8_A_BYTES + I8_B_BYTES);
 constexpr int I8_MAXSTAGES = 832;       // stages per launch: 832*32*5*127^2 < 2^31 (int32 head-room in TMEM)
 constexpr int I8_THREADS = 320;         // warp 0 producer, 1 MMA issuer, 2-9 sign (2-5 also epilogue)
-constexpr int I8_ACOL = I8_LEV * I8_TN;  // first TMEM column of the double-buffered A operand (2 x 5 digits x 8 columns)
+constexpr int I8_ACOL = I8_LEV * I8_TN;
+static_assert(I8_LEV * JVMC_I8_TN + JVMC_I8_NB * 5 * 8 <= 512, "TMEM columns");  // first TMEM column of the double-buffered A operand (2 x 5 digits x 8 columns)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -183,7 +191,8 @@ struct I8Args {
   int M, R;
   long long stage0, stage1;   // this launch covers sample stages [stage0, stage1), at most I8_MAXSTAGES
   int accumulate;             // 0: A = alpha G - kappa mu^H mu ; 1: A += alpha G
-  int dbg;                    // development ablations: 1 = MMA issue only, 2 = TMA + MMA (no sign pass)
+  int dbg;                    // development ablations: 1 = MMA issue only, 2 = TMA + MMA (no sign pass), 4 = no TMEM store,
+                              // 32 = no shared-memory reads in the sign pass, 64 = no sign arithmetic
   int cl;                     // thread-block cluster size along the pair axis (operand tiles are TMA-multicast)
   long long pairs;            // R (R + 1) / 2; CTAs beyond it only pad the last cluster
 };
@@ -195,8 +204,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   uint64_t* full = bars;                    // TMA bytes landed in the slot
   uint64_t* empty = bars + I8_SLOTS;        // MMAs reading the slot retired
   uint64_t* aready = bars + 2 * I8_SLOTS;   // [2] signed A digits of a stage are in TMEM buffer b
-  uint64_t* afree = aready + 2;             // [2] MMAs reading TMEM buffer b retired
-  uint64_t* accfull = afree + 2;
+  uint64_t* afree = aready + I8_NB;         // [NB] MMAs reading TMEM buffer b retired
+  uint64_t* accfull = afree + I8_NB;
   uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(accfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < I8_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, (unsigned)a.cl); }
-    for (int b = 0; b < 2; ++b) { mbar_init(aready + b, 8); mbar_init(afree + b, 1); }
+    for (int b = 0; b < I8_NB; ++b) { mbar_init(aready + b, 8); mbar_init(afree + b, 1); }
     mbar_init(accfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -258,10 +267,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       const uint32_t idesc3 = ibase | ((uint32_t)((3 * I8_TN) >> 3) << 17);
       for (long long g = 0; g < numStages; ++g) {
         const int slot = (int)(g % I8_SLOTS);
-        const int b = (int)(g & 1);
+        const int b = (int)(g % I8_NB);
         const uint32_t acc = (g == 0) ? 0u : 1u;
         if (!(a.dbg & 1)) mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
-        if (!(a.dbg & 3)) mbar_wait(aready + b, (unsigned)((g >> 1) & 1));
+        if (!(a.dbg & 3)) mbar_wait(aready + b, (unsigned)((g / I8_NB) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const unsigned sb = smem_u32(ring + (size_t)slot * I8_STAGE_BYTES) + I8_S * I8_A_BYTES;
         const uint32_t ta = tmem + (uint32_t)(I8_ACOL + b * I8_S * 8);
@@ -296,7 +305,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       const size_t rowOff = (size_t)(row >> 3) * 256 + (size_t)(row & 7) * 16;
       for (long long g = 0; g < ((a.dbg & 3) ? 0 : numStages); ++g) {
         const int slot = (int)(g % I8_SLOTS);
-        const int b = (int)(g & 1);
+        const int b = (int)(g % I8_NB);
         const uint32_t x = xn;                              // bit = 1 -> s_n = -1 (32 samples of the stage)
         if (g + 1 < numStages) xn = sg0[a.stage0 + g + 1] ^ sg1[a.stage0 + g + 1];
         uint32_t msk[8];
@@ -317,20 +326,21 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
           if (k >= nk) continue;
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
-            const uint4 v = *reinterpret_cast<const uint4*>(st + (kbeg + k) * I8_A_BYTES + ch * 128 + rowOff);
+            const uint4 v = (a.dbg & 32) ? make_uint4(0u, 0u, 0u, 0u)
+                                         : *reinterpret_cast<const uint4*>(st + (kbeg + k) * I8_A_BYTES + ch * 128 + rowOff);
             w[k][ch * 4 + 0] = v.x; w[k][ch * 4 + 1] = v.y; w[k][ch * 4 + 2] = v.z; w[k][ch * 4 + 3] = v.w;
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const uint32_t aa = w[k][q] ^ msk[q];
-            w[k][q] = ((aa & 0x7F7F7F7Fu) + (msk[q] & 0x01010101u)) ^ (aa & 0x80808080u);
+            if (!(a.dbg & 64)) w[k][q] = ((aa & 0x7F7F7F7Fu) + (msk[q] & 0x01010101u)) ^ (aa & 0x80808080u);
           }
         }
-        if (g >= 2) mbar_wait(afree + b, (unsigned)(((g >> 1) - 1) & 1));
+        if (g >= I8_NB) mbar_wait(afree + b, (unsigned)((g / I8_NB - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          if (k >= nk) continue;
+          if (k >= nk || (a.dbg & 4)) continue;
           const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(I8_ACOL + b * I8_S * 8 + (kbeg + k) * 8);
           asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr),
                        "r"(w[k][0]), "r"(w[k][1]), "r"(w[k][2]), "r"(w[k][3]), "r"(w[k][4]), "r"(w[k][5]), "r"(w[k][6]),
@@ -431,6 +441,13 @@ extern "C" int jvmc_i8_set_debug(int flags) {
   g_i8_dbg = flags & 0xFF;
   const int cl = (flags >> 8) & 0xF;
   if (cl == 1 || cl == 2 || cl == 4 || cl == 8) g_i8_cluster = cl;
+  return JVMC_OK;
+}
+
+// Tile shape in real columns (rows, cols); complex rows/columns are half of it.
+extern "C" int jvmc_i8_tile_shape(int* rows, int* cols) {
+  if (!rows || !cols) return JVMC_ERR_ARG;
+  *rows = I8_TM; *cols = I8_TN;
   return JVMC_OK;
 }
 

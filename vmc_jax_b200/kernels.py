@@ -310,7 +310,9 @@ def i8_tile_list(M, rows=64, cols=40):
 def _i8_tiles(M, device):
     key = (M, str(device))
     if key not in _I8_TILES:
-        _I8_TILES[key] = torch.tensor(i8_tile_list(M), dtype=I32, device=device).contiguous()
+        r, c = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(_lib.load().jvmc_i8_tile_shape(ctypes.byref(r), ctypes.byref(c)), "jvmc_i8_tile_shape")
+        _I8_TILES[key] = torch.tensor(i8_tile_list(M, r.value // 2, c.value // 2), dtype=I32, device=device).contiguous()
     return _I8_TILES[key]
 
 
