@@ -33,6 +33,11 @@ constexpr int I8_LEV = 5;               // levels t = 2..6
 #define JVMC_I8_NB 2
 #endif
 constexpr int I8_NB = JVMC_I8_NB;       // TMEM A-operand buffers
+#ifndef JVMC_I8_SIGNWARPS
+#define JVMC_I8_SIGNWARPS 8
+#endif
+constexpr int I8_SW = JVMC_I8_SIGNWARPS;  // 8: two warps per TMEM lane quarter (digits 1-3 / 4-5); 4: one warp, all digits
+constexpr int I8_KW = (I8_SW == 8) ? 3 : 5;   // digits per sign warp (max)
 constexpr int I8_TM = 128, I8_TN = JVMC_I8_TN;  // tile in real columns (5 levels x 80 + 2 x 40 A-operand columns = 480 of 512 TMEM columns)
 constexpr int I8_KS = 32;               // samples per stage (one MMA K)
 constexpr int I8_SLOTS = 6;
@@ -40,7 +45,7 @@ constexpr int I8_A_BYTES = I8_TM * I8_KS;   // per digit
 constexpr int I8_B_BYTES = I8_TN * I8_KS;
 constexpr int I8_STAGE_BYTES = I8_S * (I8_A_BYTES + I8_B_BYTES);
 constexpr int I8_MAXSTAGES = 832;       // stages per launch: 832*32*5*127^2 < 2^31 (int32 head-room in TMEM)
-constexpr int I8_THREADS = 320;         // warp 0 producer, 1 MMA issuer, 2-9 sign (2-5 also epilogue)
+constexpr int I8_THREADS = 64 + 32 * I8_SW;   // warp 0 producer, 1 MMA issuer, then the sign warps (2-5 also epilogue)
 constexpr int I8_ACOL = I8_LEV * I8_TN;
 static_assert(I8_LEV * JVMC_I8_TN + JVMC_I8_NB * 5 * 8 <= 512, "TMEM columns");  // first TMEM column of the double-buffered A operand (2 x 5 digits x 8 columns)
 
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < I8_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, (unsigned)a.cl); }
-    for (int b = 0; b < I8_NB; ++b) { mbar_init(aready + b, 8); mbar_init(afree + b, 1); }
+    for (int b = 0; b < I8_NB; ++b) { mbar_init(aready + b, I8_SW); mbar_init(afree + b, 1); }
     mbar_init(accfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -319,10 +324,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
         const unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
         // two warps share a TMEM lane quarter: warps 2-5 take digits 0-2, warps 6-9 digits 3-4
-        const int kbeg = (warp < 6) ? 0 : 3, nk = (warp < 6) ? 3 : 2;
-        uint32_t w[3][8];
+        const int kbeg = (warp < 6) ? 0 : 3, nk = (I8_SW == 4) ? I8_S : ((warp < 6) ? 3 : 2);
+        uint32_t w[I8_KW][8];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < I8_KW; ++k) {
           if (k >= nk) continue;
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         if (g >= I8_NB) mbar_wait(afree + b, (unsigned)((g / I8_NB - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < I8_KW; ++k) {
           if (k >= nk || (a.dbg & 4)) continue;
           const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(I8_ACOL + b * I8_S * 8 + (kbeg + k) * 8);
           asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr),
