@@ -60,10 +60,13 @@ __device__ __forceinline__ double conv_at(const CnnDesc& d, int l, const double*
   const int ix = d.ox[l], iy = d.oy[l];
   const double* Kp = theta + d.offK[l];
   double acc = d.hasBias[l] ? theta[d.offB[l] + co] : 0.0;
-  for (int fx = 0; fx < d.Fx; ++fx) {
-    const int qx = (px * d.sx + fx) % ix;
-    for (int fy = 0; fy < d.Fy; ++fy) {
-      const int qy = (py * d.sy + fy) % iy;
+  // wrap without integer division: the window start is inside the lattice, a tap wraps at most a few times
+  int qx = px * d.sx;
+  for (int fx = 0; fx < d.Fx; ++fx, ++qx) {
+    while (qx >= ix) qx -= ix;
+    int qy = py * d.sy;
+    for (int fy = 0; fy < d.Fy; ++fy, ++qy) {
+      while (qy >= iy) qy -= iy;
       const double* row = in + (size_t)(qx * iy + qy) * ci_n;
       const double* kr = Kp + (size_t)((fx * d.Fy + fy) * ci_n) * co_n + co;
       for (int ci = 0; ci < ci_n; ++ci) acc = fma(row[ci], kr[(size_t)ci * co_n], acc);
@@ -317,6 +320,13 @@ int make_desc(const int* h, int n, CnnDesc& d) {
   return JVMC_OK;
 }
 
+// threads per CTA: enough to give every thread a few output elements of the widest layer
+int cnn_threads(const CnnDesc& d) {
+  int widest = 0;
+  for (int l = 1; l <= d.nl; ++l) widest = max(widest, d.ox[l] * d.oy[l] * d.ch[l]);
+  return widest >= 1024 ? 512 : (widest >= 384 ? 256 : 128);
+}
+
 }  // namespace
 
 extern "C" int jvmc_cnn_num_parameters(const int* desc, int ndesc, int* P) {
@@ -337,7 +347,7 @@ extern "C" int jvmc_cnn_logpsi(const int* desc, int ndesc, const double* theta, 
   size_t smem = (size_t)(d.totA + 32) * sizeof(double);
   if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) cudaFuncSetAttribute(cnn_logpsi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cnn_logpsi_kernel<<<(unsigned)B, 128, smem, (cudaStream_t)stream>>>(d, theta, s, d.Lx * d.Ly, (cplx*)logpsi);
+  cnn_logpsi_kernel<<<(unsigned)B, cnn_threads(d), smem, (cudaStream_t)stream>>>(d, theta, s, d.Lx * d.Ly, (cplx*)logpsi);
   JVMC_CHECK_LAUNCH();
   return JVMC_OK;
 }
@@ -352,7 +362,7 @@ extern "C" int jvmc_cnn_grad(const int* desc, int ndesc, const double* theta, co
   size_t smem = (size_t)(3 * d.totA + 32) * sizeof(double);
   if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) cudaFuncSetAttribute(cnn_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cnn_grad_kernel<<<(unsigned)B, 128, smem, (cudaStream_t)stream>>>(d, theta, s, d.Lx * d.Ly, (cplx*)out);
+  cnn_grad_kernel<<<(unsigned)B, cnn_threads(d), smem, (cudaStream_t)stream>>>(d, theta, s, d.Lx * d.Ly, (cplx*)out);
   JVMC_CHECK_LAUNCH();
   return JVMC_OK;
 }
@@ -377,7 +387,7 @@ extern "C" int jvmc_cnn_mcmc(const int* desc, int ndesc, const double* theta, in
   size_t smem = (size_t)(d.totA + 32) * sizeof(double) + (size_t)2 * N * sizeof(int32_t);
   if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) cudaFuncSetAttribute(cnn_mcmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cnn_mcmc_kernel<<<(unsigned)C, 128, smem, (cudaStream_t)stream>>>(d, theta, a);
+  cnn_mcmc_kernel<<<(unsigned)C, cnn_threads(d), smem, (cudaStream_t)stream>>>(d, theta, a);
   JVMC_CHECK_LAUNCH();
   return JVMC_OK;
 }
