@@ -127,6 +127,12 @@ int jvmc_rbm_gram_T(const double* Y, long long B, int M, int R, const unsigned i
 
 /* S = q(S0) (+ diagonal shift) in the reference's flat layout from A: jVMC/util/tdvp.py:140-146.
  * mode 0: Re -> double[P,P]; mode 1: i*Im -> complex128[P,P]; column-major. */
+/* Multi-GPU reduction of the Hermitian A: only the suffix [r0 M, Pc) of every block row is communicated; this fills
+ * A[i][k] = conj(A[k][i]) below the block diagonal afterwards (blocks of M x M, A row-major complex128 [Pc, Pc]). */
+int jvmc_hermitian_mirror_blocks(double* A, int Pc, int M, void* stream);
+long long jvmc_hermitian_packed_elems(int Pc, int M);   /* complex elements of the packed upper block triangle */
+int jvmc_hermitian_pack_blocks(double* A, int Pc, int M, double* packed, int unpack, void* stream);
+
 int jvmc_expand_S(const double* A, int M, int N, int hasBias, int mode, double shift, double* out, void* stream);
 
 /* jnp.linalg.eigh (jVMC/util/tdvp.py:153-171): cuSOLVER Xsyevd, lower, vectors; column-major in/out. */

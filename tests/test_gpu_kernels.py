@@ -230,3 +230,19 @@ def test_cnn_logpsi_and_gradients(shape, F, channels, strides, act, bias, flb):
                                                    ((6,), (4,), "spin_flip_zeroMag", True)])
 def test_cnn_sampler_chi2(shape, F, proposer, sector):
     G.check_cnn_sampler(shape=shape, F=F, proposer=proposer, sector=sector)
+
+
+@pytest.mark.parametrize("R,M", [(3, 5), (7, 24), (4, 64), (11, 33)])
+def test_hermitian_mirror_blocks(R, M):
+    """rebuilds the part of a Hermitian matrix below the block diagonal from the part above (multi-GPU reduction)."""
+    import torch
+    Pc = R * M
+    g = torch.Generator(device="cuda").manual_seed(R * 100 + M)
+    X = torch.randn((Pc, Pc), dtype=torch.float64, device="cuda", generator=g) + \
+        1j * torch.randn((Pc, Pc), dtype=torch.float64, device="cuda", generator=g)
+    A = (X + X.conj().T).contiguous()
+    B = A.clone()
+    blk = torch.arange(Pc, device="cuda") // M
+    B[blk[:, None] > blk[None, :]] = float("nan")          # destroy everything below the block diagonal
+    G.K.hermitian_mirror_blocks(B, M)
+    assert torch.equal(B, A)

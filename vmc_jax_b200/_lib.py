@@ -41,6 +41,9 @@ _SIGS = {
     "jvmc_rbm_krmatvec": (c_int, [c_ptr, c_ptr, c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "jvmc_i8_layout": (c_int, [c_ll, c_int, ctypes.POINTER(c_ll), ctypes.POINTER(c_int), ctypes.POINTER(c_ll)]),
     "jvmc_i8_set_debug": (c_int, [c_int]),
+    "jvmc_hermitian_mirror_blocks": (c_int, [c_ptr, c_int, c_int, c_ptr]),
+    "jvmc_hermitian_packed_elems": (c_ll, [c_int, c_int]),
+    "jvmc_hermitian_pack_blocks": (c_int, [c_ptr, c_int, c_int, c_ptr, c_int, c_ptr]),
     "jvmc_i8_tile_shape": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "jvmc_mcmc_set_generic": (c_int, [c_int]),
     "jvmc_cnn_num_parameters": (c_int, [c_ptr, c_int, ctypes.POINTER(c_int)]),

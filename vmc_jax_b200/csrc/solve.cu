@@ -109,6 +109,40 @@ int ensure_handle() {
   return JVMC_OK;
 }
 
+
+// packed <-> A: the suffix [r M, Pc) of every matrix row i = (r, j), rows back to back (direction 0: pack, 1: unpack)
+__global__ void hermitian_pack_kernel(cplx* __restrict__ A, int Pc, int M, cplx* __restrict__ packed, int unpack) {
+  const int i = blockIdx.y;
+  const int r = i / M, j = i - r * M;
+  const long long c0 = (long long)r * M;
+  const long long off = (long long)M * ((long long)r * Pc - (long long)M * r * (r - 1) / 2) + (long long)j * (Pc - c0);
+  for (long long k = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < Pc; k += (long long)gridDim.x * blockDim.x) {
+    if (unpack) A[(size_t)i * Pc + k] = packed[off + k - c0];
+    else packed[off + k - c0] = A[(size_t)i * Pc + k];
+  }
+}
+
+// A[i][k] = conj(A[k][i]) for every element below the block diagonal (block = M x M): restores the full Hermitian
+// matrix after only the block rows' suffixes [r0 M, Pc) were all-reduced.  32 x 32 tiles through shared memory.
+__global__ void hermitian_mirror_kernel(cplx* __restrict__ A, int Pc, int M) {
+  __shared__ cplx tile[32][33];
+  const int bi = blockIdx.y, bk = blockIdx.x;          // destination tile (rows bi, cols bk), bk <= bi
+  if (bk > bi) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;        // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int srow = bk * 32 + r, scol = bi * 32 + tx; // source A[k][i]
+    if (srow < Pc && scol < Pc) tile[r][tx] = A[(size_t)srow * Pc + scol];
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, k = bk * 32 + tx;
+    if (i < Pc && k < Pc && k < (i / M) * M) {         // strictly below the block diagonal
+      const cplx v = tile[tx][r];
+      A[(size_t)i * Pc + k] = cmk(v.x, -v.y);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int jvmc_expand_S(const double* A, int M, int N, int hasBias, int mode, double shift, double* out,
@@ -165,6 +199,29 @@ extern "C" int jvmc_tdvp_regularize(int n, const double* ev, const double* VtF, 
   if (n <= 0 || !ev || !VtF || !F || !pinvEv || !scal) return JVMC_ERR_ARG;
   tdvp_regularize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, ev, (const cplx*)VtF, snr, (const cplx*)F, pinvTol,
                                                                pinvCutoff, snrTol, pinvEv, scal);
+  JVMC_CHECK_LAUNCH();
+  return JVMC_OK;
+}
+
+extern "C" int jvmc_hermitian_mirror_blocks(double* A, int Pc, int M, void* stream) {
+  if (!A || Pc <= 0 || M <= 0) return JVMC_ERR_ARG;
+  const unsigned nt = (unsigned)((Pc + 31) / 32);
+  hermitian_mirror_kernel<<<dim3(nt, nt), dim3(32, 8), 0, (cudaStream_t)stream>>>((cplx*)A, Pc, M);
+  JVMC_CHECK_LAUNCH();
+  return JVMC_OK;
+}
+
+/* number of complex elements of the packed upper block triangle */
+extern "C" long long jvmc_hermitian_packed_elems(int Pc, int M) {
+  if (Pc <= 0 || M <= 0 || Pc % M != 0) return -1;
+  const long long R = Pc / M;
+  return (long long)M * (R * Pc - (long long)M * R * (R - 1) / 2);
+}
+
+extern "C" int jvmc_hermitian_pack_blocks(double* A, int Pc, int M, double* packed, int unpack, void* stream) {
+  if (!A || !packed || Pc <= 0 || M <= 0 || Pc % M != 0 || Pc > 65535) return JVMC_ERR_ARG;
+  unsigned gx = (unsigned)((Pc + 1023) / 1024);
+  hermitian_pack_kernel<<<dim3(gx, (unsigned)Pc), 256, 0, (cudaStream_t)stream>>>((cplx*)A, Pc, M, (cplx*)packed, unpack);
   JVMC_CHECK_LAUNCH();
   return JVMC_OK;
 }

@@ -357,6 +357,25 @@ def rbm_gram_T(s, tau, p, mu, hasBias, scale=1.0):
     return T
 
 
+def hermitian_pack_blocks(A, M, packed=None, unpack=False):
+    """Upper block triangle of A (row suffixes [r M, Pc)) <-> packed 1-d buffer."""
+    assert A.dtype == CPX and A.is_contiguous() and A.shape[0] == A.shape[1]
+    Pc = int(A.shape[0])
+    n = _lib.load().jvmc_hermitian_packed_elems(Pc, int(M))
+    if packed is None:
+        packed = torch.empty(n, dtype=CPX, device=A.device)
+    assert packed.numel() == n
+    call("jvmc_hermitian_pack_blocks", ptr(A), Pc, int(M), ptr(packed), int(bool(unpack)))
+    return packed
+
+
+def hermitian_mirror_blocks(A, M):
+    """In place: A[i][k] = conj(A[k][i]) below the block diagonal (blocks M x M)."""
+    assert A.dtype == CPX and A.is_contiguous() and A.shape[0] == A.shape[1]
+    call("jvmc_hermitian_mirror_blocks", ptr(A), int(A.shape[0]), int(M))
+    return A
+
+
 def expand_S(A, M, N, hasBias, mode, shift):
     """Column-major S = q(S0) in the reference's flat layout (returned as a [P,P] tensor holding S^T)."""
     Mb = M if hasBias else 0

@@ -75,6 +75,25 @@ def first_sample_id():
     return firstSampleId
 
 
+def all_reduce_hermitian_blocks(A, M):
+    """SUM all-reduce of a fully populated Hermitian matrix A [Pc, Pc] with block structure M x M, moving half the
+    bytes: the suffix [r0 M, Pc) of every block row (contiguous per matrix row) is packed, reduced and unpacked, the
+    part below the block diagonal is rebuilt by conjugate transposition (kernels.hermitian_mirror_blocks)."""
+    global communicationTime
+    _refresh()
+    if commSize == 1:
+        return A
+    from . import kernels as K
+    t0 = time.perf_counter()
+    packed = K.hermitian_pack_blocks(A, M)
+    dist.all_reduce(torch.view_as_real(packed), op=dist.ReduceOp.SUM)
+    K.hermitian_pack_blocks(A, M, packed, unpack=True)
+    del packed
+    K.hermitian_mirror_blocks(A, M)
+    communicationTime += time.perf_counter() - t0
+    return A
+
+
 def _all_reduce_sum(x):
     """In-place SUM all-reduce of a device tensor (complex via its real view)."""
     global communicationTime

@@ -241,7 +241,11 @@ class RBMGradientObs(SampledObs):
                 A = gram(self._tau, self._sigT, mu, float(self._uniform), kappa)
             else:
                 A = gram(self._tau * torch.sqrt(p)[:, None], self._sigT, mu, 1.0, kappa)
-            self._A = mpi._all_reduce_sum(A)
+            # Hermitian: from 8 ranks on communicate the upper block triangle only (half the bytes) and rebuild the
+            # rest; below that the pack / unpack / mirror passes cost more than the saved NVLink time (measured)
+            half = os.environ.get("JVMC_HERMITIAN_ALLREDUCE")
+            half = (mpi.commSize >= 8) if half is None else (half == "1")
+            self._A = mpi.all_reduce_hermitian_blocks(A, self.M) if half else mpi._all_reduce_sum(A)
         return self._A
 
     def _expand_S0(self):
