@@ -17,8 +17,8 @@
 
 namespace {
 
-constexpr int T_KC = 16;      // hidden units per stage
-constexpr int T_STAGES = 4;
+constexpr int T_KC = 32;      // hidden units per stage (512-byte bulk copies: the 256-byte ones of T_KC = 16 starve the consumers)
+constexpr int T_STAGES = 3;
 constexpr int T_TS = 64;      // CTA tile (samples)
 constexpr int T_LD = T_KC + 4;  // row pitch in complex elements, == 4 (mod 8): conflict-free LDS.128
 constexpr int T_NCW = 16;
