@@ -103,10 +103,11 @@ int jvmc_rbm_gram_S(const double* Y, long long B, int M, int R, const unsigned i
 
 /* Same contract as jvmc_rbm_gram_S on the tcgen05 INT8 tensor cores (Ozaki splitting, fp64-equivalent result):
  * jvmc_i8_layout -> scratch sizes; jvmc_i8_slice -> per-column power-of-two scales + 5 balanced base-255 int8 digits in
- * the UMMA canonical layout (digits must be zero-initialised); jvmc_rbm_gram_S_i8 -> A.  tiles: device int quadruples
- * (rowGroup, J, jlo, jhi), one per 128 x 80 real-column tile: rows start at complex row 4 rowGroup, columns at complex
- * column 40 J, and the tile writes the elements jlo <= j < jhi, l <= j (plus their Hermitian images); the list must
- * cover every (j, l <= j) exactly once (vmc_jax_b200/kernels.py:i8_tile_list). */
+ * the UMMA canonical layout (digits must be zero-initialised); jvmc_rbm_gram_S_i8 -> A.  tiles: device int array, 8 ints
+ * per tile (rowGroup, colGroup, NC, jlo, jhi, 0, 0, 0): 128 real rows from real column 8 rowGroup (complex row
+ * 4 rowGroup), NC real columns (multiple of 16, <= cols of jvmc_i8_tile_shape) from real column 8 colGroup; the tile
+ * writes the elements jlo <= j < jhi, l <= j (plus their Hermitian images); the list must cover every (j, l <= j)
+ * exactly once (vmc_jax_b200/kernels.py:i8_tile_list). */
 int jvmc_i8_layout(long long B, int M, long long* numChunks, int* numZGroups, long long* digitBytes);
 int jvmc_i8_tile_shape(int* rows, int* cols);   /* tile of jvmc_rbm_gram_S_i8 in real columns */
 int jvmc_i8_set_debug(int flags);   /* development ablations of the int8 Gram pipeline (timing only; results invalid) */

@@ -164,10 +164,13 @@ def test_i8_gram_tile_list_covers_lower_triangle_once(M, rows, cols):
     launches, so the host-built tile list must cover the lower triangle exactly once."""
     from vmc_jax_b200.kernels import i8_tile_list
     cover = np.zeros((M, M), dtype=np.int32)
-    for rg, J, lo, hi in i8_tile_list(M, rows, cols):
-        assert rg % 1 == 0 and 4 * rg <= lo and hi <= 4 * rg + rows      # written rows lie inside the tile
+    pad = max((2 * M + 127) // 128 * 128, (2 * M + 2 * cols - 1) // (2 * cols) * (2 * cols))   # jvmc_i8_layout
+    for rg, cg, nc, lo, hi in i8_tile_list(M, rows, cols):
+        assert 4 * rg <= lo and hi <= 4 * rg + rows                     # written rows lie inside the tile
+        assert nc % 16 == 0 and 16 <= nc <= 2 * cols and (8 * cg) % 2 == 0 and 8 * cg + nc <= pad
+        assert 8 * rg + 2 * rows <= pad
         j = np.arange(max(lo, 4 * rg), min(hi, M))
-        l = np.arange(cols * J, min(cols * J + cols, M))
+        l = np.arange(4 * cg, min(4 * cg + nc // 2, M))
         jj, ll = np.meshgrid(j, l, indexing="ij")
         cover[jj[ll <= jj], ll[ll <= jj]] += 1
     want = np.tril(np.ones((M, M), dtype=np.int32))

@@ -189,7 +189,8 @@ struct I8Args {
   const double* scale;     // [2M]
   const uint32_t* sigT;    // [R][words]
   long long words;
-  const int4* tiles;       // (first row group, column block J, jlo, jhi): rows written are jlo <= j < jhi
+  const int* tiles;        // 8 ints per tile: first row group, first column group, real columns NC (multiple of 16,
+                           // <= I8_TN), jlo, jhi (rows written: jlo <= j < jhi), 3 unused
   const cplx* mu;
   double alpha, kappa;
   cplx* A;
@@ -222,8 +223,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   const bool padCta = (long long)blockIdx.x >= a.pairs;
   int r1, r0;
   tri_decode(padCta ? 0 : blockIdx.x, r1, r0);   // r0 <= r1
-  const int4 tile = a.tiles[blockIdx.y];
-  const int RG = tile.x, TJ = tile.y;   // tile rows start at real column 8 RG (any multiple of 8), columns at 80 TJ
+  const int* tile = a.tiles + 8 * (size_t)blockIdx.y;
+  // tile rows start at real column 8 RG, its NC columns at real column 8 CG; tiles that end at the diagonal are
+  // narrower than I8_TN so that less of the rectangle above the diagonal is computed
+  const int RG = tile[0], CG = tile[1], NC = tile[2], jlo = tile[3], jhi = tile[4];
+  const unsigned bBytes = (unsigned)(NC * I8_KS);       // bytes of one B digit tile of a stage
   const long long numStages = a.stage1 - a.stage0;
 
   if (threadIdx.x == 0) {
@@ -248,14 +252,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       const int slot = (int)(g % I8_SLOTS);
       if (g >= I8_SLOTS) mbar_wait(empty + slot, (unsigned)((g / I8_SLOTS - 1) & 1));
       unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
-      if (lane == 0) mbar_expect_tx(full + slot, (unsigned)I8_STAGE_BYTES);
+      if (lane == 0) mbar_expect_tx(full + slot, (unsigned)(I8_S * I8_A_BYTES) + I8_S * bBytes);
       __syncwarp();
       if (lane < 2 * I8_S) {
         const int k = lane >> 1, which = lane & 1;
         const size_t base = ((size_t)(a.stage0 + g) * I8_S + k) * a.numZGroups;
-        unsigned char* dst = which == 0 ? st + k * I8_A_BYTES : st + I8_S * I8_A_BYTES + k * I8_B_BYTES;
-        const int8_t* src = a.dig + (base + (which == 0 ? (size_t)RG : (size_t)TJ * (I8_TN / 8))) * 256;
-        const unsigned bytes = which == 0 ? I8_A_BYTES : I8_B_BYTES;
+        unsigned char* dst = which == 0 ? st + k * I8_A_BYTES : st + I8_S * I8_A_BYTES + k * bBytes;   // B digits packed
+        const int8_t* src = a.dig + (base + (which == 0 ? (size_t)RG : (size_t)CG)) * 256;
+        const unsigned bytes = which == 0 ? (unsigned)I8_A_BYTES : bBytes;
         if (a.cl == 1) bulk_g2s(dst, src, bytes, full + slot);
         else if ((unsigned)lane % (unsigned)a.cl == crank) bulk_g2s_mc(dst, src, bytes, full + slot, cmask);   // my share
       }
@@ -267,9 +271,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       // TMEM column blocks, so ONE instruction with N = 80 n multiplies A_k with B_k'..B_k'+n-1 and accumulates into
       // levels k+k' .. k+k'+n-1: 7 instructions per stage instead of 15 (UTCIMMA issue is the scarce resource).
       const uint32_t ibase = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_TM >> 4) << 24);
-      const uint32_t idesc1 = ibase | ((uint32_t)((1 * I8_TN) >> 3) << 17);
-      const uint32_t idesc2 = ibase | ((uint32_t)((2 * I8_TN) >> 3) << 17);
-      const uint32_t idesc3 = ibase | ((uint32_t)((3 * I8_TN) >> 3) << 17);
+      const uint32_t idesc1 = ibase | ((uint32_t)((1 * NC) >> 3) << 17);
+      const uint32_t idesc2 = ibase | ((uint32_t)((2 * NC) >> 3) << 17);
+      const uint32_t idesc3 = ibase | ((uint32_t)((3 * NC) >> 3) << 17);
       for (long long g = 0; g < numStages; ++g) {
         const int slot = (int)(g % I8_SLOTS);
         const int b = (int)(g % I8_NB);
@@ -281,8 +285,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         const uint32_t ta = tmem + (uint32_t)(I8_ACOL + b * I8_S * 8);
         // (digit k, first k', count n): level column = (k + k' - 2) * 80
         auto mma = [&](int k, int kp, int n, uint32_t idesc, uint32_t accumulate) {
-          uint64_t db = umma_desc(sb + (kp - 1) * I8_B_BYTES, 128, 256);   // LBO: next 16-sample chunk, SBO: next 8 rows
-          umma_i8_ts(tmem + (uint32_t)((k + kp - 2) * I8_TN), ta + (uint32_t)((k - 1) * 8), db, idesc, accumulate);
+          uint64_t db = umma_desc(sb + (kp - 1) * bBytes, 128, 256);   // LBO: next 16-sample chunk, SBO: next 8 rows
+          umma_i8_ts(tmem + (uint32_t)((k + kp - 2) * NC), ta + (uint32_t)((k - 1) * 8), db, idesc, accumulate);
         };
         mma(1, 1, 3, idesc3, acc);      // levels 2,3,4 (first writer)
         mma(1, 4, 2, idesc2, acc);      // levels 5,6   (first writer)
@@ -369,14 +373,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
     const bool samePair = (r0 == r1);
     mbar_wait(accfull, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    for (int cb = 0; cb < I8_TN / 16; ++cb) {
+    for (int cb = 0; cb < NC / 16; ++cb) {
       double v[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) v[c] = 0.0;
 #pragma unroll
       for (int t = 0; t < I8_LEV; ++t) {
         uint32_t r[16];
-        const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(t * I8_TN + cb * 16);
+        const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(t * NC + cb * 16);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       // C[zrow][zcol] with both column scales; the partner lane (lane ^ 1) holds the other part of the same j
 #pragma unroll
       for (int cc = 0; cc < 8; ++cc) {
-        const int l = TJ * (I8_TN / 2) + cb * 8 + cc;
+        const int l = CG * 4 + cb * 8 + cc;
         const bool lok = l < a.M;
         const double c0 = lok ? v[2 * cc] * srow * a.scale[2 * l] : 0.0;          // column Re Y_l
         const double c1 = lok ? v[2 * cc + 1] * srow * a.scale[2 * l + 1] : 0.0;  // column Im Y_l
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         (void)p0;
         const double part = isIm ? (p1 - c0) : (c0 + p1);
         const double other = __shfl_xor_sync(0xffffffffu, part, 1);   // even lane receives Im G
-        if (!lok || j >= a.M || j < tile.z || j >= tile.w || l > j || isIm || padCta) continue;
+        if (!lok || j >= a.M || j < jlo || j >= jhi || l > j || isIm || padCta) continue;
         const double gr = a.alpha * part;
         const double gi = (l == j) ? 0.0 : a.alpha * other;
         const long long a0 = (long long)r0 * a.M + j, b1 = (long long)r1 * a.M + l;
@@ -490,9 +494,10 @@ extern "C" int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long 
   return JVMC_OK;
 }
 
-// tiles: device array of int quadruples (rowGroup, J, jlo, jhi): the tile's 128 rows start at real column 8 rowGroup
-// (complex row 4 rowGroup), its 80 columns at real column 80 J; it writes the elements jlo <= j < jhi, l <= j.  The
-// caller's list must cover every (j, l <= j) exactly once (later launches add into A).
+// tiles: device array of 8 ints per tile (rowGroup, colGroup, NC, jlo, jhi, 0, 0, 0): the tile's 128 rows start at real
+// column 8 rowGroup (complex row 4 rowGroup), its NC real columns (multiple of 16, <= 80) at real column 8 colGroup; it
+// writes the elements jlo <= j < jhi, l <= j.  The caller's list must cover every (j, l <= j) exactly once (later
+// launches add into A); digit rows up to 8 colGroup + NC must lie inside the padded layout of jvmc_i8_layout.
 extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale, long long B, int M, int R,
                                   const unsigned int* sigT, const int* tiles, int numTiles, const double* mu,
                                   double alpha, double kappa, double* A, void* stream) {
@@ -501,12 +506,13 @@ extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale
   long long digitBytes;
   jvmc_i8_layout(B, M, &a.numChunks, &a.numZGroups, &digitBytes);
   a.dig = (const int8_t*)digits; a.scale = scale; a.sigT = sigT; a.words = (B + 31) / 32;
-  a.tiles = (const int4*)tiles; a.mu = (const cplx*)mu; a.alpha = alpha; a.kappa = kappa; a.A = (cplx*)A;
+  a.tiles = tiles; a.mu = (const cplx*)mu; a.alpha = alpha; a.kappa = kappa; a.A = (cplx*)A;
   a.M = M; a.R = R;
   size_t smem = (size_t)I8_SLOTS * I8_STAGE_BYTES + 32 * sizeof(uint64_t);
   cudaFuncSetAttribute(gram_s_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   long long pairs = (long long)R * (R + 1) / 2;
   if (numTiles > 65535 || pairs > 2147483647LL) return JVMC_ERR_UNSUPPORTED;
+  // (tile descriptors are device data: NC in {16, 32, ..., I8_TN} and the padding bound are the caller's contract)
   a.cl = g_i8_cluster; a.pairs = pairs;
   dim3 grid((unsigned)((pairs + a.cl - 1) / a.cl * a.cl), (unsigned)numTiles);
   const long long numStages = a.numChunks / 2;

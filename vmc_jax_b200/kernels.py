@@ -287,23 +287,27 @@ _I8_TILES = {}
 
 
 def i8_tile_list(M, rows=64, cols=40):
-    """Tiles (rowGroup, J, jlo, jhi) of rows x cols complex elements (the kernel's tile is 128 x 80 real columns =
-    64 x 40 complex) covering every (j, l <= j) exactly once.
+    """Tiles (rowGroup, colGroup, NC, jlo, jhi) covering every (j, l <= j) exactly once: `rows` complex rows starting at
+    complex row 4 rowGroup, NC real columns starting at real column 8 colGroup (the kernel's full tile is 128 x 80 real
+    columns = 64 x 40 complex).
 
-    Full row blocks are anchored at the END of the row range (the block ending at row e needs ceil(e/cols) column
-    tiles), so the ragged remainder sits at rows [0, o) where it needs only ceil(o/cols) tiles instead of a full
-    tile row: 39 tiles at M = 400 (ideal 31.25; 46 with the remainder at the bottom)."""
+    Full row blocks are anchored at the END of the row range (the block ending at row e needs the columns [0, e)), so
+    the ragged remainder sits at rows [0, o) where it needs few columns; the last column tile of every row block is
+    only as wide as the diagonal requires (multiple of 16 real columns).  M = 400: 39 tiles, 2912 real columns
+    (ideal 2500; full-width tiles 3120; remainder at the bottom 3680)."""
     M4 = (M + 3) // 4 * 4            # row blocks start on 8-real-row (4 complex) boundaries of the digit layout
     nFull = M4 // rows
     o = M4 - rows * nFull
+    blocks = ([(0, 0, min(o, M))] if o > 0 else []) + \
+        [(o + rows * b, o + rows * b, min(o + rows * (b + 1), M)) for b in range(nFull)]
     tl = []
-    for J in range((min(o, M) + cols - 1) // cols):
-        tl.append((0, J, 0, min(o, M)))
-    for b in range(nFull):
-        lo = o + rows * b
-        hi = min(lo + rows, M)
-        for J in range((hi + cols - 1) // cols):
-            tl.append((lo // 4, J, lo, hi))
+    for start, lo, hi in blocks:
+        need = hi                                    # complex columns [0, hi)
+        for J in range((need + cols - 1) // cols):
+            c0 = cols * J
+            width = min(cols, need - c0)             # complex columns of this tile
+            nc = min(2 * cols, (2 * width + 15) // 16 * 16)
+            tl.append((start // 4, (2 * c0) // 8, nc, lo, hi))
     return tl
 
 
@@ -312,7 +316,8 @@ def _i8_tiles(M, device):
     if key not in _I8_TILES:
         r, c = ctypes.c_int(0), ctypes.c_int(0)
         _lib.check(_lib.load().jvmc_i8_tile_shape(ctypes.byref(r), ctypes.byref(c)), "jvmc_i8_tile_shape")
-        _I8_TILES[key] = torch.tensor(i8_tile_list(M, r.value // 2, c.value // 2), dtype=I32, device=device).contiguous()
+        tl = [t + (0, 0, 0) for t in i8_tile_list(M, r.value // 2, c.value // 2)]
+        _I8_TILES[key] = torch.tensor(tl, dtype=I32, device=device).contiguous()
     return _I8_TILES[key]
 
 
