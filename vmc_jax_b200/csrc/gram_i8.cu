@@ -10,16 +10,23 @@
 //    d_k in [-127, 127] (int8, symmetric so that negation is exact).  Digits are stored in the K-major SWIZZLE_NONE
 //    UMMA canonical layout [n/32][digit][z/8][(n/16)%2][z%8][n%16], so that a (tile, 32-sample stage, digit) is one
 //    contiguous block (one TMA bulk copy each).
-// 2. gram_s_i8_kernel: CTA = (site pair r<=r', tile I,J): rows = 128 real columns (64 complex j), cols = 96 real
-//    columns (48 complex l).  Per 32-sample stage the producer warp bulk-copies (TMA engine) 5 A-digit and 5 B-digit
-//    tiles into an mbarrier-guarded smem ring; four "sign" warps apply s_n to the A tiles by byte-wise negation;
-//    one thread issues 15 tcgen05.mma kind::i8 (M=128, N=96, K=32; SASS UTCIMMA), digit pair (k,k') accumulating
-//    exactly in int32 into the TMEM accumulator of level t = k+k' (5 levels x 96 columns = 480 TMEM columns).
+// 2. gram_s_i8_kernel: CTA = (site pair r<=r', tile): 128 real rows (64 complex j) x NC <= 80 real columns (the tile list
+//    comes from the host: kernels.py:i8_tile_list; tiles that end at the diagonal are narrower).  Clusters of two CTAs
+//    work on consecutive site pairs of the same tile and share every operand copy by TMA multicast.  Per 32-sample
+//    stage the producer warp bulk-copies (TMA engine) the 5 A-digit and 5 B-digit tiles into an mbarrier-guarded
+//    6-slot smem ring; eight "sign" warps apply s_n to the A digits (byte-wise SWAR negation in registers) and store
+//    them into a double-buffered TMEM A operand (tcgen05.st); one thread issues 7 tcgen05.mma kind::i8 (M=128,
+//    N = NC n, K=32; SASS UTCIMMA; A from TMEM, B from smem): digit pair (k,k') accumulates exactly in int32 into the
+//    TMEM accumulator of level t = k+k', and because the B digit tiles are contiguous in smem and the level
+//    accumulators adjacent TMEM column blocks, ONE instruction covers n consecutive digit pairs (5 levels x 80 columns
+//    + 2 x 40 A-operand columns = 480 of the 512 TMEM columns).
 //    One launch covers at most 26624 samples (int32 head-room); at its end four epilogue warps read TMEM
 //    (tcgen05.ld), weight level t by 255^-t in fp64, combine real/imag parts with a lane shuffle, apply scales, alpha
 //    and the mean correction and scatter the Hermitian images (later launches add into A).
 //    Dropped digit pairs (k+k' > 6) are below 4 * 255^-7 = 6e-17 of c_z c_z'; the splitting itself is exact to
 //    255^-5 = 9e-13 of the column scale.
+//    Compile-time knobs for experiments: JVMC_I8_TN (full tile width), JVMC_I8_NB (TMEM A buffers),
+//    JVMC_I8_SIGNWARPS (8 or 4).
 #include "common.cuh"
 
 namespace {
@@ -38,7 +45,7 @@ constexpr int I8_NB = JVMC_I8_NB;       // TMEM A-operand buffers
 #endif
 constexpr int I8_SW = JVMC_I8_SIGNWARPS;  // 8: two warps per TMEM lane quarter (digits 1-3 / 4-5); 4: one warp, all digits
 constexpr int I8_KW = (I8_SW == 8) ? 3 : 5;   // digits per sign warp (max)
-constexpr int I8_TM = 128, I8_TN = JVMC_I8_TN;  // tile in real columns (5 levels x 80 + 2 x 40 A-operand columns = 480 of 512 TMEM columns)
+constexpr int I8_TM = 128, I8_TN = JVMC_I8_TN;  // full tile in real columns
 constexpr int I8_KS = 32;               // samples per stage (one MMA K)
 constexpr int I8_SLOTS = 6;
 constexpr int I8_A_BYTES = I8_TM * I8_KS;   // per digit
@@ -46,8 +53,8 @@ constexpr int I8_B_BYTES = I8_TN * I8_KS;
 constexpr int I8_STAGE_BYTES = I8_S * (I8_A_BYTES + I8_B_BYTES);
 constexpr int I8_MAXSTAGES = 832;       // stages per launch: 832*32*5*127^2 < 2^31 (int32 head-room in TMEM)
 constexpr int I8_THREADS = 64 + 32 * I8_SW;   // warp 0 producer, 1 MMA issuer, then the sign warps (2-5 also epilogue)
-constexpr int I8_ACOL = I8_LEV * I8_TN;
-static_assert(I8_LEV * JVMC_I8_TN + JVMC_I8_NB * 5 * 8 <= 512, "TMEM columns");  // first TMEM column of the double-buffered A operand (2 x 5 digits x 8 columns)
+constexpr int I8_ACOL = I8_LEV * I8_TN;   // first TMEM column of the A operand buffers (I8_NB x 5 digits x 8 columns)
+static_assert(I8_LEV * JVMC_I8_TN + JVMC_I8_NB * 5 * 8 <= 512, "TMEM columns");
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
