@@ -3,7 +3,9 @@
 // Replaces MCSampler._get_samples / _sweep.perform_mc_update (reference jVMC/sampler.py:301-356)
 // and the proposers propose_spin_flip / _Z2 / _zeroMag (jVMC/sampler.py:15-19,30-39,42-64).
 //
-// One warp per Markov chain.  The chain keeps tau_j = tanh(theta_j) (theta = sigma W + b) in shared
+// Two kernels: rbm_mcmc_flip_kernel (below; single-flip proposers, the hot path) and the generic
+// rbm_mcmc_kernel (exchange proposer, anything else).  Generic kernel: one warp per Markov chain, the chain
+// keeps tau_j = tanh(theta_j) (theta = sigma W + b) in shared
 // memory and the configuration as a bit mask in registers (lane l owns sites 32l..32l+31).  A
 // proposal that flips sites a (and b) changes theta by Delta = -2 sigma_a W_a (- 2 sigma_b W_b) and
 //    psi(s')/psi(s) = prod_a cosh-prod(a) * prod_j [ d_j + tau_j n_j ],
@@ -260,7 +262,8 @@ rbm_mcmc_kernel(McmcArgs a) {
 //  * the row T_a of the NEXT proposal is copied global -> shared with cp.async while the current proposal is
 //    evaluated (the site of step st+1 only depends on the counter RNG, not on the accept decision), so the L2
 //    latency of the weight-row stream is off the per-step critical path;
-//  * the current row lives in registers (JT complex numbers per lane), the loop over hidden units is fully unrolled;
+//  * tau lives in registers (JT complex numbers per lane), the rows in two ping-pong shared buffers, the loop over
+//    hidden units is fully unrolled (JT = ceil(M / 32 / WPCH) exactly, zero padding instead of predicates);
 //  * Philox is evaluated once per 32 steps (lane l computes step base + l) and broadcast by shuffles;
 //  * exp(mu Re lc_a) comes from a per-CTA shared table instead of an exp per proposal.
 // Same RNG counters as the generic kernel: the accept/reject sequence is identical up to floating-point rounding.
