@@ -64,6 +64,20 @@ class Operator(metaclass=abc.ABCMeta):
         out = K.oloc_reduce(matEl.reshape(-1, Kmax), logPsiS.reshape(-1), logPsiSP.reshape(-1))
         return out.reshape(lead)
 
+    @staticmethod
+    def _eval_deduplicated(psi, sp):
+        """psi on the connected configurations, evaluating runs of identical consecutive rows once.  get_s_primes keeps
+        the reference's layout (XX and YY strings of a bond give the same s' twice, padding repeats the last s'), so
+        for exchange-type operators about half of the forward passes are duplicates."""
+        if getattr(psi, "khatri_rao", False) or sp.shape[1] < 2:
+            return psi(sp)
+        flat = sp.reshape(sp.shape[1], -1)
+        uniq, inverse = torch.unique_consecutive(flat, dim=0, return_inverse=True)
+        if uniq.shape[0] > 0.75 * flat.shape[0]:
+            return psi(sp)
+        vals = psi(uniq.reshape((1, uniq.shape[0]) + tuple(sp.shape[2:])))
+        return vals.reshape(-1)[inverse].reshape(1, -1)
+
     def get_O_loc(self, samples, psi, logPsiS=None, *args):
         """O_loc(s) = sum_s' O_{s,s'} psi(s')/psi(s) (reference :166-192)."""
         samples = torch.as_tensor(samples).to(global_defs.myDevice).to(torch.int32)
@@ -80,7 +94,7 @@ class Operator(metaclass=abc.ABCMeta):
         if self.ElocBatchSize > 0:
             return self.get_O_loc_batched(samples, psi, logPsiS, self.ElocBatchSize, *args)
         sampleOffdConfigs, _ = self.get_s_primes(samples, *args)
-        logPsiSP = psi(sampleOffdConfigs)
+        logPsiSP = self._eval_deduplicated(psi, sampleOffdConfigs)
         if not psi.logarithmic:
             logPsiSP = torch.log(logPsiSP)
         return self.get_O_loc_unbatched(logPsiS, logPsiSP)
@@ -105,7 +119,7 @@ class Operator(metaclass=abc.ABCMeta):
         for lo, hi in bounds:
             batch = samples[:, lo:hi].contiguous()
             sp, _ = self.get_s_primes(batch, *args)
-            logPsiSP = psi(sp)
+            logPsiSP = self._eval_deduplicated(psi, sp)
             if not psi.logarithmic:
                 logPsiSP = torch.log(logPsiSP)
             Oloc[:, lo:hi] = self.get_O_loc_unbatched(logPsiS[:, lo:hi], logPsiSP)
