@@ -19,6 +19,7 @@ ap.add_argument("--tile", type=int, default=0)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--dbg", type=int, default=0)
 ap.add_argument("--i8", action="store_true")
+ap.add_argument("--clocks", action="store_true", help="sample nvidia-smi SM clock / power during the timed repetitions")
 a = ap.parse_args()
 TILE_ARG = a.tile + 1000 * (0 if a.i8 else a.dbg)
 from vmc_jax_b200 import _lib  # noqa: E402
@@ -48,6 +49,12 @@ if a.i8:
     print("i8 vs fp64 DMMA: max abs diff %.3e, scale %.3e, hermitian %s" % (float((A8 - A).abs().max()), float(A.abs().max()),
                                                                      bool(torch.equal(A8, A8.conj().T))))
     del A8
+clk = None
+if a.clocks:
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import ClockSampler
+    clk = ClockSampler(0)
+    clk.start()
 ts = []
 for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -57,6 +64,8 @@ for _ in range(a.reps):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 ms = min(ts)
+if clk is not None:
+    print("clocks under load:", clk.stop())
 TS = a.tile or (80 if (a.M % 80 == 0 or a.M == 40) else 64)
 nT = (a.M + TS - 1) // TS
 execf = 8.0 * a.B * (a.N * (a.N + 1) / 2) * (nT * (nT + 1) / 2) * TS * TS
