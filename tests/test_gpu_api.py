@@ -655,3 +655,47 @@ def test_two_nets_gradients_and_sampling():
     pmc = torch.zeros(16, dtype=torch.float64, device=ints.device).index_add_(0, ints, p[0])
     assert float(torch.max(torch.abs(pmc / pmc.sum() - pex.reshape(-1)[:16]))) < 2e-3
     assert float(lp.imag.abs().max()) > 0        # the phase network contributes
+
+
+@pytest.mark.parametrize("makeReal,x,shift,bias", [('real', 1.0, 0.0, False), ('real', 1.0, 3.0, True),
+                                                  ('imag', 1.j, 0.0, False), ('imag', 1.j, 0.0, True)])
+def test_tdvp_pc_level_solve_matches_reference_layout(makeReal, x, shift, bias):
+    """TDVP.solve through the P_c x P_c complex eigen-decomposition vs the reference's doubled P x P layout on the
+    same samples: spectrum, forces, solver outputs; eigenvector matrix V (built on demand) diagonalises q(S0)."""
+    L = 6
+    psi = NQS(nets.CpxRBM(numHidden=5, bias=bias), seed=7)
+    psi(torch.zeros((1, 1, L), dtype=torch.int32))
+    rng = np.random.default_rng(5)
+    n = psi.get_parameters().shape[0]
+    psi.set_parameters(torch.as_tensor(0.4 * rng.standard_normal(n)))
+    H = tfim(L, -1.0, -0.8)
+    for exact in (True, False):
+        smp = sampler.ExactSampler(psi, L) if exact else \
+            sampler.MCSampler(psi, (L,), 3, numSamples=4000, updateProposer=sampler.propose_spin_flip, numChains=200)
+        s, logPsi, p = smp.sample()
+        Eloc = SampledObs(H.get_O_loc(s, psi, logPsi), p)
+        out = []
+        for pc in (True, False):
+            td = jVMC.util.TDVP(smp, snrTol=2, pinvTol=1e-8, pinvCutoff=1e-8, rhsPrefactor=x, makeReal=makeReal,
+                                diagonalShift=shift)
+            td.pcLevel = pc
+            upd, res, cut = td.solve(Eloc, RBMGradientObs(psi, s, p))
+            out.append((td, upd, res, cut))
+        (a, ua, ra, ca), (b, ub, rb, cb) = out
+        scale = float(b.ev.abs().max())
+        assert torch.allclose(a.ev, b.ev, atol=1e-10 * scale)
+        assert torch.allclose(a.F0, b.F0, rtol=1e-12, atol=1e-14)
+        assert torch.allclose(a.S.to(torch.complex128), b.S.to(torch.complex128), atol=1e-12 * scale)
+        # the doubled eigenbasis reconstructed from the eigenvectors of A is orthonormal and diagonalises q(S0)
+        V = a.V.to(torch.complex128)
+        S = b.S.to(torch.complex128)
+        assert torch.allclose(V.conj().T @ V, torch.eye(V.shape[0], dtype=V.dtype, device=V.device), atol=1e-10)
+        assert torch.allclose(V.conj().T @ S @ V, torch.diag(a.ev).to(V.dtype), atol=1e-9 * scale)
+        # basis-independent quantities: |VtF|^2 and rhoVar summed over each (possibly degenerate) eigenvalue cluster
+        assert np.isclose(float((a.VtF.abs() ** 2).sum()), float((b.VtF.abs() ** 2).sum()), rtol=1e-9)
+        assert np.isclose(float(a.rhoVar.sum()), float(b.rhoVar.sum()), rtol=1e-8)
+        if makeReal == 'imag' or exact:
+            # unique eigenvectors ('imag': +-lambda) or no SNR weighting (exact sampler): identical update
+            assert float(cb) == float(ca)
+            assert torch.allclose(ua, ub, rtol=1e-6, atol=1e-8 * float(ub.abs().max()))
+            assert np.isclose(float(ra), float(rb), rtol=1e-6, atol=1e-10)

@@ -171,6 +171,15 @@ class RBMGradientObs(SampledObs):
         parts += [v[Mb:], 1j * v[Mb:]]
         return torch.cat(parts)
 
+    def _kr_to_flat_conj(self, v):
+        """covar(grads, E) layout: sum conj(dO) dE in c = r*M + j order -> flat (holomorphic: per leaf [f, -i f])."""
+        v = v.reshape(-1)
+        if not self.holomorphic:
+            return v
+        Mb = self.M if self.hasBias else 0
+        parts = ([v[:Mb], -1j * v[:Mb]] if self.hasBias else []) + [v[Mb:], -1j * v[Mb:]]
+        return torch.cat(parts)
+
     def kr_mean(self):
         if self._mu is None:
             mu = K.rbm_moments(self._s, self._tau, self._p.to(torch.complex128), self.hasBias, 0)

@@ -6,6 +6,8 @@ factorised (stats.RBMGradientObs); S is assembled by the DMMA Gram kernel at the
 for the eigensolver; the cutoff loop of the pseudo-inverse runs in one kernel without host round trips."""
 import warnings
 
+import os
+
 import numpy as np
 import torch
 
@@ -52,6 +54,12 @@ class TDVP:
         self.crossValidation = crossValidation
         self.diagonalizeOnDevice = diagonalizeOnDevice
         self.metaData = None
+        # holomorphic (Cpx)RBM: diagonalise the P_c x P_c complex Gram A instead of the reference's doubled P x P matrix
+        # (S0 = A (x) [[1, i], [-i, 1]], so q(S0) has the spectrum of A twice ('real') or +-A ('imag')); set to False to
+        # force the reference-layout path
+        self.pcLevel = os.environ.get("JVMC_TDVP_PC_LEVEL", "1") != "0"
+        self._S = None
+        self._S_lazy = None
         self._mode = 1 if makeReal == 'imag' else 0
         self.makeReal = imagFun if makeReal == 'imag' else realFun
         self.trafo_helper = lambda x: transform_helper(x, rhsPrefactor=self.rhsPrefactor, makeReal=self.makeReal)
@@ -92,6 +100,19 @@ class TDVP:
 
     def get_S(self):
         return self.S
+
+    @property
+    def S(self):
+        """q(S0) (+ diagonal shift) in the reference layout; built on demand after a P_c-level solve."""
+        if self._S is None and self._S_lazy is not None:
+            self._S = self._S_lazy()
+            self._S_lazy = None
+        return self._S
+
+    @S.setter
+    def S(self, val):
+        self._S = val
+        self._S_lazy = None
 
     @property
     def S0(self):
@@ -138,6 +159,23 @@ class TDVP:
 
     @property
     def V(self):
+        """eigenvectors of q(S0) as columns (reference layout); after a P_c-level solve the doubled basis is built on
+        demand from the eigenvectors of A"""
+        if self._Vt is None and getattr(self, "_pc", None) is not None:
+            evc, Vtc = self._pc
+            G = self._gradObs
+            Pc = evc.shape[0]
+            if self._mode == 0:
+                rows = []
+                for part in (0, 1):
+                    a, b = (Vtc.real, Vtc.imag) if part == 0 else (-Vtc.imag, Vtc.real)
+                    rows.append(torch.stack([self._flat_from_pairs(G, a[k], b[k]) for k in range(Pc)]))
+                self._Vt = torch.stack(rows, dim=1).reshape(2 * Pc, 2 * Pc)
+            else:
+                r2 = 2.0 ** -0.5
+                plus = torch.stack([self._flat_from_pairs(G, Vtc[k] * r2, -1j * Vtc[k] * r2) for k in range(Pc)])
+                minus = torch.stack([self._flat_from_pairs(G, Vtc[k].conj() * r2, 1j * Vtc[k].conj() * r2) for k in range(Pc)])
+                self._Vt = torch.cat([minus.flip(0), plus])
         return self._Vt.T
 
     def _get_snr(self, Eloc, gradients):
@@ -149,8 +187,96 @@ class TDVP:
             self.rhoVar = EO.var().reshape(-1)
         self.snr = torch.sqrt(torch.abs(mpi.globNumSamples * (self.VtF.conj() * self.VtF).real / self.rhoVar)).reshape(-1)
 
+    # ------------------------------------------------------------------ P_c-level solve (holomorphic RBM)
+    def _flat_from_pairs(self, G, gpart, igpart):
+        """real flat vector in the reference layout (per leaf [g-part, ig-part]) from its two P_c-level halves"""
+        Mb = G.M if G.hasBias else 0
+        parts = ([gpart[:Mb], igpart[:Mb]] if G.hasBias else []) + [gpart[Mb:], igpart[Mb:]]
+        return torch.cat(parts)
+
+    def _solve_pc(self, Eloc, G):
+        """TDVP.solve (reference :183-213) with the eigen-decomposition of the complex P_c x P_c Gram matrix A.
+
+        Flat layout index f = (c, part), part 0 = d/dRe, part 1 = d/dIm: S0 = A (x) K, K = [[1, i], [-i, 1]].
+        'real': q(S0) is the real representation of A: eigenpairs (lambda_k, [Re v_k; Im v_k]), (lambda_k, [-Im v_k; Re v_k]);
+        all projections are Re / Im of zeta = v_k^dagger z with z = -x <conj(dO) dE> at the P_c level.
+        'imag': q(S0) = i Im S0 has eigenpairs (+lambda_k, v_k (x) (1,-i)/sqrt2), (-lambda_k, conj(v_k) (x) (1,i)/sqrt2) with
+        projections zeta/sqrt2 and -conj(zeta)/sqrt2.  Degenerate pairs of 'real' get this basis (the reference's is
+        whatever LAPACK returns: the SNR-weighted update is basis dependent there)."""
+        x = self.rhsPrefactor
+        self.ElocMean = Eloc.mean()[0]
+        self.ElocVar = Eloc.var()[0]
+        fk = G.kr_covar_with(Eloc).reshape(-1)
+        self.F0 = (-x) * G._kr_to_flat_conj(fk)
+        F = self.makeReal(self.F0)
+        z = ((-x) * fk).to(torch.complex128)
+        self._gradObs = G
+        self._S0 = None
+        self._St = None
+        A = G.gram_A()
+        shift = float(self.diagonalShift)
+        mode = self._mode
+        self.S = None
+        self._S_lazy = lambda: (lambda St: St if mode == 0 else St.T)(K.expand_S(A, G.M, G.N, G.hasBias, mode, shift))
+        At = A.T.contiguous()                         # column-major A for cuSOLVER (eigh_inplace overwrites its input)
+        if mode == 0 and shift > 1e-10:
+            At.diagonal().mul_(1.0 + shift)           # S[f][f] *= 1 + shift acts on diag(Re A) in both halves
+        evc, Vtc, info = K.eigh_inplace(At)           # rows of Vtc = eigenvectors v_k
+        self._pc = (evc, Vtc)
+        self._Vt = None
+        zeta = torch.mv(Vtc.conj(), z)
+        # per-sample projections zeta_kn = v_k^dagger (-x conj(dO_n) dE_n): weighted first and second moments
+        B = G._s.shape[0]
+        Pc = evc.shape[0]
+        dE = (Eloc._data.reshape(-1) / torch.sqrt(G._p)).to(torch.complex128)
+        mu = G.kr_mean().reshape(-1)
+        s1 = torch.zeros(Pc, dtype=torch.complex128, device=A.device)
+        s2r = torch.zeros(Pc, dtype=torch.float64, device=A.device)
+        s2i = torch.zeros(Pc, dtype=torch.float64, device=A.device)
+        chunk = max(1, min(B, (2 ** 28) // max(Pc, 1)))
+        VcH = Vtc.conj().T.contiguous()
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            g = K.rbm_grad(G._s[lo:hi].contiguous(), G._tau[lo:hi].contiguous(), G.hasBias, 1)     # Khatri-Rao order
+            rho = ((-x) * (g - mu[None, :]).conj() * dE[lo:hi, None]) @ VcH
+            w = G._p[lo:hi]
+            s1 += (w[:, None] * rho).sum(0)
+            s2r += (w[:, None] * rho.real ** 2).sum(0)
+            s2i += (w[:, None] * rho.imag ** 2).sum(0)
+        s1, s2r, s2i = mpi._all_reduce_sum(s1), mpi._all_reduce_sum(s2r), mpi._all_reduce_sum(s2i)
+        if mode == 0:
+            self.ev = torch.repeat_interleave(evc, 2)
+            self.VtF = torch.stack([zeta.real, zeta.imag], dim=1).reshape(-1).to(torch.complex128)
+            self.rhoVar = torch.stack([s2r - s1.real ** 2, s2i - s1.imag ** 2], dim=1).reshape(-1)
+        else:
+            r2 = 2.0 ** -0.5
+            self.ev = torch.cat([-evc.flip(0), evc])
+            self.VtF = torch.cat([(-zeta.conj() * r2).flip(0), zeta * r2])
+            rv = 0.5 * (s2r + s2i - (s1.conj() * s1).real)
+            self.rhoVar = torch.cat([rv.flip(0), rv])
+        self.snr = torch.sqrt(torch.abs(mpi.globNumSamples * (self.VtF.conj() * self.VtF).real / self.rhoVar)).reshape(-1)
+        exact = _is_exact_sampler(self.sampler)
+        pinvEv, scal = K.tdvp_regularize(self.ev, self.VtF, None if exact else self.snr, F.to(torch.complex128),
+                                         float(self.pinvTol), float(self.pinvCutoff), float(self.snrTol))
+        self.invEv = torch.where(torch.abs(self.ev / self.ev[-1]) > 1e-14, 1. / self.ev, torch.zeros_like(self.ev))
+        coef = pinvEv * self.VtF
+        V = Vtc.T                                       # columns = eigenvectors
+        if mode == 0:
+            c = coef.reshape(-1, 2)
+            u = torch.mv(V, (c[:, 0].real + 1j * c[:, 1].real).to(torch.complex128))
+            update = self._flat_from_pairs(G, u.real, u.imag)
+        else:
+            cm, cp = coef[:Pc].flip(0), coef[Pc:]
+            P1 = torch.mv(V, cp)
+            P2 = torch.mv(V, cm.conj()).conj()
+            r2 = 2.0 ** -0.5
+            update = self._flat_from_pairs(G, (P1 + P2).real * r2, (P1.imag - P2.imag) * r2)
+        return update, scal[0], scal[1]
+
     def solve(self, Eloc, gradients):
         """reference :183-213."""
+        if self.pcLevel and self.diagonalizeOnDevice and isinstance(gradients, RBMGradientObs) and gradients.holomorphic:
+            return self._solve_pc(Eloc, gradients)
         self.S, F = self.get_tdvp_equation(Eloc, gradients)
         self._transform_to_eigenbasis(self.S, F)
         exact = _is_exact_sampler(self.sampler)
