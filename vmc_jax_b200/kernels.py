@@ -3,6 +3,7 @@
 torch is used for device memory and streams only; all arithmetic of the hot path happens in the
 kernels of libjvmc_b200.so.  Complex tensors are complex128, configurations int32."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -286,6 +287,9 @@ def rbm_gram_S(Y, sigT, mu, alpha, kappa, out=None, tile=0):
 _I8_TILES = {}
 
 
+NARROW_DIAGONAL_TILES = os.environ.get("JVMC_I8_NARROW", "1") != "0"
+
+
 def i8_tile_list(M, rows=64, cols=40):
     """Tiles (rowGroup, colGroup, NC, jlo, jhi) covering every (j, l <= j) exactly once: `rows` complex rows starting at
     complex row 4 rowGroup, NC real columns starting at real column 8 colGroup (the kernel's full tile is 128 x 80 real
@@ -306,7 +310,7 @@ def i8_tile_list(M, rows=64, cols=40):
         for J in range((need + cols - 1) // cols):
             c0 = cols * J
             width = min(cols, need - c0)             # complex columns of this tile
-            nc = min(2 * cols, (2 * width + 15) // 16 * 16)
+            nc = min(2 * cols, (2 * width + 15) // 16 * 16) if NARROW_DIAGONAL_TILES else 2 * cols
             tl.append((start // 4, (2 * c0) // 8, nc, lo, hi))
     return tl
 
