@@ -699,3 +699,32 @@ def test_tdvp_pc_level_solve_matches_reference_layout(makeReal, x, shift, bias):
             assert float(cb) == float(ca)
             assert torch.allclose(ua, ub, rtol=1e-6, atol=1e-8 * float(ub.abs().max()))
             assert np.isclose(float(ra), float(rb), rtol=1e-6, atol=1e-10)
+
+
+def test_tdvp_snr_second_moments_by_gram_kernel():
+    """'imag' mode with N_s >= 2 P_c >= 512: the SNR second moments come from a second Gram matrix
+    (RBMGradientObs.weighted_second_moment) instead of per-sample projections; same rhoVar / SNR / update as the
+    reference-layout path."""
+    L, M = 10, 26
+    psi = NQS(nets.CpxRBM(numHidden=M, bias=False), seed=3)
+    psi(torch.zeros((1, 1, L), dtype=torch.int32))
+    rng = np.random.default_rng(11)
+    psi.set_parameters(torch.as_tensor(0.3 * rng.standard_normal(psi.get_parameters().shape[0])))
+    H = tfim(L, -1.0, -0.8)
+    smp = sampler.MCSampler(psi, (L,), 3, numSamples=3000, updateProposer=sampler.propose_spin_flip, numChains=300)
+    s, logPsi, p = smp.sample()
+    assert s.shape[1] >= 2 * L * M
+    Eloc = SampledObs(H.get_O_loc(s, psi, logPsi), p)
+    out = []
+    for pc in (True, False):
+        td = jVMC.util.TDVP(smp, snrTol=2, pinvTol=1e-8, pinvCutoff=1e-8, rhsPrefactor=1.j, makeReal='imag')
+        td.pcLevel = pc
+        upd, res, cut = td.solve(Eloc, RBMGradientObs(psi, s, p))
+        out.append((td, upd, res, cut))
+    (a, ua, ra, ca), (b, ub, rb, cb) = out
+    assert torch.allclose(a.ev, b.ev, atol=1e-10 * float(b.ev.abs().max()))
+    big = b.rhoVar > 1e-8 * b.rhoVar.max()
+    assert torch.allclose(a.rhoVar[big], b.rhoVar[big], rtol=1e-6)
+    assert torch.allclose(a.snr[big], b.snr[big], rtol=1e-5)
+    assert float(ca) == float(cb)
+    assert torch.allclose(ua, ub, rtol=1e-5, atol=1e-7 * float(ub.abs().max()))

@@ -257,6 +257,18 @@ class RBMGradientObs(SampledObs):
             self._A = mpi.all_reduce_hermitian_blocks(A, self.M) if half else mpi._all_reduce_sum(A)
         return self._A
 
+    def weighted_second_moment(self, w2):
+        """sum_n w2_n conj(O_n) O_n^T in Khatri-Rao order (uncentred, Hermitian [R*M, R*M], global) for real weights
+        w2 >= 0 -- the same Gram kernel as gram_A with another weight vector (SNR second moments, util/tdvp.py)."""
+        if self._sigT is None:
+            self._sigT = K.pack_sigma(self._s, self.hasBias)
+        gram = K.rbm_gram_S_i8 if GRAM_BACKEND == "i8" else K.rbm_gram_S
+        Y = self._tau * torch.sqrt(w2.to(torch.float64))[:, None]
+        A2 = gram(Y, self._sigT, torch.zeros((self.R, self.M), dtype=torch.complex128, device=Y.device), 1.0, 0.0)
+        half = os.environ.get("JVMC_HERMITIAN_ALLREDUCE")
+        half = (mpi.commSize >= 8) if half is None else (half == "1")
+        return mpi.all_reduce_hermitian_blocks(A2, self.M) if half else mpi._all_reduce_sum(A2)
+
     def _expand_S0(self):
         A = self.gram_A()
         if not self.holomorphic:

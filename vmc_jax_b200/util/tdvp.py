@@ -230,20 +230,36 @@ class TDVP:
         Pc = evc.shape[0]
         dE = (Eloc._data.reshape(-1) / torch.sqrt(G._p)).to(torch.complex128)
         mu = G.kr_mean().reshape(-1)
-        s1 = torch.zeros(Pc, dtype=torch.complex128, device=A.device)
-        s2r = torch.zeros(Pc, dtype=torch.float64, device=A.device)
-        s2i = torch.zeros(Pc, dtype=torch.float64, device=A.device)
-        chunk = max(1, min(B, (2 ** 28) // max(Pc, 1)))
-        VcH = Vtc.conj().T.contiguous()
-        for lo in range(0, B, chunk):
-            hi = min(B, lo + chunk)
-            g = K.rbm_grad(G._s[lo:hi].contiguous(), G._tau[lo:hi].contiguous(), G.hasBias, 1)     # Khatri-Rao order
-            rho = ((-x) * (g - mu[None, :]).conj() * dE[lo:hi, None]) @ VcH
-            w = G._p[lo:hi]
-            s1 += (w[:, None] * rho).sum(0)
-            s2r += (w[:, None] * rho.real ** 2).sum(0)
-            s2i += (w[:, None] * rho.imag ** 2).sum(0)
-        s1, s2r, s2i = mpi._all_reduce_sum(s1), mpi._all_reduce_sum(s2r), mpi._all_reduce_sum(s2i)
+        Bglob = int(mpi.globNumSamples) if mpi.globNumSamples else B
+        if mode == 1 and Pc >= 256 and Bglob >= 2 * Pc:
+            # 'imag' only needs sum_n w_n |zeta_kn|^2 = |x|^2 sum_n w'_n |v_k^T (O_n - mu)|^2, w'_n = w_n |dE_n|^2: a second
+            # Gram matrix A' = sum w' conj(O) O^T (same tensor-core kernel) and P_c^3 instead of N_s P_c^2 projection flops
+            w2 = (G._p * (dE.conj() * dE).real).contiguous()
+            Ap = G.weighted_second_moment(w2)
+            m1 = mpi._all_reduce_sum(K.rbm_moments(G._s, G._tau, w2.to(torch.complex128), G.hasBias, 0)).reshape(-1)
+            W2 = mpi._all_reduce_sum(w2.sum().reshape(1))[0]
+            q = ((Ap @ Vtc.T) * Vtc.conj().T).sum(0).real             # v_k^dagger A' v_k
+            b = torch.mv(Vtc, mu)                                      # v_k^T mu
+            a1 = torch.mv(Vtc, m1)                                     # v_k^T sum w' O
+            second = abs(x) ** 2 * (q - 2.0 * (b.conj() * a1).real + W2 * (b.conj() * b).real)
+            s1 = zeta                                                  # sum_n w_n zeta_kn = v_k^dagger z
+            s2r, s2i = second, torch.zeros_like(second)
+            del Ap
+        else:
+            s1 = torch.zeros(Pc, dtype=torch.complex128, device=A.device)
+            s2r = torch.zeros(Pc, dtype=torch.float64, device=A.device)
+            s2i = torch.zeros(Pc, dtype=torch.float64, device=A.device)
+            chunk = max(1, min(B, (2 ** 28) // max(Pc, 1)))
+            VcH = Vtc.conj().T.contiguous()
+            for lo in range(0, B, chunk):
+                hi = min(B, lo + chunk)
+                g = K.rbm_grad(G._s[lo:hi].contiguous(), G._tau[lo:hi].contiguous(), G.hasBias, 1)     # Khatri-Rao order
+                rho = ((-x) * (g - mu[None, :]).conj() * dE[lo:hi, None]) @ VcH
+                w = G._p[lo:hi]
+                s1 += (w[:, None] * rho).sum(0)
+                s2r += (w[:, None] * rho.real ** 2).sum(0)
+                s2i += (w[:, None] * rho.imag ** 2).sum(0)
+            s1, s2r, s2i = mpi._all_reduce_sum(s1), mpi._all_reduce_sum(s2r), mpi._all_reduce_sum(s2i)
         if mode == 0:
             self.ev = torch.repeat_interleave(evc, 2)
             self.VtF = torch.stack([zeta.real, zeta.imag], dim=1).reshape(-1).to(torch.complex128)
