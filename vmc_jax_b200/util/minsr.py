@@ -20,6 +20,19 @@ def pinv_hermitian(T, rtol):
     return (V * inv.to(V.dtype)[None, :]) @ V.conj().T
 
 
+def pinv_hermitian_apply(T, rtol, b):
+    """pinv(T, rtol, hermitian=True) @ b without forming the pseudo-inverse: V (inv_ev * (V^dagger b)) -- two
+    matrix-vector products instead of an N^3 matrix product (T is destroyed on the device path's copy only)."""
+    if T.is_cuda:
+        ev, Vt, _ = K.eigh_inplace(T.T.contiguous())
+        V = Vt.T
+    else:
+        ev, V = torch.linalg.eigh(T)
+    cut = rtol * ev.abs().max()
+    inv = torch.where(ev.abs() > cut, 1.0 / torch.where(ev == 0, torch.ones_like(ev), ev), torch.zeros_like(ev))
+    return torch.mv(V, inv.to(V.dtype) * torch.mv(V.conj().T, b.to(V.dtype)))
+
+
 class MinSR:
     """reference jVMC/util/minsr.py:16-165; constructor as in the reference (:28)."""
 
@@ -46,9 +59,8 @@ class MinSR:
         """reference :53-80."""
         if holomorphic:
             T = gradients.tangent_kernel()
-            T_inv = pinv_hermitian(T, self.pinvTol)
-            eloc_all = mpi.gather(eloc._data).reshape(-1).to(T_inv.dtype)
-            x = T_inv @ eloc_all
+            eloc_all = mpi.gather(eloc._data).reshape(-1).to(T.dtype)
+            x = pinv_hermitian_apply(T, self.pinvTol, eloc_all)        # = pinv(T) @ eloc (reference :61-62)
             if isinstance(gradients, RBMGradientObs):
                 return gradients.minsr_contract(x)
             gradients_all = mpi.gather(gradients._data)
@@ -59,10 +71,9 @@ class MinSR:
         G = torch.cat([gradients_all.real, gradients_all.imag], dim=0)
         T = G @ G.T
         T = T + self.diagonalShift * torch.eye(T.shape[-1], dtype=T.dtype, device=T.device)
-        T_inv = pinv_hermitian(T, self.pinvTol)
         eloc_all = mpi.gather(eloc._data).reshape(-1)
         eloc_all = torch.cat([eloc_all.real, eloc_all.imag], dim=0)
-        return -G.T @ (T_inv @ eloc_all)
+        return -G.T @ pinv_hermitian_apply(T, self.pinvTol, eloc_all)
 
     def __call__(self, netParameters, t, *, psi, hamiltonian, **rhsArgs):
         """reference :82-165."""
