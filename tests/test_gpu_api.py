@@ -728,3 +728,14 @@ def test_tdvp_snr_second_moments_by_gram_kernel():
     assert torch.allclose(a.snr[big], b.snr[big], rtol=1e-5)
     assert float(ca) == float(cb)
     assert torch.allclose(ua, ub, rtol=1e-5, atol=1e-7 * float(ub.abs().max()))
+
+
+def test_nqs_orbit_argument_wraps_symnet():
+    """NQS(net, orbit=...) wraps the net into SymNet itself (reference vqs.py:170-173)."""
+    L = 4
+    orbit = _orbit_1d(L, "translation", "reflection")
+    a = NQS(nets.CpxRBM(numHidden=3, bias=True), orbit=orbit, seed=5)
+    b = NQS(nets.sym_wrapper.SymNet(net=nets.CpxRBM(numHidden=3, bias=True), orbit=orbit), seed=5)
+    s = torch.randint(0, 2, (1, 9, L), dtype=torch.int32, device="cuda")
+    assert a.kind == "symrbm" and torch.equal(a(s), b(s)) and torch.equal(a.gradients(s), b.gradients(s))
+    assert torch.equal(a.get_parameters(), b.get_parameters())
