@@ -200,3 +200,29 @@ def test_symmetry_orbits_match_oracle(kind, L, args, fac):
     for g in range(o.shape[0]):
         assert np.allclose(o[g] @ x, ls.sign[g] * x[ls.perm[g]])
         assert np.array_equal(ls.perm[g][ls.inv[g]], np.arange(n))
+
+
+def test_symmetry_orbit_sizes_reference_cases():
+    """reference tests/symmetries_test.py:17-44: every on/off combination of the lattice symmetries (None entries in
+    the argument list, as the reference test passes them), integer orbit matrices, expected group orders in 1-D."""
+    import warnings
+    from vmc_jax_b200.util import symmetries
+    L = 3
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for rotation in (True, False):
+            for reflection in (True, False):
+                for translation in (True, False):
+                    for spinflip in (True, False):
+                        symms = ("rotation" if rotation else None, "reflection" if reflection else None,
+                                 "translation" if translation else None, "spinflip" if spinflip else None)
+                        orbit = symmetries.get_orbit_2D_square(L, *symms)
+                        assert np.issubdtype(orbit.dtype, np.integer) and orbit.shape[1:] == (L * L, L * L)
+        for translation in (True, False):
+            for reflection in (True, False):
+                for spinflip in (True, False):
+                    symms = ("reflection" if reflection else None, "translation" if translation else None,
+                             "spinflip" if spinflip else None)
+                    orbit = symmetries.get_orbit_1D(L, *symms)
+                    assert orbit.shape[0] == (2 if reflection else 1) * (L if translation else 1) * (2 if spinflip else 1)
+                    assert np.issubdtype(orbit.dtype, np.integer)
