@@ -110,7 +110,7 @@ def cpu_reference_step(shape, g, alpha, bias, nsamp, chains, rng_seed=0, gram_co
     per-sample gradients and the zgemm Gram (jVMC/stats.py:52-58) -- the Gram is timed on a column block of
     ``gram_cols`` complex parameters and scaled to P_c (the full P_c x P_c host matrix does not fit every box).
     Returns (seconds for nsamp samples, detail)."""
-    from oracle import rbm as orbm, bfo as obfo, sampling as osamp, stats as ostats
+    from oracle import rbm as orbm, bfo as obfo, sampling as osamp
     N = int(np.prod(shape))
     M = alpha * N
     W, b = o1_weights(N, M, bias)

@@ -5,7 +5,6 @@ The MCMC here is the *reference's algorithm* (full forward pass per proposal,
 jVMC/sampler.py:327-356), vectorised over chains with NumPy; its random stream is NumPy's
 (the reference's threefry stream is parity-unpinned).
 """
-import math
 import numpy as np
 
 

@@ -8,7 +8,6 @@ Two device paths:
     tanh(theta) with per-parameter tables; s' is never materialised."""
 import abc
 
-import numpy as np
 import torch
 
 from .. import global_defs

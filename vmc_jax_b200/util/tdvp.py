@@ -4,14 +4,12 @@ Differences in *how* (not in what) it is computed: for (Cpx)RBM states the per-s
 factorised (stats.RBMGradientObs); S is assembled by the DMMA Gram kernel at the complex-parameter level
 (P_c x P_c instead of the reference's doubled P x P zgemm) and expanded into the reference's layout only
 for the eigensolver; the cutoff loop of the pseudo-inverse runs in one kernel without host round trips."""
-import warnings
 
 import os
 
 import numpy as np
 import torch
 
-from .. import global_defs
 from .. import kernels as K
 from .. import mpi_wrapper as mpi
 from ..stats import SampledObs, RBMGradientObs

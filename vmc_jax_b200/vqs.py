@@ -7,7 +7,7 @@ import torch
 
 from . import global_defs
 from . import kernels as K
-from .nets.rbm import CpxRBM, RBM, _RBMBase
+from .nets.rbm import _RBMBase
 from .nets.sym_wrapper import SymNet
 from .nets.cnn import CNN
 from .nets.two_nets_wrapper import TwoNets
