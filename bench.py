@@ -615,11 +615,11 @@ def aux_config5_minsr(jVMC, op, torch, K, L=20, alpha=4, nsamp=2 ** 14, chains=1
     return out
 
 
-def aux_config4_cnn(jVMC, op, torch, L=12, nsamp=2 ** 12, chains=296):
+def aux_config4_cnn(jVMC, op, torch, L=12, nsamp=2 ** 13, chains=1184):
     """BASELINE configs[3] on ONE GPU, bounded: 2D Heisenberg J1 12x12 (Marshall-rotated), real CNN, exchange proposer:
     sample + E_loc (s' enumeration + forward passes) + dense gradients + S, F.  Correctness-level kernels."""
     dev = jVMC.global_defs.myDevice
-    H = op.BranchFreeOperator(ElocBatchSize=256)
+    H = op.BranchFreeOperator(ElocBatchSize=2048)
     for x in range(L):
         for y in range(L):
             i = x * L + y

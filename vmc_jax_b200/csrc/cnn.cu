@@ -207,15 +207,22 @@ struct CnnMcmcArgs {
   int numSamples;
   int32_t* out;
   unsigned long long* counters;
+  int thetaInSmem;
 };
 
 // one CTA per chain, full forward pass per proposal
-__global__ void cnn_mcmc_kernel(CnnDesc d, const double* __restrict__ theta, CnnMcmcArgs a) {
+__global__ void cnn_mcmc_kernel(CnnDesc d, const double* theta, CnnMcmcArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* act = reinterpret_cast<double*>(smem_raw);
   double* red = act + d.totA;
   int32_t* cfg = reinterpret_cast<int32_t*>(red + 32);     // current configuration
   int32_t* prop = cfg + a.N;                                 // proposal
+  // the chain evaluates the net at every step: keep the parameters in shared memory when they fit
+  if (a.thetaInSmem) {
+    double* th = reinterpret_cast<double*>(prop + a.N + (a.N & 1));
+    for (int i = threadIdx.x; i < d.P; i += blockDim.x) th[i] = theta[i];
+    theta = th;
+  }
   __shared__ int sh_accept;
   const long long chain = blockIdx.x;
   const int N = a.N;
@@ -384,8 +391,10 @@ extern "C" int jvmc_cnn_mcmc(const int* desc, int ndesc, const double* theta, in
   a.states = states; a.C = C; a.N = N; a.seed = seed; a.step0 = step0; a.chain0 = chain0; a.proposer = proposer;
   a.mu = mu; a.K = sweepSteps; a.thermSteps = thermSteps; a.numSamples = numSamplesPerChain; a.out = out;
   a.counters = counters;
-  size_t smem = (size_t)(d.totA + 32) * sizeof(double) + (size_t)2 * N * sizeof(int32_t);
+  size_t smem = (size_t)(d.totA + 32) * sizeof(double) + (size_t)(2 * N + (N & 1)) * sizeof(int32_t);
   if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
+  a.thetaInSmem = (smem + (size_t)d.P * sizeof(double) <= 100 * 1024) ? 1 : 0;
+  if (a.thetaInSmem) smem += (size_t)d.P * sizeof(double);
   if (smem > 48 * 1024) cudaFuncSetAttribute(cnn_mcmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cnn_mcmc_kernel<<<(unsigned)C, cnn_threads(d), smem, (cudaStream_t)stream>>>(d, theta, a);
   JVMC_CHECK_LAUNCH();
