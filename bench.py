@@ -21,6 +21,20 @@ import sys
 import threading
 import time
 
+
+def _is_reference_arm(argv):
+    for i, a in enumerate(argv):
+        if a == "--impl=reference" or (a == "--impl" and i + 1 < len(argv) and argv[i + 1] == "reference"):
+            return True
+    return False
+
+
+if _is_reference_arm(sys.argv):
+    # the CPU arm uses every host core whatever the launcher exported (torch.distributed.run sets OMP_NUM_THREADS=1):
+    # the BLAS pools read these when numpy is first imported
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -37,6 +51,8 @@ DEFAULT_WORKLOAD = "tfim2d_10x10_cpxrbm_a4_2p16"
 _REAL_STDOUT = 1
 METRIC = "VMC step samples/sec (sample + E_loc + S/F)"
 UNIT = "samples/s"
+TDVP_METRIC = "TDVP step ms (sample + E_loc + O_k + S/F + eigh + SNR + regularised solve)"
+TDVP_WORKLOAD = "tfim1d_L20_cpxrbm_a2_2p12"
 
 
 def o1_weights(N, M, bias, seed=4321):
@@ -104,11 +120,27 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_step(shape, g, alpha, bias, nsamp, chains, rng_seed=0, gram_cols=4000):
+REF_SAMPLES, REF_CHAINS = 64, 32          # bounded sample of the workload one CPU "step" runs
+
+
+def host_threads():
+    """Threads the BLAS pool really uses (threadpoolctl), else the core count."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [int(x.get("num_threads", 0)) for x in threadpool_info() if x.get("user_api") == "blas"]
+        if n:
+            return max(n)
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_reference_step(shape, g, alpha, bias, nsamp, chains, rng_seed=0, gram_block=4000):
     """The reference's algorithm on the host cores (oracle port): Metropolis with a full forward pass per proposal
     (jVMC/sampler.py:327-356), get_s_primes -> psi(s') local energy (jVMC/operator/base.py:166-192), materialised
-    per-sample gradients and the zgemm Gram (jVMC/stats.py:52-58) -- the Gram is timed on a column block of
-    ``gram_cols`` complex parameters and scaled to P_c (the full P_c x P_c host matrix does not fit every box).
+    per-sample gradients and the zgemm Gram (jVMC/stats.py:52-58).  The whole P_c x P_c Gram is EXECUTED, in column
+    blocks of ``gram_block`` (each block is reduced to a checksum and dropped: the 25.6 GB host matrix of config 2 does
+    not fit every box).  The reference itself forms the doubled P x P = (2 P_c)^2 matrix, i.e. 4x this zgemm.
     Returns (seconds for nsamp samples, detail)."""
     from oracle import rbm as orbm, bfo as obfo, sampling as osamp
     N = int(np.prod(shape))
@@ -134,26 +166,72 @@ def cpu_reference_step(shape, g, alpha, bias, nsamp, chains, rng_seed=0, gram_co
     mu = p @ O
     D = np.sqrt(p)[:, None] * (O - mu[None, :])
     Fv = D.conj().T @ (np.sqrt(p) * (E - np.sum(p * E)))
-    cols = min(gram_cols, D.shape[1])
+    Dh = np.ascontiguousarray(D.conj().T)
     t3 = time.perf_counter()
-    Ablk = D.conj().T @ D[:, :cols]
+    chk, Pc = 0.0, D.shape[1]
+    for c0 in range(0, Pc, gram_block):
+        Ablk = Dh @ D[:, c0:c0 + gram_block]
+        chk += float(np.abs(Ablk[::97, ::89]).sum())
     t4 = time.perf_counter()
-    t_gram = (t4 - t3) * (D.shape[1] / cols)
-    total = (t1 - t0) + (t2 - t1) + (t3 - t2) + t_gram
+    total = t4 - t0
     detail = {"samples": int(cfg.shape[0]), "t_sample_s": t1 - t0, "t_eloc_s": t2 - t1, "t_grad_moments_s": t3 - t2,
-              "t_gram_scaled_s": t_gram, "gram_cols_timed": int(cols), "checksum": float(np.abs(Ablk).sum() + np.abs(Fv).sum())}
+              "t_gram_s": t4 - t3, "gram_cols": int(Pc), "gram_block": int(min(gram_block, Pc)),
+              "checksum": chk + float(np.abs(Fv).sum())}
     return total, detail
 
 
+def cpu_tdvp_step(L=20, alpha=2, nsamp=4096, chains=500, seed=0):
+    """One complete SR/TDVP step of BASELINE configs[0] by the reference's algorithm on the host (oracle port):
+    sample (full forward per proposal, 25 thermalisation sweeps) -> E_loc via s' -> dense gradients -> S, F ->
+    eigh(P x P) -> SNR -> regularised solve (jVMC/util/tdvp.py:219-290).  Returns (seconds, energy per site)."""
+    from oracle import rbm as orbm, bfo as obfo, sampling as osamp, solve as osolve
+    M = alpha * L
+    W, b = orbm.init_cpx_rbm(L, M, False)
+    ham = obfo.Tables(obfo.tfim_strings((L,), -0.7, -1.0))
+    f = lambda s: orbm.cpx_rbm_logpsi(s, W, b)
+    smp = osamp.MCSampler(lambda s: np.real(f(s)), L, numChains=chains, proposer="spin_flip_Z2",
+                          thermalizationSweeps=25, sweepSteps=L, seed=seed)
+    tdvp = osolve.TDVP(snrTol=2, pinvTol=1e-8, makeReal='real', rhsPrefactor=1., diagonalShift=10)
+    t0 = time.perf_counter()
+    cfg, glob = smp.sample(nsamp)
+    lp = f(cfg)
+    E = obfo.get_O_loc(ham, cfg, f, 0.0, logPsiS=lp)
+    p = np.ones(cfg.shape[0]) / cfg.shape[0]
+    upd, res, cut = osolve.tdvp_rhs(W, b, cfg, p, E, tdvp, glob, orbm.gradients_holomorphic)
+    t1 = time.perf_counter()
+    return t1 - t0, {"samples": int(cfg.shape[0]), "energy_per_site": float(np.real(tdvp.ElocMean)) / L,
+                     "residual": float(res), "update_norm": float(np.linalg.norm(upd))}
+
+
 def run_reference_arm(args, wl):
-    shape, g, alpha, bias, nsamp_gpu, chains_gpu = WORKLOADS[wl]
+    """`--impl reference`: the reference's own algorithm for the path, on the host cores (jax cannot be installed in this
+    image, so this is the oracle port, kind = "port").  Rank 0 alone works; every step is a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    nsamp, chains = 64, 32
+    cores = host_threads()
+    if args.metric == "tdvp":
+        for _ in range(min(args.warmup, 1)):
+            cpu_tdvp_step()
+        times = []
+        for k in range(args.steps):
+            t, detail = cpu_tdvp_step(seed=k)
+            times.append(t)
+        ms = float(np.mean(times)) * 1e3
+        sample = ("oracle port of the reference algorithm (jax not installable): one complete TDVP/SR step of configs[0] "
+                  "(1D TFIM L=20, CpxRBM alpha=2, 500 chains, %d samples), full size" % detail["samples"])
+        line = {"metric": TDVP_METRIC, "value": ms, "unit": "ms", "impl": "reference", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": TDVP_WORKLOAD, "samples_per_step": detail["samples"], "bounded_sample": False},
+                "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "detail": detail}
+        print(json.dumps(line), flush=True)
+        return
+    shape, g, alpha, bias, nsamp_gpu, chains_gpu = WORKLOADS[wl]
+    nsamp, chains = REF_SAMPLES, REF_CHAINS
     for _ in range(args.warmup):
-        cpu_reference_step(shape, g, alpha, bias, chains, chains, gram_cols=500)
+        cpu_reference_step(shape, g, alpha, bias, nsamp, chains, rng_seed=1000)
     times = []
     for k in range(args.steps):
         t, detail = cpu_reference_step(shape, g, alpha, bias, nsamp, chains, rng_seed=k)
@@ -161,8 +239,8 @@ def run_reference_arm(args, wl):
     sec = float(np.mean(times))
     value = nsamp / sec
     sample = ("oracle port of the reference algorithm (jax not installable): %d samples/step from %d chains, full forward "
-              "pass per proposal, s'->psi(s') E_loc, dense O and zgemm Gram timed on %d of %d columns and scaled"
-              % (nsamp, chains, detail["gram_cols_timed"], alpha * int(np.prod(shape)) ** 2))
+              "pass per proposal, s'->psi(s') E_loc, dense O and the whole %d x %d zgemm Gram executed in column blocks of %d"
+              % (nsamp, chains, detail["gram_cols"], detail["gram_cols"], detail["gram_block"]))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -170,7 +248,21 @@ def run_reference_arm(args, wl):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "detail": detail}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+
+
+def reference_arm_subprocess(extra, timeout=600):
+    """Runs `bench.py --impl reference ...` in a fresh interpreter (own BLAS thread pool, all host cores) and returns
+    its JSON line: the cpu_baseline leg of the GPU arm."""
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference"] + extra, env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    for ln in reversed(out.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)
+    raise RuntimeError("reference arm printed no JSON: " + out.stderr[-500:])
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -181,6 +273,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--metric", default="vmc", choices=["vmc", "tdvp"],
+                    help="vmc: samples/s of sample + E_loc + S/F at configs[1] (headline); tdvp: ms of one complete "
+                         "TDVP/SR step at configs[0], the size the reference's CPU path runs in full")
     ap.add_argument("--samples", type=int, default=0, help="override samples per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tdvp", action="store_true")
@@ -192,6 +287,9 @@ def main():
         run_reference_arm(args, wl)
         return
 
+    if args.metric == "tdvp":
+        run_tdvp_metric(args)
+        return
     os.environ["JVMC_GRAM_BACKEND"] = args.gram
     # stdout carries exactly ONE JSON line: everything libraries print to fd 1 (e.g. "NCCL version ..." at communicator
     # creation) is diverted to stderr, the JSON line is written to the saved descriptor at the end
@@ -242,9 +340,7 @@ def main():
                                  sweepSteps=N, thermalizationSweeps=25, numSamples=nsamp * world)
     smp.refreshEvery = 8
 
-    ev_g0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + args.warmup + 8)]
-    ev_g1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + args.warmup + 8)]
-    state = {"i": 0, "launches": 0}
+    gram_events = []          # one (start, stop) CUDA-event pair per Gram call, appended as the steps run
 
     def vmc_step():
         s, logPsi, p = smp.sample()
@@ -253,13 +349,13 @@ def main():
         G = RBMGradientObs(psi, s, p)
         Emean, Evar = E.mean()[0], E.var()[0]
         F = G.covar(E)
-        i = state["i"]
         G.kr_mean()
         G._sigT = K.pack_sigma(G._s, G.hasBias)
-        ev_g0[i].record()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
         A = G.gram_A()
-        ev_g1[i].record()
-        state["i"] = i + 1
+        g1.record()
+        gram_events.append((g0, g1))
         return s, Emean, Evar, F, A
 
     def barrier():
@@ -281,7 +377,7 @@ def main():
     time.sleep(0.3)
     from vmc_jax_b200 import _lib as _jl
     launches0 = _jl.LAUNCHES
-    i0 = state["i"]
+    i0 = len(gram_events)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -291,7 +387,8 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _jl.LAUNCHES - launches0
-    gram_ms = float(np.mean([ev_g0[i].elapsed_time(ev_g1[i]) for i in range(i0, state["i"])]))
+    i1 = len(gram_events)
+    gram_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in gram_events[i0:i1]]))
     energy = complex(out[1].item())
     del out
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -389,10 +486,13 @@ def main():
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             with open(peaks_path) as fh:
-                bf16 = float(json.load(fh)["bf16_tflops"])
-            i8_src = "2 x bf16_tflops of MEASURED_PEAKS.json (B200 dense INT8 rate = 2 x dense bf16 rate)"
+                pk = json.load(fh)
+            # the Gram runs for seconds inside the step under the board power cap: sustained figure
+            bf16 = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
+            i8_src = ("2 x bf16_tflops_sustained of MEASURED_PEAKS.json (measured; B200 dense INT8 rate = 2 x dense bf16 "
+                      "rate; burst figure bf16_tflops = %.1f)" % float(pk["bf16_tflops"]))
         else:
-            bf16, i8_src = 1590.0, "2 x 1.59 PFLOP/s bf16 fallback of B200_PROFILING.md"
+            bf16, i8_src = 1400.0, "2 x 1.4 PFLOP/s sustained bf16 fallback of B200_PROFILING.md"
         i8_peak = 2.0 * bf16
         ach = algo_ops / (gram_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "gram_s_i8_kernel (tcgen05.mma kind::i8, UTCIMMA) + i8 slicing",
@@ -449,7 +549,8 @@ def main():
     # figures, against the measured peaks; the binding resource of all of them is the fp64 pipe, not HBM)
     kernels = None
     if phases:
-        FP64_PEAK = 36.3       # TFLOP/s, DFMA issue-rate probe tools/fp64_probe.cu on this pool's B200 (profiles/README.md)
+        # fp64 denominator: cuBLAS DGEMM 8192^3 measured live above (MEASURED_PEAKS.json holds no fp64 figure)
+        FP64_PEAK = float(peak_tf)
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
                 hbm_peak, hbm_src = float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
@@ -466,7 +567,7 @@ def main():
                     "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "algorithmic": note}
         t_mc = max(phases["sampling_ms"] - phases["logpsi_ms"], 1e-6)
         kernels = {
-            "fp64_peak_tflops": FP64_PEAK, "fp64_peak_source": "DFMA issue-rate probe (tools/fp64_probe.cu, 36.3 TFLOP/s measured)",
+            "fp64_peak_tflops": FP64_PEAK, "fp64_peak_source": peak_src,
             "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
             "list": [
                 entry("rbm_mcmc_flip_kernel (sampler sweep incl. %d thermalisation sweeps)" % 25, t_mc,
@@ -482,11 +583,19 @@ def main():
             ]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t, detail = cpu_reference_step(shape, g, alpha, bias, 64, 32)
-        cpu = {"value": 64 / t, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": "oracle port of the reference algorithm on 64 samples (32 chains): full-forward Metropolis, "
-                         "s'->psi(s') E_loc, dense O + zgemm Gram timed on %d of %d columns and scaled"
-                         % (detail["gram_cols_timed"], Pc), "detail": detail}
+        try:
+            ref = reference_arm_subprocess(["--workload", wl, "--steps", "8", "--warmup", "1"])
+            cpu = dict(ref["cpu_baseline"], steps=ref["steps"], ms_per_step=ref["ms_per_step"], detail=ref.get("detail"))
+        except Exception as ex:  # pragma: no cover
+            cpu = {"error": repr(ex)}
+        if tdvp_info is not None and "error" not in tdvp_info:
+            try:
+                ref = reference_arm_subprocess(["--metric", "tdvp", "--steps", "3", "--warmup", "1"])
+                tdvp_info["reference_cpu"] = {"ms_per_step": ref["value"], "cores": ref["cpu_baseline"]["cores"],
+                                              "kind": "port", "detail": ref.get("detail")}
+                tdvp_info["speedup_vs_reference_cpu"] = ref["value"] / tdvp_info["ms_per_step"]
+            except Exception as ex:  # pragma: no cover
+                tdvp_info["reference_cpu"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -507,7 +616,7 @@ def main():
         dist.destroy_process_group()
 
 
-def tdvp_step_ms(jVMC, op, torch, L=20, alpha=2, nsamp=4096, chains=500, steps=5):
+def tdvp_step_ms(jVMC, op, torch, L=20, alpha=2, nsamp=4096, chains=500, steps=5, warm=2):
     """Full TDVP/SR step (TDVP.__call__: sample + E_loc + gradients + S,F + eigh + SNR + regularised solve) on
     BASELINE configs[0] (1D TFIM L=20, CpxRBM alpha=2, 500 chains, 2^12 -> 4500 samples, ex0-style SR)."""
     dev = jVMC.global_defs.myDevice
@@ -522,16 +631,56 @@ def tdvp_step_ms(jVMC, op, torch, L=20, alpha=2, nsamp=4096, chains=500, steps=5
     tdvp = jVMC.util.TDVP(smp, rhsPrefactor=1., pinvTol=1e-8, diagonalShift=10, makeReal='real')
     stepper = jVMC.util.stepper.Euler(timeStep=1e-2)
     times = []
-    for k in range(steps + 2):
+    for k in range(steps + warm):
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        a.record()
         dp, _ = stepper.step(0, tdvp, psi.get_parameters(), hamiltonian=H, psi=psi, numSamples=None)
         psi.set_parameters(dp)
+        b_.record()
         torch.cuda.synchronize()
-        times.append((time.perf_counter() - t0) * 1e3)
+        times.append(a.elapsed_time(b_))
     return {"config": "1D TFIM L=%d, CpxRBM alpha=%d (P=%d), %d chains, %d samples, SR (makeReal=real, diagonalShift=10)"
                       % (L, alpha, 2 * L * alpha * L, chains, smp.get_last_number_of_samples()),
-            "ms_per_step": float(np.median(times[2:])), "energy_per_site": float(tdvp.ElocMean0.real) / L}
+            "ms_per_step": float(np.mean(times[warm:])), "ms_median": float(np.median(times[warm:])),
+            "steps": steps, "timer": "CUDA events around Euler.step(TDVP.__call__) + set_parameters",
+            "energy_per_site": float(tdvp.ElocMean0.real) / L}
+
+
+def run_tdvp_metric(args):
+    """`--metric tdvp`: the "TDVP step ms" half of BASELINE.json's metric, on configs[0] -- the configuration the
+    reference's CPU path runs at full size, so `--impl reference --metric tdvp` is its exact counterpart."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    import vmc_jax_b200 as jVMC
+    from vmc_jax_b200 import mpi_wrapper as mpi, _lib as _jl
+    import vmc_jax_b200.operator as op
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    mpi.init_distributed()
+    clocks = ClockSampler(jVMC.global_defs.myDevice.index or 0)
+    clocks.start()
+    l0 = _jl.LAUNCHES
+    info = tdvp_step_ms(jVMC, op, torch, steps=args.steps, warm=max(args.warmup, 3))
+    launches = (_jl.LAUNCHES - l0) * args.steps // (args.steps + max(args.warmup, 3))
+    clk = clocks.stop()
+    if mpi.rank == 0:
+        ms = info["ms_per_step"]
+        line = {"metric": TDVP_METRIC, "value": ms, "unit": "ms", "n_gpus": mpi.commSize, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": False, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": TDVP_WORKLOAD, "detail": info["config"],
+                           "l2": "latency-bound configuration (P = 1600): inputs fit L2, nothing to flush"},
+                "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16,
+                        "note": "TDVP.__call__ through the public API; the step reads <E> back (ElocMean0)"},
+                "gpu_launches": launches, "clocks": clk, "tdvp_step": info}
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    if mpi.commSize > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 def tdvp_step_ms_config3(jVMC, op, torch, L=40, alpha=2, nsamp=2 ** 16, chains=2368, steps=2):
@@ -552,11 +701,13 @@ def tdvp_step_ms_config3(jVMC, op, torch, L=40, alpha=2, nsamp=2 ** 16, chains=2
     tdvp = jVMC.util.TDVP(smp, snrTol=2, pinvTol=1e-8, rhsPrefactor=1.j, makeReal='imag')
     times = []
     for k in range(steps + 1):
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        a.record()
         tdvp(psi.get_parameters(), 0.0, hamiltonian=H, psi=psi, numSamples=None)
+        b_.record()
         torch.cuda.synchronize()
-        times.append((time.perf_counter() - t0) * 1e3)
+        times.append(a.elapsed_time(b_))
     P = 2 * (alpha * L + L * alpha * L)
     return {"config": "1D TFIM L=%d quench, CpxRBM alpha=%d with bias (P=%d), %d chains, %d samples, real-time TDVP "
                       "(rhsPrefactor=1j, makeReal=imag, snrTol=2)" % (L, alpha, P, chains, smp.get_last_number_of_samples()),
