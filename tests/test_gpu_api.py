@@ -699,6 +699,28 @@ def test_tdvp_pc_level_solve_matches_reference_layout(makeReal, x, shift, bias):
             assert float(cb) == float(ca)
             assert torch.allclose(ua, ub, rtol=1e-6, atol=1e-8 * float(ub.abs().max()))
             assert np.isclose(float(ra), float(rb), rtol=1e-6, atol=1e-10)
+        else:
+            # 'real' with an MC sampler: every eigenvalue of q(S0) is doubly degenerate and the SNR weighting is active.
+            # The P_c-level solve regularises with the eigenspace-invariant SNR; the same rule applied to the
+            # reference-layout decomposition (whatever basis cuSOLVER returned inside the pairs) gives the same update.
+            from vmc_jax_b200 import kernels as K, mpi_wrapper as mpi
+            vtf2 = (b.VtF.abs() ** 2).reshape(-1, 2).sum(1)
+            rvp = b.rhoVar.reshape(-1, 2).sum(1)
+            snr_pair = torch.sqrt(torch.abs(mpi.globNumSamples * vtf2 / rvp))
+            assert torch.allclose(a.snr.reshape(-1, 2)[:, 0], snr_pair, rtol=1e-6)
+            assert torch.allclose(a.snr.reshape(-1, 2)[:, 1], snr_pair, rtol=1e-6)
+            F = realFunOrImag(b, makeReal)
+            pinvEv, scal = K.tdvp_regularize(b.ev, b.VtF, torch.repeat_interleave(snr_pair, 2), F.to(torch.complex128),
+                                             1e-8, 1e-8, 2.0)
+            uref = torch.mv(b.V.to(torch.complex128), pinvEv * b.VtF).real
+            assert float(scal[1]) == float(ca)
+            assert torch.allclose(ua, uref, rtol=1e-6, atol=1e-8 * float(uref.abs().max()))
+            assert np.isclose(float(ra), float(scal[0]), rtol=1e-6, atol=1e-10)
+
+
+def realFunOrImag(td, makeReal):
+    """q(F0) of a solved TDVP object"""
+    return td.makeReal(td.F0)
 
 
 def test_tdvp_snr_second_moments_by_gram_kernel():

@@ -226,3 +226,64 @@ def test_symmetry_orbit_sizes_reference_cases():
                     orbit = symmetries.get_orbit_1D(L, *symms)
                     assert orbit.shape[0] == (2 if reflection else 1) * (L if translation else 1) * (2 if spinflip else 1)
                     assert np.issubdtype(orbit.dtype, np.integer)
+
+
+def test_output_manager_layout(tmp_path):
+    """reference tests/output_manager_test.py:17-60 against the npz-backed tree (h5py is not in this image): same group
+    and dataset names, rows appended along axis 0, scalars stored as shape-(1,) rows."""
+    from vmc_jax_b200.util.output_manager import OutputManager
+    fn = str(tmp_path / "test.h5")
+    outp = OutputManager(fn, append=False, backend="npz")
+    outp.set_group("test")
+    with np.load(outp.path) as z:
+        assert list(z["__groups__"]) == ["/test"]
+    x = np.array([13.2])
+    outp.write_metadata(0.3, bla=x)
+    assert outp.has("/test/metadata") and outp.has("/test/metadata/bla")
+    assert np.allclose(outp.read_dataset("/test/metadata/bla")[0], x)
+    y = 99.1
+    outp.write_metadata(0.5, bla=y)
+    assert np.allclose(outp.read_dataset("/test/metadata/bla"), np.array([x, [y]]))
+    assert np.allclose(outp.read_dataset("/test/metadata/times"), [0.3, 0.5])
+    x = np.random.uniform(1, 2, size=(13,))
+    y = np.random.uniform(-1, 1, size=(3,))
+    outp.write_observables(0.1, obs1={"mean": x}, obs2={"mean": torch.as_tensor(y)})
+    assert outp.has("/test/observables/obs1")
+    assert np.allclose(outp.read_dataset("/test/observables/obs1/mean")[0], x)
+    assert np.allclose(outp.read_dataset("/test/observables/obs2/mean")[0], y)
+    outp.write_observables(0.5, bla={"mean": 99.1})
+    assert np.allclose(outp.read_dataset("/test/observables/bla/mean")[0], np.array([99.1]))
+    # checkpoints: flat parameter vectors, retrieved by index or by nearest time; the archive on disk is complete
+    w0, w1 = np.arange(6.0), np.arange(6.0) + 0.5
+    outp.write_network_checkpoint(0.0, w0)
+    outp.write_network_checkpoint(1.0, torch.as_tensor(w1))
+    t, w = outp.get_network_checkpoint(time=0.9)
+    assert t == 1.0 and np.allclose(w, w1)
+    t, w = outp.get_network_checkpoint(idx=0)
+    assert t == 0.0 and np.allclose(w, w0)
+    outp.write_error_data("bad", np.array([1, 2, 3]))
+    again = OutputManager(fn, group="test", append=True, backend="npz")
+    assert np.allclose(again.read_dataset("/test/network_checkpoints/checkpoints"), np.stack([w0, w1]))
+    assert np.array_equal(again.read_dataset("/error_data/bad"), [1, 2, 3])
+    again.write_metadata(0.7, bla=1.0)
+    assert again.read_dataset("/test/metadata/bla").shape == (3, 1)
+    # timers
+    outp.start_timing("a"); outp.stop_timing("a"); outp.add_timing("b", 2.0)
+    assert outp.timings["a"]["count"] == 1 and outp.timings["b"]["total"] == 2.0
+    outp.print_timings(indent=" ")
+    assert outp.timings["b"]["last_total"] == 2.0
+    assert OutputManager(None).timings == {}
+
+
+def test_bench_reference_arm_and_argument_handling():
+    """bench.py: the reference arm is recognised before numpy is imported (thread pinning) and the CPU step functions
+    run at a reduced size; the driver's `--steps 20 --warmup 5` needs no pre-sized event pool any more."""
+    import bench
+    assert bench._is_reference_arm(["bench.py", "--impl", "reference"]) and bench._is_reference_arm(["x", "--impl=reference"])
+    assert not bench._is_reference_arm(["bench.py", "--gpus", "1"])
+    t, d = bench.cpu_reference_step((4, 4), 3.04, 2, False, 16, 8, gram_block=100)
+    assert d["samples"] == 16 and d["gram_cols"] == 16 * 32 and t > 0
+    t, d = bench.cpu_tdvp_step(L=6, alpha=1, nsamp=200, chains=50)
+    assert d["samples"] == 200 and np.isfinite(d["update_norm"])
+    src = open(bench.__file__).read()
+    assert "args.steps + args.warmup + 8" not in src

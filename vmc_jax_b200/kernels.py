@@ -394,10 +394,10 @@ def expand_S(A, M, N, hasBias, mode, shift):
     return out
 
 
-def eigh_inplace(St):
+def eigh_inplace(St, check=True):
     """Eigen-decomposition of the Hermitian matrix whose column-major image is ``St`` (i.e. St = S^T as
     a row-major tensor; lower triangle of S referenced).  Overwrites St with the eigenvectors: row k of
-    the result is eigenvector k.  Returns (ev ascending, Vt)."""
+    the result is eigenvector k.  Returns (ev ascending, Vt, devInfo); raises if cuSOLVER's devInfo is non-zero."""
     n = St.shape[0]
     isC = St.is_complex()
     lib = _lib.load()
@@ -409,6 +409,14 @@ def eigh_inplace(St):
     w = torch.empty(n, dtype=F64, device=St.device)
     info = torch.zeros(1, dtype=I32, device=St.device)
     call("jvmc_eigh", n, int(isC), ptr(St), ptr(w), ptr(work), d.value, ptr(info))
+    if check:
+        # cuSOLVER reports non-convergence / illegal arguments only through the device flag: a failed decomposition must
+        # not flow into the pseudo-inverse (the reference re-solves on the host, jVMC/util/tdvp.py:156-164; there is no
+        # CPU path here, so it is an error).  The callers consume ev / V on the host side right after, so this sync is
+        # not an extra one on the step's critical path.
+        bad = int(info.item())
+        if bad != 0:
+            raise RuntimeError("cuSOLVER eigen-decomposition failed (n = %d, devInfo = %d)" % (n, bad))
     return w, St, info
 
 

@@ -7,6 +7,7 @@ Two device paths:
   * fused path (get_O_loc with a (Cpx)RBM): jvmc_rbm_eloc_bfo evaluates psi(s')/psi(s) from the cached
     tanh(theta) with per-parameter tables; s' is never materialised."""
 import abc
+import os
 
 import torch
 
@@ -14,6 +15,9 @@ from .. import global_defs
 from .. import kernels as K
 
 opDtype = global_defs.tCpx
+# the fused E_loc kernel raises a device flag for strings it cannot evaluate (more than two flipped sites); reading it
+# costs one stream sync per get_O_loc call (JVMC_CHECK_DEVICE_FLAGS=0 skips it)
+_CHECK_ELOC_FLAG = os.environ.get("JVMC_CHECK_DEVICE_FLAGS", "1") != "0"
 
 __all__ = ["Operator", "opDtype"]
 
@@ -89,6 +93,8 @@ class Operator(metaclass=abc.ABCMeta):
             out, err = K.rbm_eloc(flat, psi._tau(flat), psi.flip_tables(), tab.device_tables(),
                                   tab.eval_prefactors(*args))
             self._last_err = err
+            if _CHECK_ELOC_FLAG and int(err.item()) != 0:
+                raise RuntimeError("fused E_loc kernel reported an unsupported operator string (flag %d)" % int(err.item()))
             return out.reshape(lead)
         if self.ElocBatchSize > 0:
             return self.get_O_loc_batched(samples, psi, logPsiS, self.ElocBatchSize, *args)

@@ -61,7 +61,8 @@ class AdaptiveHeun:
             k01 = f(ymid, t + 0.5 * dt, **rhsArgs, intStep=3)
             k11 = f(ymid + 0.5 * dt * k01, t + dt, **rhsArgs, intStep=4)
             dy1 = dy1 + 0.25 * dt * (k01 + k11)
-            fe = self.tolerance / float(normFunction(dy1 - dy0))
+            err = float(normFunction(dy1 - dy0))
+            fe = float('inf') if err == 0. else self.tolerance / err    # identical estimates: accept, dt doubles
             realDt = dt
             dt = min(dt * min(max(0.9 * fe ** 0.33333, 0.2), 2.), self.maxStep)
         self.dt = dt

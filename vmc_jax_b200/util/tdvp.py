@@ -145,7 +145,7 @@ class TDVP:
         if self._St is not None:
             St = self._St.clone()
         else:
-            St = S.T.contiguous().clone()
+            St = S.T.clone(memory_format=torch.contiguous_format)
         if not self.diagonalizeOnDevice:
             ev, V = np.linalg.eigh(S.cpu().numpy())
             self.ev = torch.as_tensor(ev).to(S.device)
@@ -199,8 +199,8 @@ class TDVP:
         'real': q(S0) is the real representation of A: eigenpairs (lambda_k, [Re v_k; Im v_k]), (lambda_k, [-Im v_k; Re v_k]);
         all projections are Re / Im of zeta = v_k^dagger z with z = -x <conj(dO) dE> at the P_c level.
         'imag': q(S0) = i Im S0 has eigenpairs (+lambda_k, v_k (x) (1,-i)/sqrt2), (-lambda_k, conj(v_k) (x) (1,i)/sqrt2) with
-        projections zeta/sqrt2 and -conj(zeta)/sqrt2.  Degenerate pairs of 'real' get this basis (the reference's is
-        whatever LAPACK returns: the SNR-weighted update is basis dependent there)."""
+        projections zeta/sqrt2 and -conj(zeta)/sqrt2.  The degenerate pairs of 'real' are regularised with the
+        eigenspace-invariant SNR (see below), so the update does not depend on the basis chosen inside a pair."""
         x = self.rhsPrefactor
         self.ElocMean = Eloc.mean()[0]
         self.ElocVar = Eloc.var()[0]
@@ -216,7 +216,7 @@ class TDVP:
         mode = self._mode
         self.S = None
         self._S_lazy = lambda: (lambda St: St if mode == 0 else St.T)(K.expand_S(A, G.M, G.N, G.hasBias, mode, shift))
-        At = A.T.contiguous()                         # column-major A for cuSOLVER (eigh_inplace overwrites its input)
+        At = A.T.clone(memory_format=torch.contiguous_format)   # private column-major copy: eigh_inplace overwrites it
         if mode == 0 and shift > 1e-10:
             At.diagonal().mul_(1.0 + shift)           # S[f][f] *= 1 + shift acts on diag(Re A) in both halves
         evc, Vtc, info = K.eigh_inplace(At)           # rows of Vtc = eigenvectors v_k
@@ -229,9 +229,15 @@ class TDVP:
         dE = (Eloc._data.reshape(-1) / torch.sqrt(G._p)).to(torch.complex128)
         mu = G.kr_mean().reshape(-1)
         Bglob = int(mpi.globNumSamples) if mpi.globNumSamples else B
-        if mode == 1 and Pc >= 256 and Bglob >= 2 * Pc:
-            # 'imag' only needs sum_n w_n |zeta_kn|^2 = |x|^2 sum_n w'_n |v_k^T (O_n - mu)|^2, w'_n = w_n |dE_n|^2: a second
-            # Gram matrix A' = sum w' conj(O) O^T (same tensor-core kernel) and P_c^3 instead of N_s P_c^2 projection flops
+        # Both modes only need the first moment sum_n w_n zeta_kn = zeta_k and the second moment sum_n w_n |zeta_kn|^2:
+        #   'imag': the two members +-lambda_k carry zeta/sqrt2 and -conj(zeta)/sqrt2: Var rho = (E|zeta|^2 - |E zeta|^2)/2;
+        #   'real': the eigenvalue lambda_k of q(S0) is doubly degenerate, the reference's per-eigenvector SNR depends on the
+        #           basis LAPACK happens to return inside the 2-d eigenspace.  The eigenspace-invariant
+        #           definition is used for both members: SNR^2 = N (|Re zeta|^2 + |Im zeta|^2) / (Var Re zeta + Var Im zeta)
+        #           -- it equals the reference's value whenever that is basis independent (equal member SNRs).
+        if Pc >= 256 and Bglob >= 2 * Pc:
+            # sum_n w_n |zeta_kn|^2 = |x|^2 sum_n w'_n |v_k^T (O_n - mu)|^2, w'_n = w_n |dE_n|^2: a second Gram matrix
+            # A' = sum w' conj(O) O^T (same tensor-core kernel) and P_c^3 instead of N_s P_c^2 projection flops
             w2 = (G._p * (dE.conj() * dE).real).contiguous()
             Ap = G.weighted_second_moment(w2)
             m1 = mpi._all_reduce_sum(K.rbm_moments(G._s, G._tau, w2.to(torch.complex128), G.hasBias, 0)).reshape(-1)
@@ -241,12 +247,10 @@ class TDVP:
             a1 = torch.mv(Vtc, m1)                                     # v_k^T sum w' O
             second = abs(x) ** 2 * (q - 2.0 * (b.conj() * a1).real + W2 * (b.conj() * b).real)
             s1 = zeta                                                  # sum_n w_n zeta_kn = v_k^dagger z
-            s2r, s2i = second, torch.zeros_like(second)
             del Ap
         else:
             s1 = torch.zeros(Pc, dtype=torch.complex128, device=A.device)
-            s2r = torch.zeros(Pc, dtype=torch.float64, device=A.device)
-            s2i = torch.zeros(Pc, dtype=torch.float64, device=A.device)
+            second = torch.zeros(Pc, dtype=torch.float64, device=A.device)
             chunk = max(1, min(B, (2 ** 28) // max(Pc, 1)))
             VcH = Vtc.conj().T.contiguous()
             for lo in range(0, B, chunk):
@@ -255,20 +259,21 @@ class TDVP:
                 rho = ((-x) * (g - mu[None, :]).conj() * dE[lo:hi, None]) @ VcH
                 w = G._p[lo:hi]
                 s1 += (w[:, None] * rho).sum(0)
-                s2r += (w[:, None] * rho.real ** 2).sum(0)
-                s2i += (w[:, None] * rho.imag ** 2).sum(0)
-            s1, s2r, s2i = mpi._all_reduce_sum(s1), mpi._all_reduce_sum(s2r), mpi._all_reduce_sum(s2i)
+                second += (w[:, None] * (rho.conj() * rho).real).sum(0)
+            s1, second = mpi._all_reduce_sum(s1), mpi._all_reduce_sum(second)
+        rv = 0.5 * (second - (s1.conj() * s1).real)                    # variance of rho per member of the pair
         if mode == 0:
             self.ev = torch.repeat_interleave(evc, 2)
             self.VtF = torch.stack([zeta.real, zeta.imag], dim=1).reshape(-1).to(torch.complex128)
-            self.rhoVar = torch.stack([s2r - s1.real ** 2, s2i - s1.imag ** 2], dim=1).reshape(-1)
+            self.rhoVar = torch.repeat_interleave(rv, 2)
+            snr_pair = torch.sqrt(torch.abs(mpi.globNumSamples * 0.5 * (zeta.conj() * zeta).real / rv))
+            self.snr = torch.repeat_interleave(snr_pair, 2)
         else:
             r2 = 2.0 ** -0.5
             self.ev = torch.cat([-evc.flip(0), evc])
             self.VtF = torch.cat([(-zeta.conj() * r2).flip(0), zeta * r2])
-            rv = 0.5 * (s2r + s2i - (s1.conj() * s1).real)
             self.rhoVar = torch.cat([rv.flip(0), rv])
-        self.snr = torch.sqrt(torch.abs(mpi.globNumSamples * (self.VtF.conj() * self.VtF).real / self.rhoVar)).reshape(-1)
+            self.snr = torch.sqrt(torch.abs(mpi.globNumSamples * (self.VtF.conj() * self.VtF).real / self.rhoVar)).reshape(-1)
         exact = _is_exact_sampler(self.sampler)
         pinvEv, scal = K.tdvp_regularize(self.ev, self.VtF, None if exact else self.snr, F.to(torch.complex128),
                                          float(self.pinvTol), float(self.pinvCutoff), float(self.snrTol))
