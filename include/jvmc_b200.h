@@ -102,7 +102,7 @@ int jvmc_rbm_gram_S(const double* Y, long long B, int M, int R, const unsigned i
                     double alpha, double kappa, double* A, int tile, void* stream);
 
 /* Same contract as jvmc_rbm_gram_S on the tcgen05 INT8 tensor cores (Ozaki splitting, fp64-equivalent result):
- * jvmc_i8_layout -> scratch sizes; jvmc_i8_slice -> per-column power-of-two scales + 5 balanced base-255 int8 digits in
+ * jvmc_i8_layout -> scratch sizes; jvmc_i8_slice -> per-column scales (2 x column maximum) + 5 balanced base-255 int8 digits in
  * the UMMA canonical layout (digits must be zero-initialised); jvmc_rbm_gram_S_i8 -> A.  tiles: device int array, 8 ints
  * per tile (rowGroup, colGroup, NC, jlo, jhi, 0, 0, 0): 128 real rows from real column 8 rowGroup (complex row
  * 4 rowGroup), NC real columns (multiple of 16, <= cols of jvmc_i8_tile_shape) from real column 8 colGroup; the tile
@@ -111,6 +111,7 @@ int jvmc_rbm_gram_S(const double* Y, long long B, int M, int R, const unsigned i
 int jvmc_i8_layout(long long B, int M, long long* numChunks, int* numZGroups, long long* digitBytes);
 int jvmc_i8_tile_shape(int* rows, int* cols);   /* tile of jvmc_rbm_gram_S_i8 in real columns */
 int jvmc_i8_set_debug(int flags);   /* development ablations of the int8 Gram pipeline (timing only; results invalid) */
+int jvmc_i8_set_trace(void* buf, int tile);   /* development: per-stage clock64 trace of one CTA (16 x 832 int64, device) */
 int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long long* colmax, double* scale,
                   signed char* digits, void* stream);
 int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale, long long B, int M, int R,
@@ -184,6 +185,33 @@ int jvmc_cnn_mcmc(const int* desc, int ndesc, const double* theta, int32_t* stat
                   unsigned long long seed, unsigned long long step0, long long chain0, int proposer, double mu,
                   int sweepSteps, long long thermSteps, int numSamplesPerChain, int32_t* out,
                   unsigned long long* counters, void* stream);
+
+/* ---- the whole regularised solve of one step as single entry points (so that a binding without Python between
+ * kernels can call it): TDVP.solve, reference jVMC/util/tdvp.py:153-213, and MinSR.solve, jVMC/util/minsr.py:59-78.
+ * mode 0 = makeReal 'real' (S real symmetric, double), mode 1 = 'imag' (S complex Hermitian).  S / T: column-major,
+ * overwritten by the eigenvectors.  D: complex[B, n] centred data sqrt(w)(O - <O>) of the gradients, or NULL for the
+ * ExactSampler semantics without SNR weighting (tdvp.py:203); e: complex[B] centred local energies; w: [B] weights.
+ * comm: communicator of jvmc_comm_init or NULL (single rank).  The per-sample projections V^dagger x_n are a cuBLAS gemm. */
+int jvmc_tdvp_solve_workspace(int n, int mode, long long B, long long* bytes);
+int jvmc_tdvp_solve(int n, int mode, double* S, const double* F, long long B, const double* D, const double* e,
+                    const double* w, double xre, double xim, double numSamplesGlobal, int useSnr, double snrTol, double pinvTol,
+                    double pinvCutoff, void* comm, double* ev, double* VtF, double* rhoVar, double* snr, double* pinvEv,
+                    double* update, double* scal, int* info, void* work, long long workBytes, void* stream);
+int jvmc_minsr_solve_workspace(int n, int isComplex, long long* bytes);
+int jvmc_minsr_solve(int n, int isComplex, double* T, const double* e, double rtol, double* x, double* ev, int* info,
+                     void* work, long long workBytes, void* stream);
+
+/* ---- NCCL plumbing replacing jVMC/mpi_wrapper.py (global_sum/mean/variance/covariance :114-243, gather :278-292,
+ * bcast_unknown_size :246-275) on device buffers, in-stream.  NCCL is resolved at run time (libnccl.so.2);
+ * JVMC_ERR_UNSUPPORTED when it cannot be loaded.  The 128-byte id of rank 0 is shipped to the other ranks by the caller. */
+int jvmc_comm_nccl_version(void);
+int jvmc_comm_unique_id(void* hostId128);
+int jvmc_comm_init(const void* hostId128, int rank, int world, void** comm);
+int jvmc_comm_destroy(void* comm);
+int jvmc_comm_allreduce_sum_f64(void* comm, double* buf, long long count, void* stream);
+int jvmc_comm_allgather_bytes(void* comm, const void* send, void* recv, long long bytesPerRank, void* stream);
+int jvmc_comm_bcast_bytes(void* comm, void* buf, long long bytes, int root, void* stream);
+int jvmc_comm_reduce_scatter_sum_f64(void* comm, const double* send, double* recv, long long recvCount, void* stream);
 
 #ifdef __cplusplus
 }

@@ -198,6 +198,35 @@ def check_moments_gram(N=7, M=24, B=211, bias=True, seed=11, uniform=True, tile=
     return r
 
 
+def check_gram_heavy_tail(N=5, M=40, B=4096, seed=31, tail=3000.0, backend="i8"):
+    """tau columns whose maximum is far above their typical size (tanh(theta) next to a pole).  The int8 digits
+    resolve 255^-5 of the column MAXIMUM, so the absolute error of the entries that involve such a column grows with
+    it -- but so does their natural size: the check is entry-wise, |dA_jl| <= 1e-10 sqrt(A_jj A_ll), which is stricter
+    than the max|A| normalisation of check_moments_gram exactly where it matters (small entries of A are not allowed
+    to hide behind a large one).  Bound behind it: an entry of column z is off by <= 0.5 * 255^-5 c_z with
+    c_z = 2 max_n|Z_nz| <= 2 sqrt(B) rms_z, the sum over B samples of independent roundings divides by sqrt(B) again."""
+    rng = np.random.default_rng(seed)
+    Y = 0.5 * (rng.standard_normal((B, M)) + 1j * rng.standard_normal((B, M)))
+    Y[rng.integers(0, B, 3), 7] *= tail                       # three outliers in column 7 (Re and Im)
+    Y[rng.integers(0, B), 21] = tail * 0.3                    # one in column 21
+    Y[:, 30] *= 1e-6                                           # and a uniformly tiny column
+    s = rand_configs(B, N, seed + 1)
+    sig = 2.0 * s - 1.0
+    O = (sig[:, :, None] * Y[:, None, :]).reshape(B, N * M)   # Khatri-Rao order
+    al = 1.0 / B
+    A_ref = al * (O.conj().T @ O)
+    nat = np.sqrt(np.outer(np.real(np.diag(A_ref)), np.real(np.diag(A_ref))))
+    dY, ds = dev(Y), dev(s)
+    sigT = K.pack_sigma(ds, False)
+    mu0 = torch.zeros((N, M), dtype=torch.complex128, device=dY.device)
+    fn = K.rbm_gram_S_i8 if backend == "i8" else K.rbm_gram_S
+    A = host(fn(dY, sigT, mu0, al, 0.0))
+    err = float(np.max(np.abs(A - A_ref) / nat))
+    assert err < RTOL, err
+    assert np.array_equal(A, A.conj().T)
+    return err
+
+
 def check_gram_T(N=7, M=24, B=211, bias=True, seed=21, uniform=False):
     """Khatri-Rao tangent kernel T = 2 Obar Obar^dagger and O.x mat-vec vs the dense oracle (stats.py:332-336)."""
     W, b = orbm.init_o1(N, M, bias, seed)

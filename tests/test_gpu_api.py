@@ -707,8 +707,10 @@ def test_tdvp_pc_level_solve_matches_reference_layout(makeReal, x, shift, bias):
             vtf2 = (b.VtF.abs() ** 2).reshape(-1, 2).sum(1)
             rvp = b.rhoVar.reshape(-1, 2).sum(1)
             snr_pair = torch.sqrt(torch.abs(mpi.globNumSamples * vtf2 / rvp))
-            assert torch.allclose(a.snr.reshape(-1, 2)[:, 0], snr_pair, rtol=1e-6)
-            assert torch.allclose(a.snr.reshape(-1, 2)[:, 1], snr_pair, rtol=1e-6)
+            ok = b.ev.reshape(-1, 2)[:, 0] > 1e-9 * scale          # 0/0 in the numerical null space of S
+            assert int(ok.sum()) > 4
+            assert torch.allclose(a.snr.reshape(-1, 2)[:, 0][ok], snr_pair[ok], rtol=1e-5)
+            assert torch.allclose(a.snr.reshape(-1, 2)[:, 1][ok], snr_pair[ok], rtol=1e-5)
             F = realFunOrImag(b, makeReal)
             pinvEv, scal = K.tdvp_regularize(b.ev, b.VtF, torch.repeat_interleave(snr_pair, 2), F.to(torch.complex128),
                                              1e-8, 1e-8, 2.0)

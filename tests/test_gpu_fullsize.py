@@ -153,3 +153,100 @@ def test_cfg5_lattice_sampler_eloc_minsr():
     upd = jVMC.util.MinSR(smp, pinvTol=1e-8).solve(SampledObs(E, p), Gobs, holomorphic=True)
     assert upd.shape == (2 * 2 * N * M // 2 * 1,) or upd.numel() == 2 * N * M
     assert bool(torch.isfinite(upd.real).all())
+
+
+def test_cfg4_cnn_12x12_parity_on_sampled_subset():
+    """BASELINE configs[3] lattice: 2D Heisenberg J1 12x12 (Marshall-rotated), real CNN F=(3,3) channels=(6,4), exchange
+    proposer.  Sampled configurations stay in the zero-magnetisation sector; log psi, the per-sample gradients (central
+    finite differences of the oracle, the reference's own method for real nets, tests/vqs_test.py:133-164) and E_loc
+    (the reference's s' -> psi(s') algorithm) are compared with oracle/cnn.py on a subset of the samples."""
+    from oracle import cnn as ocnn
+    L = 12
+    H = op.BranchFreeOperator(ElocBatchSize=512)
+    strings = []
+    for x in range(L):
+        for y in range(L):
+            i = x * L + y
+            for j in (x * L + (y + 1) % L, ((x + 1) % L) * L + y):
+                H.add(op.scal_opstr(-0.25, (op.Sx(i), op.Sx(j))))
+                H.add(op.scal_opstr(-0.25, (op.Sy(i), op.Sy(j))))
+                H.add(op.scal_opstr(0.25, (op.Sz(i), op.Sz(j))))
+                strings += [(-0.25, [obfo.Sx(i), obfo.Sx(j)]), (-0.25, [obfo.Sy(i), obfo.Sy(j)]),
+                            (0.25, [obfo.Sz(i), obfo.Sz(j)])]
+    kw = dict(F=(3, 3), channels=(6, 4), strides=(1, 1), bias=True, firstLayerBias=False)
+    psi = jVMC.vqs.NQS(jVMC.nets.CNN(**kw), seed=7)
+    neel = np.indices((L, L)).sum(0) % 2
+    smp = jVMC.sampler.MCSampler(psi, (L, L), 99, updateProposer=jVMC.sampler.propose_spin_flip_zeroMag, numChains=296,
+                                 numSamples=592, thermalizationSweeps=4, sweepSteps=L * L, initState=neel)
+    s, logPsi, p = smp.sample()
+    assert s.shape == (1, 592, L, L)
+    assert bool((s.reshape(592, -1).sum(1) == L * L // 2).all())          # exchange moves conserve the magnetisation
+    assert 0.05 < float(smp.acceptance_ratio()) <= 1.0
+    theta = G.host(psi.get_parameters())
+    idx = np.arange(0, 592, 37)
+    sn = G.host(s[0])[idx]
+    okw = dict(F=(3, 3), channels=(6, 4), strides=(1, 1), actFun=("elu",), bias=True, firstLayerBias=False)
+    ref = ocnn.cnn_logpsi(sn, theta, **okw)
+    got = G.host(logPsi[0])[idx]
+    assert np.max(np.abs(got.real - ref) / np.maximum(np.abs(ref), 1e-3)) < 1e-10 and np.all(got.imag == 0)
+    g = G.host(psi.gradients(s[:, torch.as_tensor(idx, device="cuda")]))[0]
+    eps = 1e-6
+    for k in range(0, theta.size, 13):
+        tp, tm = theta.copy(), theta.copy()
+        tp[k] += eps
+        tm[k] -= eps
+        fd = (ocnn.cnn_logpsi(sn, tp, **okw) - ocnn.cnn_logpsi(sn, tm, **okw)) / (2 * eps)
+        assert np.max(np.abs(g[:, k].real - fd)) < 1e-7 * max(1.0, np.max(np.abs(fd)))
+    E = H.get_O_loc(s, psi, logPsi)
+    tab = obfo.Tables(strings)
+    refE = obfo.get_O_loc(tab, sn.reshape(len(idx), -1),
+                          lambda x: ocnn.cnn_logpsi(x.reshape((-1, L, L)), theta, **okw).astype(np.complex128))
+    assert G.relerr(G.host(E[0])[idx], refE) < 1e-10
+
+
+def test_cfg3_chain_L40_bias_eloc_F_parity():
+    """BASELINE configs[2] shape: 1D TFIM L=40, CpxRBM alpha=2 with bias (P = 6560), 2^16 samples: E_loc on a subset vs the
+    reference's algorithm, F = <conj(dO) dE> vs the dense oracle on a subset re-weighted consistently, and the
+    matrix-free identity S.v for the full-sample Gram matrix."""
+    L, M = 40, 80
+    psi = jVMC.vqs.NQS(jVMC.nets.CpxRBM(numHidden=M, bias=True), seed=1)
+    psi(torch.zeros((1, 1, L), dtype=torch.int32, device="cuda"))
+    W, b = orbm.init_o1(L, M, True, 4321)
+    psi.set_parameters(torch.as_tensor(orbm.flatten_params(0.3 * W, 0.3 * b)))
+    W, b = 0.3 * W, 0.3 * b
+    H = op.BranchFreeOperator()
+    for l in range(L):
+        H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz((l + 1) % L))))
+        H.add(op.scal_opstr(-0.3, (op.Sx(l),)))
+    smp = jVMC.sampler.MCSampler(psi, (L,), 4321, updateProposer=jVMC.sampler.propose_spin_flip, numChains=2368,
+                                 sweepSteps=L, thermalizationSweeps=25, numSamples=2 ** 16)
+    s, logPsi, p = smp.sample()
+    B = s.shape[1]
+    assert B == 66304
+    E = H.get_O_loc(s, psi, logPsi)
+    idx = np.arange(0, B, 259)
+    tab = obfo.Tables(obfo.tfim_strings((L,), -0.3, -1.0))
+    sn = G.host(s[0])[idx]
+    refE = obfo.get_O_loc(tab, sn, lambda x: orbm.cpx_rbm_logpsi(x, W, b))
+    assert G.relerr(G.host(E[0])[idx], refE) < 1e-10
+    assert G.relerr(G.host(logPsi[0])[idx].real, orbm.cpx_rbm_logpsi(sn, W, b).real) < 1e-10
+    Gobs = RBMGradientObs(psi, s, p)
+    Eobs = SampledObs(E, p)
+    A = Gobs.gram_A()
+    assert torch.equal(A, A.conj().T)
+    # S.v matrix-free: A v = sum_n p_n conj(O_n - mu) ((O_n - mu).v) in Khatri-Rao order
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    v = torch.randn(A.shape[0], dtype=torch.complex128, device="cuda", generator=gen)
+    mu = Gobs.kr_mean()
+    t = K.rbm_krmatvec(Gobs._s, Gobs._tau, v.reshape(mu.shape), True) - (mu.reshape(-1) * v).sum()
+    Av = K.rbm_moments(Gobs._s, Gobs._tau, Gobs._p * t, True, 1).reshape(-1) - mu.conj().reshape(-1) * (Gobs._p * t).sum()
+    ref = A @ v
+    assert float((Av - ref).abs().max() / ref.abs().max()) < 1e-10
+    # F on the subset, weights renormalised: same estimator through the oracle's dense route
+    sub = torch.as_tensor(idx, device="cuda")
+    ps = p[:, sub] / p[:, sub].sum()
+    Fk = RBMGradientObs(psi, s[:, sub], ps).covar(SampledObs(E[:, sub], ps)).reshape(-1)
+    from oracle import stats as ostats
+    pn = G.host(ps)[0]
+    oF = ostats.SampledObs(orbm.gradients_holomorphic(sn, W, b), pn).covar(ostats.SampledObs(G.host(E[0])[idx], pn)).ravel()
+    assert G.relerr(G.host(Fk), oF) < 1e-10

@@ -111,6 +111,13 @@ def test_gram_int8_tensor_cores(N, M, B, bias, uniform):
     G.check_moments_gram(N, M, B, bias, uniform=uniform, backend="i8")
 
 
+@pytest.mark.parametrize("backend,B", [("i8", 4096), ("i8", 30000), ("dmma", 4096)])
+def test_gram_heavy_tailed_columns(backend, B):
+    """Columns of tau with max >> rms (and a uniformly tiny one): entry-wise accuracy |dA_jl| <= 1e-10 sqrt(A_jj A_ll)
+    of the int8 tensor-core Gram (1 and 2 launches) and of the fp64 DMMA Gram."""
+    G.check_gram_heavy_tail(B=B, backend=backend)
+
+
 @pytest.mark.parametrize("N,M,B,bias,uniform", [(7, 24, 211, True, False), (7, 24, 64, False, True),
                                                  (5, 40, 129, False, False), (40, 7, 65, True, False),
                                                  (3, 16, 1, False, True), (12, 33, 300, True, True)])

@@ -40,7 +40,21 @@ _SIGS = {
     "jvmc_rbm_moments": (c_int, [c_ptr, c_ptr, c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "jvmc_rbm_krmatvec": (c_int, [c_ptr, c_ptr, c_ptr, c_ll, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "jvmc_i8_layout": (c_int, [c_ll, c_int, ctypes.POINTER(c_ll), ctypes.POINTER(c_int), ctypes.POINTER(c_ll)]),
+    "jvmc_tdvp_solve_workspace": (c_int, [c_int, c_int, c_ll, ctypes.POINTER(c_ll)]),
+    "jvmc_tdvp_solve": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ll, c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_dbl, c_int, c_dbl,
+                                c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ll, c_ptr]),
+    "jvmc_minsr_solve_workspace": (c_int, [c_int, c_int, ctypes.POINTER(c_ll)]),
+    "jvmc_minsr_solve": (c_int, [c_int, c_int, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ll, c_ptr]),
+    "jvmc_comm_nccl_version": (c_int, []),
+    "jvmc_comm_unique_id": (c_int, [c_ptr]),
+    "jvmc_comm_init": (c_int, [c_ptr, c_int, c_int, ctypes.POINTER(c_ptr)]),
+    "jvmc_comm_destroy": (c_int, [c_ptr]),
+    "jvmc_comm_allreduce_sum_f64": (c_int, [c_ptr, c_ptr, c_ll, c_ptr]),
+    "jvmc_comm_allgather_bytes": (c_int, [c_ptr, c_ptr, c_ptr, c_ll, c_ptr]),
+    "jvmc_comm_bcast_bytes": (c_int, [c_ptr, c_ptr, c_ll, c_int, c_ptr]),
+    "jvmc_comm_reduce_scatter_sum_f64": (c_int, [c_ptr, c_ptr, c_ptr, c_ll, c_ptr]),
     "jvmc_i8_set_debug": (c_int, [c_int]),
+    "jvmc_i8_set_trace": (c_int, [c_ptr, c_int]),
     "jvmc_hermitian_mirror_blocks": (c_int, [c_ptr, c_int, c_int, c_ptr]),
     "jvmc_hermitian_packed_elems": (c_ll, [c_int, c_int]),
     "jvmc_hermitian_pack_blocks": (c_int, [c_ptr, c_int, c_int, c_ptr, c_int, c_ptr]),
@@ -122,7 +136,8 @@ def check(rc, what=""):
 
 
 # kernels launched per entry point (for the gpu_launches figure of bench.py)
-_KERNELS_PER_CALL = {"jvmc_bfo_matels": 2, "jvmc_rbm_moments": 2, "jvmc_i8_slice": 3, "jvmc_eigh": 0}
+_KERNELS_PER_CALL = {"jvmc_bfo_matels": 2, "jvmc_rbm_moments": 2, "jvmc_i8_slice": 3, "jvmc_eigh": 0,
+                     "jvmc_tdvp_solve": 6, "jvmc_minsr_solve": 3}
 LAUNCHES = 0
 
 

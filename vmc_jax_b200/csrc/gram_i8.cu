@@ -5,8 +5,8 @@
 //
 //   A[(r,j),(r',l)] = alpha sum_n s_n conj(Y_nj) Y_nl - kappa conj(mu_rj) mu_r'l ,   s_n = sigma_nr sigma_nr'
 //
-// 1. jvmc_i8_slice: every real column z of Z = [Re Y_j, Im Y_j] (interleaved, 2M columns) gets a power-of-two scale
-//    c_z > 2 max_n |Z_nz| and each entry is split into 5 balanced base-255 digits, Z_nz = c_z sum_k d_k 255^-k,
+// 1. jvmc_i8_slice: every real column z of Z = [Re Y_j, Im Y_j] (interleaved, 2M columns) gets the scale
+//    c_z = 2 max_n |Z_nz| (1 + 2^-30) and each entry is split into 5 balanced base-255 digits, Z_nz = c_z sum_k d_k 255^-k,
 //    d_k in [-127, 127] (int8, symmetric so that negation is exact).  Digits are stored in the K-major SWIZZLE_NONE
 //    UMMA canonical layout [n/32][digit][z/8][(n/16)%2][z%8][n%16], so that a (tile, 32-sample stage, digit) is one
 //    contiguous block (one TMA bulk copy each).
@@ -150,14 +150,13 @@ __global__ void i8_colmax_kernel(const cplx* __restrict__ Y, long long B, int M,
   atomicMax(colmax + 2 * j + 1, (unsigned long long)__double_as_longlong(mi));
 }
 
-// scale[z] = 2^(e+1) with max < 2^e  (so that |Z/scale| < 1/2); 1 for empty columns
+// scale[z] = 2 max_n |Z_nz| (1 + 2^-30), so that |Z/scale| < 1/2 and the leading digit uses its whole range
+// (a power-of-two scale would waste up to one bit); 1 for empty columns
 __global__ void i8_scale_kernel(const unsigned long long* __restrict__ colmax, int twoM, double* __restrict__ scale) {
   const int z = blockIdx.x * blockDim.x + threadIdx.x;
   if (z >= twoM) return;
   double m = __longlong_as_double((long long)colmax[z]);
-  int e = 0;
-  if (m > 0.0) { (void)frexp(m, &e); ++e; }
-  scale[z] = ldexp(1.0, e);
+  scale[z] = (m > 0.0) ? 2.0 * m * (1.0 + 9.313225746154785e-10) : 1.0;
 }
 
 // one thread per (16-sample chunk, real column z): 16 strided loads, 5 x 16 B stores
@@ -208,7 +207,10 @@ struct I8Args {
                               // 32 = no shared-memory reads in the sign pass, 64 = no sign arithmetic
   int cl;                     // thread-block cluster size along the pair axis (operand tiles are TMA-multicast)
   long long pairs;            // R (R + 1) / 2; CTAs beyond it only pad the last cluster
+  long long* trace;           // development: clock64 time stamps of one CTA, 8 events per stage (jvmc_i8_set_trace)
+  int traceTile;
 };
+#define I8_TRACE(ev) do { if (tracing) a.trace[(size_t)g * 16 + (ev)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   const int RG = tile[0], CG = tile[1], NC = tile[2], jlo = tile[3], jhi = tile[4];
   const unsigned bBytes = (unsigned)(NC * I8_KS);       // bytes of one B digit tile of a stage
   const long long numStages = a.stage1 - a.stage0;
+  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && (int)blockIdx.y == a.traceTile && lane == 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < I8_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, (unsigned)a.cl); }
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         if (a.cl == 1) bulk_g2s(dst, src, bytes, full + slot);
         else if ((unsigned)lane % (unsigned)a.cl == crank) bulk_g2s_mc(dst, src, bytes, full + slot, cmask);   // my share
       }
+      I8_TRACE(0);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread): 15 UTCIMMA per stage, A from TMEM, B from smem =====================
@@ -281,31 +285,63 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       const uint32_t idesc1 = ibase | ((uint32_t)((1 * NC) >> 3) << 17);
       const uint32_t idesc2 = ibase | ((uint32_t)((2 * NC) >> 3) << 17);
       const uint32_t idesc3 = ibase | ((uint32_t)((3 * NC) >> 3) << 17);
-      for (long long g = 0; g < numStages; ++g) {
-        const int slot = (int)(g % I8_SLOTS);
-        const int b = (int)(g % I8_NB);
-        const uint32_t acc = (g == 0) ? 0u : 1u;
-        if (!(a.dbg & 1)) mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
-        if (!(a.dbg & 3)) mbar_wait(aready + b, (unsigned)((g / I8_NB) & 1));
+      // Issue loop.  tcgen05.mma issue blocks once the tensor pipe's short queue is full, so every cycle this thread
+      // spends between two stages (barrier polls, ring arithmetic) is a cycle the pipe drains and then idles: the
+      // round-1 trace (tools/gram_trace.py) showed ~620-800 cycles of MMA execution per stage followed by ~365 idle
+      // cycles of bookkeeping (64-bit g % 6, two mbarrier polls).  Therefore (i) the ring position / phase bits are
+      // carried in 32-bit registers, (ii) the barriers of stage g+1 are polled in the MIDDLE of stage g, right after
+      // two N = 240 instructions were queued, and (iii) with the sign pass on, `aready` alone is waited for: the sign
+      // warps observed `full` of that stage before they arrived on it (acquire/release chain).
+      const bool useFull = (a.dbg & 3) != 0 && !(a.dbg & 1);     // ablation modes without a sign pass
+      const bool useReady = !(a.dbg & 3);
+      uint32_t slot = 0, fullPar = 0, bufPar = 0, b = 0;       // bufPar bit q: parity of the next use of TMEM A buffer q
+      const uint32_t ring0 = smem_u32(ring) + I8_S * I8_A_BYTES;
+      auto wait_stage = [&](uint32_t sl, uint32_t fp, uint32_t bb, uint32_t bp) {
+        if (useFull) mbar_wait(full + sl, fp);
+        if (useReady) mbar_wait(aready + bb, bp);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const unsigned sb = smem_u32(ring + (size_t)slot * I8_STAGE_BYTES) + I8_S * I8_A_BYTES;
+      };
+      if (numStages > 0) wait_stage(0u, 0u, 0u, 0u);
+      for (long long g = 0; g < numStages; ++g) {
+        I8_TRACE(2);
+        const unsigned sb = ring0 + slot * (unsigned)I8_STAGE_BYTES;
         const uint32_t ta = tmem + (uint32_t)(I8_ACOL + b * I8_S * 8);
-        // (digit k, first k', count n): level column = (k + k' - 2) * 80
+        // (digit k, first k', count n): level column = (k + k' - 2) * NC
         auto mma = [&](int k, int kp, int n, uint32_t idesc, uint32_t accumulate) {
           uint64_t db = umma_desc(sb + (kp - 1) * bBytes, 128, 256);   // LBO: next 16-sample chunk, SBO: next 8 rows
           umma_i8_ts(tmem + (uint32_t)((k + kp - 2) * NC), ta + (uint32_t)((k - 1) * 8), db, idesc, accumulate);
         };
-        mma(1, 1, 3, idesc3, acc);      // levels 2,3,4 (first writer)
-        mma(1, 4, 2, idesc2, acc);      // levels 5,6   (first writer)
-        mma(2, 1, 3, idesc3, 1u);       // levels 3,4,5
-        mma(2, 4, 1, idesc1, 1u);       // level 6
-        mma(3, 1, 3, idesc3, 1u);       // levels 4,5,6
-        mma(4, 1, 2, idesc2, 1u);       // levels 5,6
-        mma(5, 1, 1, idesc1, 1u);       // level 6
+        // next stage's ring position
+        uint32_t nslot = slot + 1, nfullPar = fullPar;
+        if (nslot == I8_SLOTS) { nslot = 0; nfullPar ^= 1u; }
+        uint32_t nb = b + 1;
+        if (nb == I8_NB) nb = 0;
+        bufPar ^= 1u << b;                                       // parity of this buffer's NEXT use
+        if (g == 0) {
+          mma(1, 1, 3, idesc3, 0u);       // levels 2,3,4 (first writer)
+          mma(1, 4, 2, idesc2, 0u);       // levels 5,6   (first writer)
+          mma(2, 4, 1, idesc1, 1u);       // level 6
+          mma(5, 1, 1, idesc1, 1u);       // level 6
+          mma(4, 1, 2, idesc2, 1u);       // levels 5,6
+          mma(2, 1, 3, idesc3, 1u);       // levels 3,4,5
+        } else {
+          mma(2, 4, 1, idesc1, 1u);
+          mma(5, 1, 1, idesc1, 1u);
+          mma(1, 4, 2, idesc2, 1u);
+          mma(4, 1, 2, idesc2, 1u);
+          mma(1, 1, 3, idesc3, 1u);
+          mma(2, 1, 3, idesc3, 1u);
+        }
+        I8_TRACE(1);
+        if (g + 1 < numStages) wait_stage(nslot, nfullPar, nb, (bufPar >> nb) & 1u);   // overlapped with the queued MMAs
+        I8_TRACE(8);
+        mma(3, 1, 3, idesc3, 1u);         // levels 4,5,6
         if (a.cl == 1) umma_commit(empty + slot);        // smem slot reusable once these MMAs retire
         else umma_commit_mc(empty + slot, cmask);        // ... in every CTA of the cluster (they all write into it)
         umma_commit(afree + b);                          // ... and so is the TMEM A buffer
         if (g + 1 == numStages) umma_commit(accfull);
+        I8_TRACE(3);
+        slot = nslot; fullPar = nfullPar; b = nb;
       }
     }
   } else {
@@ -333,6 +369,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         // The signed digits are prepared in registers BEFORE waiting for the TMEM buffer, so that only the
         // TMEM store sits on the MMA(g-2) -> sign(g) -> MMA(g) dependency chain.
         mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
+        if (warp == 2) I8_TRACE(4);
         const unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
         // two warps share a TMEM lane quarter: warps 2-5 take digits 0-2, warps 6-9 digits 3-4
         const int kbeg = (warp < 6) ? 0 : 3, nk = (I8_SW == 4) ? I8_S : ((warp < 6) ? 3 : 2);
@@ -352,7 +389,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
             if (!(a.dbg & 64)) w[k][q] = ((aa & 0x7F7F7F7Fu) + (msk[q] & 0x01010101u)) ^ (aa & 0x80808080u);
           }
         }
+        if (warp == 2) I8_TRACE(5);
         if (g >= I8_NB) mbar_wait(afree + b, (unsigned)((g / I8_NB - 1) & 1));
+        if (warp == 2) I8_TRACE(6);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
         for (int k = 0; k < I8_KW; ++k) {
@@ -363,6 +402,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
                        "r"(w[k][7]) : "memory");
         }
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        if (warp == 2) I8_TRACE(7);
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(aready + b);
@@ -452,6 +492,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
 
 static int g_i8_dbg = 0;
 static int g_i8_cluster = 2;
+static long long* g_i8_trace = nullptr;
+static int g_i8_trace_tile = 0;
+// development: device buffer of 16 * 832 int64 that receives the clock64 time stamps of CTA (pair 0, tile `tile`) of the
+// next launches (events per stage: 0 TMA issued, 2 MMA stage start, 1 six MMAs issued, 8 next stage's barriers seen, 3 stage committed, 4 sign warp saw full,
+// 5 signs prepared, 6 sign warp saw TMEM buffer free, 7 TMEM stores done); nullptr switches tracing off
+extern "C" int jvmc_i8_set_trace(void* buf, int tile) {
+  g_i8_trace = (long long*)buf;
+  g_i8_trace_tile = tile;
+  return JVMC_OK;
+}
 // development knobs: bits 0-7 ablation flags (timing only, results invalid); bits 8-11, when non-zero, set the cluster size
 extern "C" int jvmc_i8_set_debug(int flags) {
   g_i8_dbg = flags & 0xFF;
@@ -521,6 +571,7 @@ extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale
   if (numTiles > 65535 || pairs > 2147483647LL) return JVMC_ERR_UNSUPPORTED;
   // (tile descriptors are device data: NC in {16, 32, ..., I8_TN} and the padding bound are the caller's contract)
   a.cl = g_i8_cluster; a.pairs = pairs;
+  a.trace = g_i8_trace; a.traceTile = g_i8_trace_tile;
   dim3 grid((unsigned)((pairs + a.cl - 1) / a.cl * a.cl), (unsigned)numTiles);
   const long long numStages = a.numChunks / 2;
   cudaLaunchConfig_t cfg = {};

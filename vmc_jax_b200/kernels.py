@@ -431,3 +431,63 @@ def tdvp_regularize(ev, VtF, snr, F, pinvTol, pinvCutoff, snrTol):
     call("jvmc_tdvp_regularize", n, ptr(ev), ptr(VtF), ptr(snr), ptr(F), float(pinvTol), float(pinvCutoff),
          float(snrTol), ptr(pinvEv), ptr(scal))
     return pinvEv, scal
+
+
+def tdvp_solve(St, F, D, e, w, prefactor, numSamplesGlobal, snrTol, pinvTol, pinvCutoff, useSnr=True, comm=None):
+    """TDVP.solve (reference jVMC/util/tdvp.py:153-213) as ONE C-ABI call: eigh, V^dagger F, SNR from the per-sample
+    projections, cutoff loop, update.  St: column-major image of q(S0) (float64 -> 'real', complex128 -> 'imag'),
+    overwritten by the eigenvectors (row k of the returned Vt = eigenvector k).  D [B, n] / e [B] / w [B]: centred data
+    of the gradients and local energies (D None: no SNR at all); useSnr False: SNR computed but not applied (ExactSampler).
+    Returns a dict."""
+    n = St.shape[0]
+    mode = 1 if St.is_complex() else 0
+    assert St.is_contiguous() and St.dtype in (F64, CPX)
+    dev = St.device
+    F = _c(F, CPX)
+    B = 0
+    if D is not None:
+        D, e, w = _c(D, CPX), _c(e, CPX), _c(w, F64)
+        B = D.shape[0]
+    lib = _lib.load()
+    nb = ctypes.c_longlong(0)
+    _lib.require_cuda()
+    _lib.check(lib.jvmc_tdvp_solve_workspace(n, mode, B, ctypes.byref(nb)), "jvmc_tdvp_solve_workspace")
+    work = torch.empty(max(nb.value, 8), dtype=torch.uint8, device=dev)
+    out = {k: torch.empty(n, dtype=F64, device=dev) for k in ("ev", "rhoVar", "snr", "pinvEv", "update")}
+    out["VtF"] = torch.empty(n, dtype=CPX, device=dev)
+    out["scal"] = torch.empty(2, dtype=F64, device=dev)
+    info = torch.zeros(1, dtype=I32, device=dev)
+    x = complex(prefactor)
+    call("jvmc_tdvp_solve", n, mode, ptr(St), ptr(F), B, ptr(D), ptr(e), ptr(w), x.real, x.imag, float(numSamplesGlobal),
+         int(bool(useSnr)), float(snrTol), float(pinvTol), float(pinvCutoff), comm, ptr(out["ev"]), ptr(out["VtF"]), ptr(out["rhoVar"]),
+         ptr(out["snr"]), ptr(out["pinvEv"]), ptr(out["update"]), ptr(out["scal"]), ptr(info), ptr(work), nb.value)
+    bad = int(info.item())
+    if bad != 0:
+        raise RuntimeError("cuSOLVER eigen-decomposition failed inside jvmc_tdvp_solve (n = %d, devInfo = %d)" % (n, bad))
+    out["Vt"] = St
+    if D is None:
+        out["rhoVar"] = out["snr"] = None
+    return out
+
+
+def minsr_solve(Tt, e, rtol):
+    """pinv(T, rtol, hermitian=True) @ e (reference jVMC/util/minsr.py:61-62,73-78) as one C-ABI call.  Tt: column-major
+    image of T (overwritten by the eigenvectors).  Returns (x complex[n], ev)."""
+    n = Tt.shape[0]
+    isC = Tt.is_complex()
+    assert Tt.is_contiguous() and Tt.dtype in (F64, CPX)
+    dev = Tt.device
+    e = _c(e, CPX)
+    lib = _lib.load()
+    nb = ctypes.c_longlong(0)
+    _lib.require_cuda()
+    _lib.check(lib.jvmc_minsr_solve_workspace(n, int(isC), ctypes.byref(nb)), "jvmc_minsr_solve_workspace")
+    work = torch.empty(max(nb.value, 8), dtype=torch.uint8, device=dev)
+    x = torch.empty(n, dtype=CPX, device=dev)
+    ev = torch.empty(n, dtype=F64, device=dev)
+    info = torch.zeros(1, dtype=I32, device=dev)
+    call("jvmc_minsr_solve", n, int(isC), ptr(Tt), ptr(e), float(rtol), ptr(x), ptr(ev), ptr(info), ptr(work), nb.value)
+    bad = int(info.item())
+    if bad != 0:
+        raise RuntimeError("cuSOLVER eigen-decomposition failed inside jvmc_minsr_solve (n = %d, devInfo = %d)" % (n, bad))
+    return x, ev

@@ -32,7 +32,8 @@ def init_distributed(backend=None):
     """Join the torchrun rendezvous (RANK / WORLD_SIZE / MASTER_ADDR from the environment)."""
     if dist.is_available() and not dist.is_initialized() and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         if backend is None:
-            backend = "nccl" if torch.cuda.is_available() else "gloo"
+            # JVMC_DIST_BACKEND=gloo lets several ranks share one GPU (tests on a single-GPU box); NCCL otherwise
+            backend = os.environ.get("JVMC_DIST_BACKEND") or ("nccl" if torch.cuda.is_available() else "gloo")
         kw = {}
         if backend == "nccl":
             kw["device_id"] = global_defs.myDevice
@@ -41,6 +42,35 @@ def init_distributed(backend=None):
 
 
 init_distributed()
+
+
+_capi_comm = None
+
+
+def capi_comm():
+    """NCCL communicator of the C ABI (include/jvmc_b200.h: jvmc_comm_init) spanning the same ranks as the
+    torch.distributed group, created on first use -- the 128-byte NCCL id of rank 0 travels over the existing group.
+    It is handed to the C entry points that reduce in-stream themselves (jvmc_tdvp_solve).  None for a single rank or
+    when the ranks do not own one GPU each (gloo on a shared device)."""
+    global _capi_comm
+    _refresh()
+    if commSize == 1 or dist.get_backend() != "nccl":
+        return None
+    if _capi_comm is None:
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        idbuf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(lib.jvmc_comm_unique_id(idbuf), "jvmc_comm_unique_id")
+        box = [bytes(idbuf.raw) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        idbuf = ctypes.create_string_buffer(box[0], 128)
+        handle = ctypes.c_void_p()
+        torch.cuda.set_device(global_defs.myDevice)
+        _lib.check(lib.jvmc_comm_init(idbuf, rank, commSize, ctypes.byref(handle)), "jvmc_comm_init")
+        _capi_comm = handle
+    return _capi_comm
 
 
 def distribute_sampling(numSamples, localDevices=None, numChainsPerDevice=1):

@@ -19,6 +19,10 @@ from . import mpi_wrapper as mpi
 GRAM_BACKEND = os.environ.get("JVMC_GRAM_BACKEND", "i8")
 
 
+def _gram_backend():
+    return {"i8": K.rbm_gram_S_i8, "dmma": K.rbm_gram_S}[GRAM_BACKEND]
+
+
 def _w_like(w, data):
     return w.reshape(w.shape + (1,) * (data.dim() - 2))
 
@@ -245,7 +249,7 @@ class RBMGradientObs(SampledObs):
             kappa = 1.0 / mpi.commSize
             # backend: "i8" = tcgen05 INT8 tensor cores with error-free splitting (fp64-equivalent, default),
             #          "dmma" = fp64 DMMA
-            gram = K.rbm_gram_S_i8 if GRAM_BACKEND == "i8" else K.rbm_gram_S
+            gram = _gram_backend()
             if self._uniform is not None:
                 A = gram(self._tau, self._sigT, mu, float(self._uniform), kappa)
             else:
@@ -262,7 +266,7 @@ class RBMGradientObs(SampledObs):
         w2 >= 0 -- the same Gram kernel as gram_A with another weight vector (SNR second moments, util/tdvp.py)."""
         if self._sigT is None:
             self._sigT = K.pack_sigma(self._s, self.hasBias)
-        gram = K.rbm_gram_S_i8 if GRAM_BACKEND == "i8" else K.rbm_gram_S
+        gram = _gram_backend()
         Y = self._tau * torch.sqrt(w2.to(torch.float64))[:, None]
         A2 = gram(Y, self._sigT, torch.zeros((self.R, self.M), dtype=torch.complex128, device=Y.device), 1.0, 0.0)
         half = os.environ.get("JVMC_HERMITIAN_ALLREDUCE")

@@ -6,32 +6,28 @@ from .. import mpi_wrapper as mpi
 from ..stats import SampledObs, RBMGradientObs
 
 
-def _eigh_device(T):
-    """Hermitian eigen-decomposition through the C ABI (cuSOLVER): the column-major image of T goes in as a private
-    buffer (the solver overwrites it); columns of the returned V are the eigenvectors.  No host path."""
+def _device_image(T):
+    """private column-major image of T for the solver (which overwrites it); no host path"""
     if not T.is_cuda:
         raise RuntimeError("MinSR pseudo-inverse needs the CUDA library (no CPU fallback)")
-    ev, Vt, _ = K.eigh_inplace(T.T.clone(memory_format=torch.contiguous_format))
-    return ev, Vt.T
-
-
-def _pinv_weights(ev, rtol):
-    """jnp.linalg.pinv(hermitian=True): eigenvalues with |ev| <= rtol * max|ev| are dropped."""
-    cut = rtol * ev.abs().max()
-    return torch.where(ev.abs() > cut, 1.0 / torch.where(ev == 0, torch.ones_like(ev), ev), torch.zeros_like(ev))
+    return T.T.clone(memory_format=torch.contiguous_format)
 
 
 def pinv_hermitian(T, rtol):
-    """jnp.linalg.pinv(T, rtol=..., hermitian=True) (reference jVMC/util/minsr.py:61,73)."""
-    ev, V = _eigh_device(T)
-    return (V * _pinv_weights(ev, rtol).to(V.dtype)[None, :]) @ V.conj().T
+    """jnp.linalg.pinv(T, rtol=..., hermitian=True) (reference jVMC/util/minsr.py:61,73): eigenvalues with
+    |ev| <= rtol * max|ev| are dropped."""
+    ev, Vt, _ = K.eigh_inplace(_device_image(T))
+    V = Vt.T
+    cut = rtol * ev.abs().max()
+    inv = torch.where(ev.abs() > cut, 1.0 / torch.where(ev == 0, torch.ones_like(ev), ev), torch.zeros_like(ev))
+    return (V * inv.to(V.dtype)[None, :]) @ V.conj().T
 
 
 def pinv_hermitian_apply(T, rtol, b):
-    """pinv(T, rtol, hermitian=True) @ b without forming the pseudo-inverse: V (inv_ev * (V^dagger b)) -- two
-    matrix-vector products instead of an N^3 matrix product."""
-    ev, V = _eigh_device(T)
-    return torch.mv(V, _pinv_weights(ev, rtol).to(V.dtype) * torch.mv(V.conj().T, b.to(V.dtype)))
+    """pinv(T, rtol, hermitian=True) @ b without forming the pseudo-inverse -- one C-ABI call (jvmc_minsr_solve:
+    eigen-decomposition, eigenvalue cut, V (w * V^dagger b))."""
+    x, _ = K.minsr_solve(_device_image(T), b.to(torch.complex128), rtol)
+    return x if T.is_complex() or b.is_complex() else x.real
 
 
 class MinSR:

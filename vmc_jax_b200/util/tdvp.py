@@ -292,10 +292,29 @@ class TDVP:
             update = self._flat_from_pairs(G, (P1 + P2).real * r2, (P1.imag - P2.imag) * r2)
         return update, scal[0], scal[1]
 
+    def _solve_capi(self, Eloc, gradients):
+        """TDVP.solve (reference :183-213) for dense gradient data in ONE C-ABI call (jvmc_tdvp_solve: eigh, V^dagger F,
+        per-sample SNR projections, cutoff loop, update), the moments of rho summed over ranks in-stream."""
+        self.S, F = self.get_tdvp_equation(Eloc, gradients)
+        S = self.S
+        St = S.contiguous().clone() if self._mode == 0 else S.T.clone(memory_format=torch.contiguous_format)
+        P = St.shape[0]
+        D = gradients._data.reshape(-1, P)
+        res = K.tdvp_solve(St, F.to(torch.complex128), D, Eloc._data.reshape(-1), gradients._weights.reshape(-1),
+                           self.rhsPrefactor, mpi.globNumSamples, self.snrTol, self.pinvTol, self.pinvCutoff,
+                           useSnr=not _is_exact_sampler(self.sampler), comm=mpi.capi_comm())
+        self.ev, self._Vt, self.VtF = res["ev"], res["Vt"], res["VtF"]
+        self.rhoVar, self.snr = res["rhoVar"], res["snr"]
+        self.invEv = torch.where(torch.abs(self.ev / self.ev[-1]) > 1e-14, 1. / self.ev, torch.zeros_like(self.ev))
+        return res["update"], res["scal"][0], res["scal"][1]
+
     def solve(self, Eloc, gradients):
         """reference :183-213."""
         if self.pcLevel and self.diagonalizeOnDevice and isinstance(gradients, RBMGradientObs) and gradients.holomorphic:
             return self._solve_pc(Eloc, gradients)
+        if self.diagonalizeOnDevice and not isinstance(gradients, RBMGradientObs) and \
+                (mpi.commSize == 1 or mpi.capi_comm() is not None):
+            return self._solve_capi(Eloc, gradients)
         self.S, F = self.get_tdvp_equation(Eloc, gradients)
         self._transform_to_eigenbasis(self.S, F)
         exact = _is_exact_sampler(self.sampler)
