@@ -114,6 +114,9 @@ int jvmc_i8_set_debug(int flags);   /* development ablations of the int8 Gram pi
 int jvmc_i8_set_trace(void* buf, int tile);   /* development: per-stage clock64 trace of one CTA (16 x 832 int64, device) */
 int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long long* colmax, double* scale,
                   signed char* digits, void* stream);
+/* Heavy-tail diagnostic behind the choice between the int8 and the fp64 DMMA Gram (kernels.py:rbm_gram_S_auto):
+ * ratios[z] (device, 2M) <- max_n|Z_nz| / rms_n(Z_nz) per real column of Y.  scratch: 4M doubles (device). */
+int jvmc_i8_tail_ratios(const double* Y, long long B, int M, double* scratch, double* ratios, void* stream);
 int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale, long long B, int M, int R,
                        const unsigned int* sigT, const int* tiles, int numTiles, const double* mu, double alpha,
                        double kappa, double* A, void* stream);

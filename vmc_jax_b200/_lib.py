@@ -71,6 +71,7 @@ _SIGS = {
     "jvmc_symrbm_mcmc": (c_int, [c_ptr, c_ll, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ull,
                                  c_ull, c_ll, c_dbl, c_int, c_ll, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "jvmc_i8_slice": (c_int, [c_ptr, c_ll, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "jvmc_i8_tail_ratios": (c_int, [c_ptr, c_ll, c_int, c_ptr, c_ptr, c_ptr]),
     "jvmc_rbm_gram_S_i8": (c_int, [c_ptr, c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_dbl, c_dbl, c_ptr,
                                    c_ptr]),
     "jvmc_pack_sigma_rows": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr]),
@@ -136,7 +137,7 @@ def check(rc, what=""):
 
 
 # kernels launched per entry point (for the gpu_launches figure of bench.py)
-_KERNELS_PER_CALL = {"jvmc_bfo_matels": 2, "jvmc_rbm_moments": 2, "jvmc_i8_slice": 3, "jvmc_eigh": 0,
+_KERNELS_PER_CALL = {"jvmc_bfo_matels": 2, "jvmc_rbm_moments": 2, "jvmc_i8_slice": 3, "jvmc_i8_tail_ratios": 2, "jvmc_eigh": 0,
                      "jvmc_tdvp_solve": 6, "jvmc_minsr_solve": 3}
 LAUNCHES = 0
 

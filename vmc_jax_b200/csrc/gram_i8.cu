@@ -92,6 +92,16 @@ __device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, unsigned
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ unsigned cluster_ctarank() {
   unsigned r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
@@ -157,6 +167,34 @@ __global__ void i8_scale_kernel(const unsigned long long* __restrict__ colmax, i
   if (z >= twoM) return;
   double m = __longlong_as_double((long long)colmax[z]);
   scale[z] = (m > 0.0) ? 2.0 * m * (1.0 + 9.313225746154785e-10) : 1.0;
+}
+
+// Heavy-tail diagnostic: per real column sum_n Z_nz^2 and max_n |Z_nz| (scratch zeroed by the caller), then
+// ratio[z] = max_n|Z_nz| / rms_n(Z_nz) (0 for an all-zero column).  The digit resolution is relative to the column
+// maximum: the error of A_zz' relative to its natural size sqrt(A_zz A_z'z') grows like ratio_z ratio_z' / sqrt(B).
+__global__ void i8_colsq_kernel(const cplx* __restrict__ Y, long long B, int M, double* __restrict__ colsq,
+                                unsigned long long* __restrict__ colmax) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const long long n0 = (long long)blockIdx.y * 1024;
+  const long long n1 = min(B, n0 + 1024);
+  double sr = 0.0, si = 0.0, mr = 0.0, mi = 0.0;
+  for (long long n = n0; n < n1; ++n) {
+    cplx v = Y[n * M + j];
+    sr = fma(v.x, v.x, sr); si = fma(v.y, v.y, si);
+    mr = fmax(mr, fabs(v.x)); mi = fmax(mi, fabs(v.y));
+  }
+  atomicAdd(colsq + 2 * j, sr);
+  atomicAdd(colsq + 2 * j + 1, si);
+  atomicMax(colmax + 2 * j, (unsigned long long)__double_as_longlong(mr));
+  atomicMax(colmax + 2 * j + 1, (unsigned long long)__double_as_longlong(mi));
+}
+__global__ void i8_tail_ratio_kernel(const double* __restrict__ colsq, const unsigned long long* __restrict__ colmax,
+                                     int twoM, double invB, double* __restrict__ ratio) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= twoM) return;
+  const double ms = colsq[z] * invB;
+  ratio[z] = ms > 0.0 ? __longlong_as_double((long long)colmax[z]) / sqrt(ms) : 0.0;
 }
 
 // one thread per (16-sample chunk, real column z): 16 strided loads, 5 x 16 B stores
@@ -276,26 +314,28 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       I8_TRACE(0);
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread): 15 UTCIMMA per stage, A from TMEM, B from smem =====================
-    if (lane == 0) {
-      // Digit tiles of B are contiguous in smem ([digit][rowgroup][chunk]), and the level accumulators are adjacent
-      // TMEM column blocks, so ONE instruction with N = 80 n multiplies A_k with B_k'..B_k'+n-1 and accumulates into
-      // levels k+k' .. k+k'+n-1: 7 instructions per stage instead of 15 (UTCIMMA issue is the scarce resource).
+    // ===================== MMA issuer: warp 1, convergent; one elected lane issues =====================
+    // Digit tiles of B are contiguous in smem ([digit][rowgroup][chunk]), and the level accumulators are adjacent
+    // TMEM column blocks, so ONE instruction with N = NC n multiplies A_k with B_k'..B_k'+n-1 and accumulates into
+    // levels k+k' .. k+k'+n-1: 7 instructions per stage instead of 15.
+    // The warp stays convergent and every address / descriptor is computed from warp-uniform values, so that the
+    // operands live in uniform registers: issuing from a divergent `lane == 0` branch (round 1) made the compiler
+    // wrap every UTCIMMA into an ELECT / R2UR / BRA.U.ANY loop, ~60 cycles per instruction, and the single-thread
+    // bookkeeping between stages (64-bit g % 6, two barrier polls) left the tensor pipe idle for ~365 of ~1080
+    // cycles per stage (trace: tools/gram_trace.py).  The barriers of stage g+1 are polled between the MMAs of stage
+    // g; with the sign pass on, `aready` alone is waited for (the sign warps observed `full` before arriving on it).
+    {
+      const uint32_t NCu = (uint32_t)__shfl_sync(0xffffffffu, NC, 0);
+      const uint32_t tmemU = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t ibase = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_TM >> 4) << 24);
-      const uint32_t idesc1 = ibase | ((uint32_t)((1 * NC) >> 3) << 17);
-      const uint32_t idesc2 = ibase | ((uint32_t)((2 * NC) >> 3) << 17);
-      const uint32_t idesc3 = ibase | ((uint32_t)((3 * NC) >> 3) << 17);
-      // Issue loop.  tcgen05.mma issue blocks once the tensor pipe's short queue is full, so every cycle this thread
-      // spends between two stages (barrier polls, ring arithmetic) is a cycle the pipe drains and then idles: the
-      // round-1 trace (tools/gram_trace.py) showed ~620-800 cycles of MMA execution per stage followed by ~365 idle
-      // cycles of bookkeeping (64-bit g % 6, two mbarrier polls).  Therefore (i) the ring position / phase bits are
-      // carried in 32-bit registers, (ii) the barriers of stage g+1 are polled in the MIDDLE of stage g, right after
-      // two N = 240 instructions were queued, and (iii) with the sign pass on, `aready` alone is waited for: the sign
-      // warps observed `full` of that stage before they arrived on it (acquire/release chain).
+      const uint32_t idesc1 = ibase | (((1u * NCu) >> 3) << 17);
+      const uint32_t idesc2 = ibase | (((2u * NCu) >> 3) << 17);
+      const uint32_t idesc3 = ibase | (((3u * NCu) >> 3) << 17);
       const bool useFull = (a.dbg & 3) != 0 && !(a.dbg & 1);     // ablation modes without a sign pass
       const bool useReady = !(a.dbg & 3);
       uint32_t slot = 0, fullPar = 0, bufPar = 0, b = 0;       // bufPar bit q: parity of the next use of TMEM A buffer q
       const uint32_t ring0 = smem_u32(ring) + I8_S * I8_A_BYTES;
+      const uint32_t bStep = (NCu * (uint32_t)I8_KS) >> 4;       // one B digit tile in 16-byte units
       auto wait_stage = [&](uint32_t sl, uint32_t fp, uint32_t bb, uint32_t bp) {
         if (useFull) mbar_wait(full + sl, fp);
         if (useReady) mbar_wait(aready + bb, bp);
@@ -304,42 +344,46 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       if (numStages > 0) wait_stage(0u, 0u, 0u, 0u);
       for (long long g = 0; g < numStages; ++g) {
         I8_TRACE(2);
-        const unsigned sb = ring0 + slot * (unsigned)I8_STAGE_BYTES;
-        const uint32_t ta = tmem + (uint32_t)(I8_ACOL + b * I8_S * 8);
+        // K-major SWIZZLE_NONE descriptor of B digit tile k': low word = (address >> 4) | LBO(128 B) << 16,
+        // high word = SBO(256 B) | version bit
+        const uint32_t dlo = (((ring0 + slot * (uint32_t)I8_STAGE_BYTES) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
+        const uint32_t ta = tmemU + (uint32_t)I8_ACOL + b * (uint32_t)(I8_S * 8);
         // (digit k, first k', count n): level column = (k + k' - 2) * NC
-        auto mma = [&](int k, int kp, int n, uint32_t idesc, uint32_t accumulate) {
-          uint64_t db = umma_desc(sb + (kp - 1) * bBytes, 128, 256);   // LBO: next 16-sample chunk, SBO: next 8 rows
-          umma_i8_ts(tmem + (uint32_t)((k + kp - 2) * NC), ta + (uint32_t)((k - 1) * 8), db, idesc, accumulate);
+        auto mma = [&](uint32_t k, uint32_t kp, uint32_t idesc, uint32_t accumulate) {
+          const uint64_t db = ((uint64_t)((256u >> 4) | (1u << 14)) << 32) | (uint64_t)(dlo + (kp - 1u) * bStep);
+          umma_i8_ts(tmemU + (k + kp - 2u) * NCu, ta + (k - 1u) * 8u, db, idesc, accumulate);
         };
-        // next stage's ring position
         uint32_t nslot = slot + 1, nfullPar = fullPar;
         if (nslot == I8_SLOTS) { nslot = 0; nfullPar ^= 1u; }
         uint32_t nb = b + 1;
         if (nb == I8_NB) nb = 0;
         bufPar ^= 1u << b;                                       // parity of this buffer's NEXT use
-        if (g == 0) {
-          mma(1, 1, 3, idesc3, 0u);       // levels 2,3,4 (first writer)
-          mma(1, 4, 2, idesc2, 0u);       // levels 5,6   (first writer)
-          mma(2, 4, 1, idesc1, 1u);       // level 6
-          mma(5, 1, 1, idesc1, 1u);       // level 6
-          mma(4, 1, 2, idesc2, 1u);       // levels 5,6
-          mma(2, 1, 3, idesc3, 1u);       // levels 3,4,5
-        } else {
-          mma(2, 4, 1, idesc1, 1u);
-          mma(5, 1, 1, idesc1, 1u);
-          mma(1, 4, 2, idesc2, 1u);
-          mma(4, 1, 2, idesc2, 1u);
-          mma(1, 1, 3, idesc3, 1u);
-          mma(2, 1, 3, idesc3, 1u);
+        const bool leader = elect_one();
+        if (leader) {
+          if (g == 0) {
+            mma(1, 1, idesc3, 0u);       // levels 2,3,4 (first writer)
+            mma(1, 4, idesc2, 0u);       // levels 5,6   (first writer)
+          } else {
+            mma(1, 1, idesc3, 1u);
+            mma(1, 4, idesc2, 1u);
+          }
+          mma(2, 1, idesc3, 1u);         // levels 3,4,5
+          mma(2, 4, idesc1, 1u);         // level 6
+          mma(3, 1, idesc3, 1u);         // levels 4,5,6
         }
+        __syncwarp();
         I8_TRACE(1);
         if (g + 1 < numStages) wait_stage(nslot, nfullPar, nb, (bufPar >> nb) & 1u);   // overlapped with the queued MMAs
         I8_TRACE(8);
-        mma(3, 1, 3, idesc3, 1u);         // levels 4,5,6
-        if (a.cl == 1) umma_commit(empty + slot);        // smem slot reusable once these MMAs retire
-        else umma_commit_mc(empty + slot, cmask);        // ... in every CTA of the cluster (they all write into it)
-        umma_commit(afree + b);                          // ... and so is the TMEM A buffer
-        if (g + 1 == numStages) umma_commit(accfull);
+        if (leader) {
+          mma(4, 1, idesc2, 1u);         // levels 5,6
+          mma(5, 1, idesc1, 1u);         // level 6
+          if (a.cl == 1) umma_commit(empty + slot);        // smem slot reusable once these MMAs retire
+          else umma_commit_mc(empty + slot, cmask);        // ... in every CTA of the cluster (they all write into it)
+          umma_commit(afree + b);                          // ... and so is the TMEM A buffer
+          if (g + 1 == numStages) umma_commit(accfull);
+        }
+        __syncwarp();
         I8_TRACE(3);
         slot = nslot; fullPar = nfullPar; b = nb;
       }
@@ -528,6 +572,20 @@ extern "C" int jvmc_i8_layout(long long B, int M, long long* numChunks, int* num
   int pad = padA > padB ? padA : padB;
   *numZGroups = pad / 8;
   *digitBytes = (long long)I8_S * (*numChunks) * (*numZGroups) * 128;
+  return JVMC_OK;
+}
+
+// ratios[z] <- max_n|Z_nz| / rms_n(Z_nz) for the 2M real columns Z = [Re Y_j, Im Y_j] (interleaved).  scratch: 4M doubles.
+extern "C" int jvmc_i8_tail_ratios(const double* Y, long long B, int M, double* scratch, double* ratios, void* stream) {
+  if (!Y || !scratch || !ratios || B <= 0 || M <= 0) return JVMC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(scratch, 0, sizeof(double) * 4 * M, st);
+  dim3 g1((M + 127) / 128, (unsigned)((B + 1023) / 1024));
+  i8_colsq_kernel<<<g1, 128, 0, st>>>((const cplx*)Y, B, M, scratch, (unsigned long long*)(scratch + 2 * M));
+  JVMC_CHECK_LAUNCH();
+  i8_tail_ratio_kernel<<<(2 * M + 255) / 256, 256, 0, st>>>(scratch, (const unsigned long long*)(scratch + 2 * M), 2 * M,
+                                                            1.0 / (double)B, ratios);
+  JVMC_CHECK_LAUNCH();
   return JVMC_OK;
 }
 

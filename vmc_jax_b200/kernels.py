@@ -347,6 +347,43 @@ def rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out=None):
     return out
 
 
+# ---- which Gram kernel.  The int8 digits resolve 255^-5 of each column's MAXIMUM c_z/2, and the dropped digit pairs
+# (level >= 7) are ~255^-5 c_z c_z' per sample; summed over B samples with random signs, the error of A_zz' relative to
+# its natural size sqrt(A_zz A_z'z') is ~ 0.3 * 4 * 255^-5 * r_z r_z' / sqrt(B) with r_z = max_n|Z_nz| / rms_n(Z_nz)
+# (prefactor measured on B200: 3-8e-14 at config 2 where r ~ 2.5, 2e-10 for two columns with r ~ 200 at B = 30000).
+# Benign tau (|theta| = O(1)) has r of a few; next to a pole of tanh r reaches the hundreds, and entries BETWEEN two such
+# columns lose relative accuracy.  Above I8_MAX_PREDICTED_ERROR the exact fp64 DMMA kernel (4x slower) is used.
+I8_MAX_PREDICTED_ERROR = float(os.environ.get("JVMC_I8_MAX_ERROR", "2e-11"))
+LAST_GRAM = {"backend": None, "tail_ratios": None, "predicted_error": None}
+
+
+def i8_tail_ratios(Y):
+    """max_n |Z_nz| / rms_n(Z_nz) for the 2M real columns of Y (device tensor)."""
+    Y = _c(Y, CPX)
+    B, M = Y.shape
+    scratch = torch.empty(4 * M, dtype=F64, device=Y.device)
+    ratios = torch.empty(2 * M, dtype=F64, device=Y.device)
+    call("jvmc_i8_tail_ratios", ptr(Y), B, M, ptr(scratch), ptr(ratios))
+    return ratios
+
+
+def i8_predicted_error(r1, r2, B):
+    return 0.3 * 4.0 * 255.0 ** -5 * r1 * r2 / max(B, 1) ** 0.5
+
+
+def rbm_gram_S_auto(Y, sigT, mu, alpha, kappa, out=None):
+    """A by the int8 tensor-core kernel when its predicted entry-wise splitting error is below I8_MAX_PREDICTED_ERROR, by
+    the fp64 DMMA kernel otherwise.  Costs one pass over Y and one 16-byte read-back per Gram."""
+    Y = _c(Y, CPX)
+    r = i8_tail_ratios(Y)
+    top = torch.topk(r, 2 if r.numel() > 1 else 1).values.tolist()
+    r1, r2 = top[0], top[-1]
+    err = i8_predicted_error(r1, r2, Y.shape[0])
+    use_i8 = err <= I8_MAX_PREDICTED_ERROR
+    LAST_GRAM.update(backend="i8" if use_i8 else "dmma", tail_ratios=(r1, r2), predicted_error=err)
+    return (rbm_gram_S_i8 if use_i8 else rbm_gram_S)(Y, sigT, mu, alpha, kappa, out)
+
+
 def rbm_gram_T(s, tau, p, mu, hasBias, scale=1.0):
     """Centred tangent kernel T = scale * Obar Obar^dagger [B,B] from the Khatri-Rao factors (no dense O)."""
     s = _c(s, I32)
@@ -394,6 +431,9 @@ def expand_S(A, M, N, hasBias, mode, shift):
     return out
 
 
+EIGH_MAX_N = 32768     # largest n accepted by cuSOLVER 11.7 (CUDA 12.9) dense eigensolvers, probed with tools/eigh_probe.cu
+
+
 def eigh_inplace(St, check=True):
     """Eigen-decomposition of the Hermitian matrix whose column-major image is ``St`` (i.e. St = S^T as
     a row-major tensor; lower triangle of S referenced).  Overwrites St with the eigenvectors: row k of
@@ -404,6 +444,11 @@ def eigh_inplace(St, check=True):
     d = ctypes.c_longlong(0)
     h = ctypes.c_longlong(0)
     _lib.require_cuda()
+    if n > EIGH_MAX_N:
+        raise NotImplementedError(
+            "dense Hermitian eigen-decomposition of size %d: every cuSOLVER dense eigensolver (Xsyevd, Xsyevdx, XsyevBatched, "
+            "Zheevd, Xgesvdp) rejects n > %d (CUSOLVER_STATUS_INVALID_VALUE, measured on B200: profiles/r2_eigh_probe.txt); "
+            "a distributed / two-stage solver is needed at this size" % (n, EIGH_MAX_N))
     _lib.check(lib.jvmc_eigh_workspace(n, int(isC), ctypes.byref(d), ctypes.byref(h)), "jvmc_eigh_workspace")
     work = torch.empty(max(d.value, 8), dtype=torch.uint8, device=St.device)
     w = torch.empty(n, dtype=F64, device=St.device)

@@ -20,7 +20,7 @@ GRAM_BACKEND = os.environ.get("JVMC_GRAM_BACKEND", "i8")
 
 
 def _gram_backend():
-    return {"i8": K.rbm_gram_S_i8, "dmma": K.rbm_gram_S}[GRAM_BACKEND]
+    return {"i8": K.rbm_gram_S_auto, "i8only": K.rbm_gram_S_i8, "dmma": K.rbm_gram_S}[GRAM_BACKEND]
 
 
 def _w_like(w, data):
@@ -247,8 +247,8 @@ class RBMGradientObs(SampledObs):
                 self._sigT = K.pack_sigma(self._s, self.hasBias)
             p = self._p
             kappa = 1.0 / mpi.commSize
-            # backend: "i8" = tcgen05 INT8 tensor cores with error-free splitting (fp64-equivalent, default),
-            #          "dmma" = fp64 DMMA
+            # backend: "i8" = tcgen05 INT8 tensor cores with error-free splitting (fp64-equivalent, default; the fp64 DMMA
+            #          kernel takes over for heavy-tailed tau columns, kernels.rbm_gram_S_auto), "i8only", "dmma"
             gram = _gram_backend()
             if self._uniform is not None:
                 A = gram(self._tau, self._sigT, mu, float(self._uniform), kappa)
