@@ -479,7 +479,7 @@ def main():
         # 15 digit-pair products (levels k+k' <= 6) on tcgen05 kind::i8 with exact int32 accumulation.
         tile_cols = int(K._i8_tiles(M, dev)[:, 2].sum())      # real columns over all tiles (narrow tiles at the diagonal)
         stages = (nLocal + 31) // 32
-        launches_i8 = (stages + 831) // 832
+        launches_i8 = (stages + 799) // 800
         exec_ops = 2.0 * (R * (R + 1) / 2) * stages * (15 * tile_cols) * 128 * 32
         # minimal work of the method: symmetric half of the 2M x 2M real Gram per site pair, 15 digit-pair products
         algo_ops = 2.0 * (R * (R + 1) / 2) * (2 * M * (2 * M + 1) / 2) * nLocal * 15

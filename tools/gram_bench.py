@@ -19,12 +19,13 @@ ap.add_argument("--tile", type=int, default=0)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--dbg", type=int, default=0)
 ap.add_argument("--i8", action="store_true")
+ap.add_argument("--max-stages", type=int, default=0, help="int8 Gram: 32-sample stages per launch (0 = default)")
 ap.add_argument("--clocks", action="store_true", help="sample nvidia-smi SM clock / power during the timed repetitions")
 a = ap.parse_args()
 TILE_ARG = a.tile + 1000 * (0 if a.i8 else a.dbg)
 from vmc_jax_b200 import _lib  # noqa: E402
 if a.i8:
-    _lib.load().jvmc_i8_set_debug(a.dbg)
+    _lib.load().jvmc_i8_set_debug(a.dbg | (a.max_stages << 12))
 dev = "cuda:0"
 rng = np.random.default_rng(0)
 s = torch.as_tensor(rng.integers(0, 2, (a.B, a.N)).astype(np.int32)).to(dev)

@@ -48,7 +48,11 @@ for dbg in [int(x) for x in a.dbg.split(",")]:
     torch.cuda.synchronize()
     lib.jvmc_i8_set_trace(None, 0)
     st = (a.B + 31) // 32
-    t = buf.cpu().numpy().reshape(832, 16)[:st].astype(np.float64)
+    full = buf.cpu().numpy().reshape(832, 16).astype(np.float64)
+    t = full[:st]
+    c = full[831]
+    print("   CTA phases (clk): set-up %.0f | stage loop %.0f | last commit -> accumulators complete %.0f | epilogue %.0f | "
+          "exit barriers %.0f | total %.0f" % (c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3], c[5] - c[4], c[5] - c[0]))
     res["dbg%d" % dbg] = t
     med = lambda x: float(np.median(x))
     g = np.arange(10, st - 2)

@@ -150,6 +150,6 @@ def call(name, *args):
     rc = getattr(lib, name)(*args, stream())
     check(rc, name)
     if name == "jvmc_rbm_gram_S_i8":
-        LAUNCHES += max(1, ((int(args[2]) + 31) // 32 + 831) // 832)    # one launch per <= 26624 samples
+        LAUNCHES += 3 * max(1, ((int(args[2]) + 31) // 32 + 799) // 800)    # per <= 25600 samples: column sums, correction, Gram
     else:
         LAUNCHES += _KERNELS_PER_CALL.get(name, 1)

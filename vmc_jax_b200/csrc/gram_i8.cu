@@ -6,27 +6,33 @@
 //   A[(r,j),(r',l)] = alpha sum_n s_n conj(Y_nj) Y_nl - kappa conj(mu_rj) mu_r'l ,   s_n = sigma_nr sigma_nr'
 //
 // 1. jvmc_i8_slice: every real column z of Z = [Re Y_j, Im Y_j] (interleaved, 2M columns) gets the scale
-//    c_z = 2 max_n |Z_nz| (1 + 2^-30) and each entry is split into 5 balanced base-255 digits, Z_nz = c_z sum_k d_k 255^-k,
-//    d_k in [-127, 127] (int8, symmetric so that negation is exact).  Digits are stored in the K-major SWIZZLE_NONE
-//    UMMA canonical layout [n/32][digit][z/8][(n/16)%2][z%8][n%16], so that a (tile, 32-sample stage, digit) is one
-//    contiguous block (one TMA bulk copy each).
+//    c_z = 2 max_n |Z_nz| (1 + 1/128) and each entry is split into 5 base-256 digits, TWICE:
+//      B encoding (column operand, never negated): Z_nz = c_z sum_k b_k 256^-k,        b_k in [-128, 127] integers;
+//      A encoding (row operand, gets the signs):   Z_nz = c_z sum_k (a_k + 1/2) 256^-k, a_k in [-128, 127], i.e.
+//      half-integer digits -127.5 .. 127.5: the negative of the digit stored as byte a is stored as ~a (one's
+//      complement), so applying s_n = -1 to 4 samples of a row is ONE xor of a 32-bit word with a byte mask -- no
+//      carries, no SWAR arithmetic (the two's-complement digits of round 1 needed ~6 ALU instructions per word and
+//      made the eight sign warps, not the tensor pipe, the bottleneck: tools/gram_trace.py).
+//    Both are exact to 2^-41 of the column scale.  Digits are stored in the K-major SWIZZLE_NONE UMMA canonical layout
+//    [n/32][digit][z/8][(n/16)%2][z%8][n%16], so that a (tile, 32-sample stage, digit) is one contiguous block (one TMA
+//    bulk copy each).  Padding samples are all-zero bytes in both encodings (a' = 0, b = 0: no contribution).
 // 2. gram_s_i8_kernel: CTA = (site pair r<=r', tile): 128 real rows (64 complex j) x NC <= 80 real columns (the tile list
 //    comes from the host: kernels.py:i8_tile_list; tiles that end at the diagonal are narrower).  Clusters of two CTAs
 //    work on consecutive site pairs of the same tile and share every operand copy by TMA multicast.  Per 32-sample
 //    stage the producer warp bulk-copies (TMA engine) the 5 A-digit and 5 B-digit tiles into an mbarrier-guarded
-//    6-slot smem ring; eight "sign" warps apply s_n to the A digits (byte-wise SWAR negation in registers) and store
-//    them into a double-buffered TMEM A operand (tcgen05.st); one thread issues 7 tcgen05.mma kind::i8 (M=128,
-//    N = NC n, K=32; SASS UTCIMMA; A from TMEM, B from smem): digit pair (k,k') accumulates exactly in int32 into the
-//    TMEM accumulator of level t = k+k', and because the B digit tiles are contiguous in smem and the level
+//    6-slot smem ring; eight "sign" warps xor the A digits with the byte masks of s_n (256-entry lookup table in shared
+//    memory) and store them into a double-buffered TMEM A operand (tcgen05.st); warp 1 issues 7 tcgen05.mma kind::i8
+//    (M=128, N = NC n, K=32; SASS UTCIMMA; A from TMEM, B from smem): digit pair (k,k') accumulates exactly in int32 into
+//    the TMEM accumulator of level t = k+k', and because the B digit tiles are contiguous in smem and the level
 //    accumulators adjacent TMEM column blocks, ONE instruction covers n consecutive digit pairs (5 levels x 80 columns
 //    + 2 x 40 A-operand columns = 480 of the 512 TMEM columns).
-//    One launch covers at most 26624 samples (int32 head-room); at its end four epilogue warps read TMEM
-//    (tcgen05.ld), weight level t by 255^-t in fp64, combine real/imag parts with a lane shuffle, apply scales, alpha
-//    and the mean correction and scatter the Hermitian images (later launches add into A).
-//    Dropped digit pairs (k+k' > 6) are below 4 * 255^-7 = 6e-17 of c_z c_z'; the splitting itself is exact to
-//    255^-5 = 9e-13 of the column scale.
-//    Compile-time knobs for experiments: JVMC_I8_TN (full tile width), JVMC_I8_NB (TMEM A buffers),
-//    JVMC_I8_SIGNWARPS (8 or 4).
+//    sum_n s_n (a_n + 1/2) b_n = sum_n a'_n b_n + 1/2 sum_n b_n: the second term does not depend on the site pair; it is
+//    formed once per launch from the column sums of the B digits (i8_colsum / i8_corr kernels) and added per level in
+//    the epilogue.  One launch covers at most 25600 samples (int32 head-room 5 * 128^2 * 25600 < 2^31); at its end four
+//    epilogue warps read TMEM (tcgen05.ld), weight level t by 256^-t in fp64, combine real/imag parts with a lane
+//    shuffle, apply scales, alpha and the mean correction and scatter the Hermitian images (later launches add into A).
+//    Dropped digit pairs (k+k' > 6) are below 4 * 256^-5 / 4 of c_z c_z' per sample.
+//    Compile-time knobs for experiments: JVMC_I8_TN (full tile width), JVMC_I8_NB (TMEM A buffers).
 #include "common.cuh"
 
 namespace {
@@ -51,7 +57,8 @@ constexpr int I8_SLOTS = 6;
 constexpr int I8_A_BYTES = I8_TM * I8_KS;   // per digit
 constexpr int I8_B_BYTES = I8_TN * I8_KS;
 constexpr int I8_STAGE_BYTES = I8_S * (I8_A_BYTES + I8_B_BYTES);
-constexpr int I8_MAXSTAGES = 832;       // stages per launch: 832*32*5*127^2 < 2^31 (int32 head-room in TMEM)
+constexpr int I8_MAXSTAGES = 800;       // stages per launch: 800*32*5*128^2 < 2^31 (int32 head-room in TMEM)
+constexpr int I8_DEFAULT_STAGES = 800;  // default: as many as the head-room allows (see jvmc_rbm_gram_S_i8)
 constexpr int I8_THREADS = 64 + 32 * I8_SW;   // warp 0 producer, 1 MMA issuer, then the sign warps (2-5 also epilogue)
 constexpr int I8_ACOL = I8_LEV * I8_TN;   // first TMEM column of the A operand buffers (I8_NB x 5 digits x 8 columns)
 static_assert(I8_LEV * JVMC_I8_TN + JVMC_I8_NB * 5 * 8 <= 512, "TMEM columns");
@@ -76,6 +83,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "bra.uni WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// non-blocking probe (the potentially-blocking try_wait costs ~150-200 cycles even when the phase completed long ago)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
@@ -160,13 +178,13 @@ __global__ void i8_colmax_kernel(const cplx* __restrict__ Y, long long B, int M,
   atomicMax(colmax + 2 * j + 1, (unsigned long long)__double_as_longlong(mi));
 }
 
-// scale[z] = 2 max_n |Z_nz| (1 + 2^-30), so that |Z/scale| < 1/2 and the leading digit uses its whole range
-// (a power-of-two scale would waste up to one bit); 1 for empty columns
+// scale[z] = 2 max_n |Z_nz| (1 + 1/128): |Z/scale| <= 0.4962 keeps both digit encodings inside [-128, 127] (the
+// half-integer encoding is shifted by (256^5 - 1)/510 ~ 0.002 * 256^5); 1 for empty columns
 __global__ void i8_scale_kernel(const unsigned long long* __restrict__ colmax, int twoM, double* __restrict__ scale) {
   const int z = blockIdx.x * blockDim.x + threadIdx.x;
   if (z >= twoM) return;
   double m = __longlong_as_double((long long)colmax[z]);
-  scale[z] = (m > 0.0) ? 2.0 * m * (1.0 + 9.313225746154785e-10) : 1.0;
+  scale[z] = (m > 0.0) ? 2.0 * m * (1.0 + 0.0078125) : 1.0;
 }
 
 // Heavy-tail diagnostic: per real column sum_n Z_nz^2 and max_n |Z_nz| (scratch zeroed by the caller), then
@@ -197,37 +215,80 @@ __global__ void i8_tail_ratio_kernel(const double* __restrict__ colsq, const uns
   ratio[z] = ms > 0.0 ? __longlong_as_double((long long)colmax[z]) / sqrt(ms) : 0.0;
 }
 
-// one thread per (16-sample chunk, real column z): 16 strided loads, 5 x 16 B stores
+// one thread per (16-sample chunk, real column z): 16 strided loads, 2 x 5 x 16 B stores (A and B encodings)
 __global__ void __launch_bounds__(256)
 i8_slice_kernel(const cplx* __restrict__ Y, long long B, int M, const double* __restrict__ scale, long long numChunks,
-                int numZGroups, int8_t* __restrict__ dig) {
+                int numZGroups, int8_t* __restrict__ digA, int8_t* __restrict__ digB) {
   const int z = blockIdx.x * blockDim.x + threadIdx.x;     // fastest: coalesced over columns
   const long long ch = blockIdx.y;
   if (z >= 2 * M) return;
   const double inv = 1.0 / scale[z];
   const double* Yd = reinterpret_cast<const double*>(Y);
-  int8_t d[I8_S][16];
+  int8_t da[I8_S][16], db[I8_S][16];
   for (int q = 0; q < 16; ++q) {
     const long long n = ch * 16 + q;
-    double x = (n < B) ? Yd[n * 2 * M + z] * inv : 0.0;
-    long long X = llrint(x * 1078203909375.0);             // 255^5
+    if (n < B) {
+      const double X = Yd[n * 2 * M + z] * inv * 1099511627776.0;     // 256^5 = 2^40: exact scaling
+      long long NB = llrint(X);                                      // integer digits
+      long long NA = llrint(X - 2155905152.5);                       // half-integer digits: minus (256^5 - 1) / 510
 #pragma unroll
-    for (int k = I8_S - 1; k >= 0; --k) {
-      long long qd = (X >= 0) ? (X + 127) / 255 : -((-X + 127) / 255);   // round(X / 255), remainder in [-127,127]
-      d[k][q] = (int8_t)(X - qd * 255);
-      X = qd;
+      for (int k = I8_S - 1; k >= 0; --k) {
+        const int8_t b8 = (int8_t)(NB & 0xFF), a8 = (int8_t)(NA & 0xFF);   // balanced remainders in [-128, 127]
+        db[k][q] = b8; da[k][q] = a8;
+        NB = (NB - b8) >> 8; NA = (NA - a8) >> 8;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < I8_S; ++k) { da[k][q] = 0; db[k][q] = 0; }  // padding sample: contributes nothing
     }
   }
   // [stage][digit][zgroup][chunk of the stage][z%8][n%16]: a (tile, stage, digit) is one contiguous block
   const size_t off = ((size_t)(z >> 3) * 2 + (size_t)(ch & 1)) * 128 + (size_t)(z & 7) * 16;
 #pragma unroll
-  for (int k = 0; k < I8_S; ++k)
-    *reinterpret_cast<int4*>(dig + ((size_t)(ch >> 1) * I8_S + k) * numZGroups * 256 + off) = *reinterpret_cast<const int4*>(d[k]);
+  for (int k = 0; k < I8_S; ++k) {
+    const size_t o = ((size_t)(ch >> 1) * I8_S + k) * numZGroups * 256 + off;
+    *reinterpret_cast<int4*>(digA + o) = *reinterpret_cast<const int4*>(da[k]);
+    *reinterpret_cast<int4*>(digB + o) = *reinterpret_cast<const int4*>(db[k]);
+  }
+}
+
+// SB[k][z] += sum over the samples of stages [stage0, stage1) of the B digit k of column z (exact, int32):
+// thread = (digit, column), blockIdx.y = slice of 32 stages
+__global__ void i8_colsum_kernel(const int8_t* __restrict__ digB, int numZGroups, long long stage0, long long stage1,
+                                 int* __restrict__ SB) {
+  const int ZP = numZGroups * 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= I8_S * ZP) return;
+  const int k = idx / ZP, z = idx - k * ZP;
+  const long long s0 = stage0 + (long long)blockIdx.y * 32, s1 = min(stage1, s0 + 32);
+  int acc = 0;
+  for (long long st = s0; st < s1; ++st) {
+    const int8_t* p = digB + ((size_t)st * I8_S + k) * numZGroups * 256 + (size_t)(z >> 3) * 256 + (size_t)(z & 7) * 16;
+#pragma unroll
+    for (int chunk = 0; chunk < 2; ++chunk) {
+      const int4 v = *reinterpret_cast<const int4*>(p + chunk * 128);
+      acc = __dp4a(v.x, 0x01010101, acc); acc = __dp4a(v.y, 0x01010101, acc);
+      acc = __dp4a(v.z, 0x01010101, acc); acc = __dp4a(v.w, 0x01010101, acc);
+    }
+  }
+  if (acc) atomicAdd(SB + idx, acc);
+}
+// corr[t][z] = 1/2 sum_{k' : 1 <= t - k' <= 5} SB[k'][z], levels t = 2..6 (digits k' = 1..5)
+__global__ void i8_corr_kernel(const int* __restrict__ SB, int ZP, double* __restrict__ corr) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= I8_LEV * ZP) return;
+  const int t = idx / ZP + 2, z = idx - (t - 2) * ZP;
+  long long acc = 0;
+  for (int kp = 1; kp <= I8_S; ++kp)
+    if (t - kp >= 1 && t - kp <= I8_S) acc += SB[(kp - 1) * ZP + z];
+  corr[idx] = 0.5 * (double)acc;
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
 struct I8Args {
-  const int8_t* dig;
+  const int8_t* dig;       // A encoding (half-integer digits)
+  const int8_t* digB;      // B encoding (integer digits)
+  const double* corr;      // [5 levels][numZGroups * 8]: 1/2 sum_n b_n per level and column, this launch's samples
   long long numChunks;     // 16-sample chunks (even)
   int numZGroups;          // padded real columns / 8
   const double* scale;     // [2M]
@@ -249,6 +310,9 @@ struct I8Args {
   int traceTile;
 };
 #define I8_TRACE(ev) do { if (tracing) a.trace[(size_t)g * 16 + (ev)] = clock64(); } while (0)
+// CTA-level phases go to the row of (unused) stage 831: 0 entry, 1 set-up done, 2 last MMA committed, 3 accumulators
+// complete (seen by the epilogue), 4 epilogue done, 5 after the final CTA / cluster barriers
+#define I8_TRACE_CTA(ev) do { if (tracing) a.trace[(size_t)831 * 16 + (ev)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -260,6 +324,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   uint64_t* afree = aready + I8_NB;         // [NB] MMAs reading TMEM buffer b retired
   uint64_t* accfull = afree + I8_NB;
   uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(accfull + 1);
+  uint2* lut = reinterpret_cast<uint2*>(bars + 32);       // [256] sign bits of 8 samples -> two words of byte masks
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // The CTAs of a cluster work on consecutive site pairs of the SAME tile: the raw digit tiles are identical for
@@ -277,12 +342,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   const unsigned bBytes = (unsigned)(NC * I8_KS);       // bytes of one B digit tile of a stage
   const long long numStages = a.stage1 - a.stage0;
   const bool tracing = a.trace != nullptr && blockIdx.x == 0 && (int)blockIdx.y == a.traceTile && lane == 0;
+  if (warp == 2) I8_TRACE_CTA(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < I8_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, (unsigned)a.cl); }
-    for (int b = 0; b < I8_NB; ++b) { mbar_init(aready + b, I8_SW); mbar_init(afree + b, 1); }
+    for (int b = 0; b < I8_NB; ++b) { mbar_init(aready + b, I8_SW / 2); mbar_init(afree + b, 1); }   // 4 warps per buffer
     mbar_init(accfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (threadIdx.x >= 64) {
+    for (unsigned v = threadIdx.x - 64; v < 256; v += I8_THREADS - 64) {
+      const unsigned lo = v & 0xFu, hi = v >> 4;
+      lut[v] = make_uint2(((lo * 0x00204081u) & 0x01010101u) * 0xFFu, ((hi * 0x00204081u) & 0x01010101u) * 0xFFu);
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_base_p)));
@@ -293,6 +365,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   if (a.cl > 1) cluster_sync_all();   // peers' barriers are initialised before anything is multicast to them
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = *tmem_base_p;
+  if (warp == 2) I8_TRACE_CTA(1);
 
   if (warp == 0) {
     // ===================== producer: one bulk copy per (operand, digit) and stage =====================
@@ -306,7 +379,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         const int k = lane >> 1, which = lane & 1;
         const size_t base = ((size_t)(a.stage0 + g) * I8_S + k) * a.numZGroups;
         unsigned char* dst = which == 0 ? st + k * I8_A_BYTES : st + I8_S * I8_A_BYTES + k * bBytes;   // B digits packed
-        const int8_t* src = a.dig + (base + (which == 0 ? (size_t)RG : (size_t)CG)) * 256;
+        const int8_t* src = (which == 0 ? a.dig + (base + (size_t)RG) * 256 : a.digB + (base + (size_t)CG) * 256);
         const unsigned bytes = which == 0 ? (unsigned)I8_A_BYTES : bBytes;
         if (a.cl == 1) bulk_g2s(dst, src, bytes, full + slot);
         else if ((unsigned)lane % (unsigned)a.cl == crank) bulk_g2s_mc(dst, src, bytes, full + slot, cmask);   // my share
@@ -337,8 +410,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       const uint32_t ring0 = smem_u32(ring) + I8_S * I8_A_BYTES;
       const uint32_t bStep = (NCu * (uint32_t)I8_KS) >> 4;       // one B digit tile in 16-byte units
       auto wait_stage = [&](uint32_t sl, uint32_t fp, uint32_t bb, uint32_t bp) {
-        if (useFull) mbar_wait(full + sl, fp);
-        if (useReady) mbar_wait(aready + bb, bp);
+        if (useFull && !mbar_test(full + sl, fp)) mbar_wait(full + sl, fp);
+        if (useReady && !mbar_test(aready + bb, bp)) mbar_wait(aready + bb, bp);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       };
       if (numStages > 0) wait_stage(0u, 0u, 0u, 0u);
@@ -387,60 +460,61 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         I8_TRACE(3);
         slot = nslot; fullPar = nfullPar; b = nb;
       }
+      I8_TRACE_CTA(2);
     }
   } else {
     // ===================== sign warps: A_k <- s_n * A_k, smem -> registers -> TMEM =====================
-    // thread = tile row; per digit the row's 32 sample bytes are two 16-byte units of the canonical layout.
-    // Byte-wise two's-complement negate where s_n = -1, SWAR on 32-bit words: -x = (x ^ 0xFF) + 1 per byte.
+    // thread = tile row; per digit the row's 32 sample bytes are two 16-byte units of the canonical layout.  The digits
+    // are half-integers stored in one's complement: the sign is one xor with the byte mask of the stage's sign bits.
+    // Warps 2-5 serve the even stages (TMEM buffer 0), warps 6-9 the odd ones (buffer 1), one lane quarter each and all
+    // five digits: a warp's chain per stage (poll `full`, shared-memory loads, poll `afree`, TMEM store, arrive) is
+    // latency- not throughput-bound (~800 cycles, trace), so every warp gets two stage periods for it.
     const int ew = warp & 3;                              // TMEM lane quarter this warp may access
     const int row = ew * 32 + lane;                       // real row of the tile (z = 8 RG + row)
     {
-      const uint32_t* sg0 = a.sigT + (size_t)r0 * a.words;
-      const uint32_t* sg1 = a.sigT + (size_t)r1 * a.words;
-      uint32_t xn = (numStages > 0) ? (sg0[a.stage0] ^ sg1[a.stage0]) : 0u;
-      const size_t rowOff = (size_t)(row >> 3) * 256 + (size_t)(row & 7) * 16;
-      for (long long g = 0; g < ((a.dbg & 3) ? 0 : numStages); ++g) {
-        const int slot = (int)(g % I8_SLOTS);
-        const int b = (int)(g % I8_NB);
+      static_assert(I8_NB == 2 && I8_SW == 8, "sign warps: two groups of four, one TMEM A buffer each");
+      const uint32_t grp = (uint32_t)(warp - 2) >> 2;     // 0: even stages, 1: odd stages; also the TMEM buffer
+      const uint32_t* sg0 = a.sigT + (size_t)r0 * a.words + a.stage0;
+      const uint32_t* sg1 = a.sigT + (size_t)r1 * a.words + a.stage0;
+      const uint32_t rowOff = (uint32_t)(row >> 3) * 256u + (uint32_t)(row & 7) * 16u;
+      const unsigned char* aBase = ring + rowOff;
+      const uint32_t tBase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(I8_ACOL + grp * (I8_S * 8));
+      const long long nSign = (a.dbg & 3) ? 0 : numStages;
+      uint32_t xn = (grp < nSign) ? (sg0[grp] ^ sg1[grp]) : 0u;
+      uint32_t slot = grp, fullPar = 0, freePar = 0;
+      for (long long g = grp; g < nSign; g += 2) {
         const uint32_t x = xn;                              // bit = 1 -> s_n = -1 (32 samples of the stage)
-        if (g + 1 < numStages) xn = sg0[a.stage0 + g + 1] ^ sg1[a.stage0 + g + 1];
+        if (g + 2 < numStages) xn = sg0[g + 2] ^ sg1[g + 2];
         uint32_t msk[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const uint32_t nib = (x >> (4 * q)) & 0xFu;
-          msk[q] = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;     // nibble bits -> 0x00/0xFF byte masks
+        for (int q = 0; q < 4; ++q) {
+          const uint2 m = lut[(x >> (8 * q)) & 0xFFu];
+          msk[2 * q] = m.x; msk[2 * q + 1] = m.y;
         }
         // The signed digits are prepared in registers BEFORE waiting for the TMEM buffer, so that only the
         // TMEM store sits on the MMA(g-2) -> sign(g) -> MMA(g) dependency chain.
-        mbar_wait(full + slot, (unsigned)((g / I8_SLOTS) & 1));
+        mbar_wait(full + slot, fullPar);
         if (warp == 2) I8_TRACE(4);
-        const unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
-        // two warps share a TMEM lane quarter: warps 2-5 take digits 0-2, warps 6-9 digits 3-4
-        const int kbeg = (warp < 6) ? 0 : 3, nk = (I8_SW == 4) ? I8_S : ((warp < 6) ? 3 : 2);
-        uint32_t w[I8_KW][8];
+        const unsigned char* st = aBase + slot * (uint32_t)I8_STAGE_BYTES;
+        uint32_t w[I8_S][8];
 #pragma unroll
-        for (int k = 0; k < I8_KW; ++k) {
-          if (k >= nk) continue;
+        for (int k = 0; k < I8_S; ++k) {
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
             const uint4 v = (a.dbg & 32) ? make_uint4(0u, 0u, 0u, 0u)
-                                         : *reinterpret_cast<const uint4*>(st + (kbeg + k) * I8_A_BYTES + ch * 128 + rowOff);
-            w[k][ch * 4 + 0] = v.x; w[k][ch * 4 + 1] = v.y; w[k][ch * 4 + 2] = v.z; w[k][ch * 4 + 3] = v.w;
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint32_t aa = w[k][q] ^ msk[q];
-            if (!(a.dbg & 64)) w[k][q] = ((aa & 0x7F7F7F7Fu) + (msk[q] & 0x01010101u)) ^ (aa & 0x80808080u);
+                                         : *reinterpret_cast<const uint4*>(st + k * I8_A_BYTES + ch * 128);
+            w[k][ch * 4 + 0] = v.x ^ msk[ch * 4 + 0]; w[k][ch * 4 + 1] = v.y ^ msk[ch * 4 + 1];
+            w[k][ch * 4 + 2] = v.z ^ msk[ch * 4 + 2]; w[k][ch * 4 + 3] = v.w ^ msk[ch * 4 + 3];
           }
         }
         if (warp == 2) I8_TRACE(5);
-        if (g >= I8_NB) mbar_wait(afree + b, (unsigned)((g / I8_NB - 1) & 1));
+        if (g >= I8_NB) { mbar_wait(afree + grp, freePar); freePar ^= 1u; }
         if (warp == 2) I8_TRACE(6);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < I8_KW; ++k) {
-          if (k >= nk || (a.dbg & 4)) continue;
-          const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(I8_ACOL + b * I8_S * 8 + (kbeg + k) * 8);
+        for (int k = 0; k < I8_S; ++k) {
+          if (a.dbg & 4) continue;
+          const uint32_t taddr = tBase + (uint32_t)(k * 8);
           asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr),
                        "r"(w[k][0]), "r"(w[k][1]), "r"(w[k][2]), "r"(w[k][3]), "r"(w[k][4]), "r"(w[k][5]), "r"(w[k][6]),
                        "r"(w[k][7]) : "memory");
@@ -449,21 +523,56 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         if (warp == 2) I8_TRACE(7);
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(aready + b);
+        if (lane == 0) mbar_arrive(aready + grp);
+        slot += 2;
+        if (slot >= I8_SLOTS) { slot -= I8_SLOTS; fullPar ^= 1u; }
       }
     }
     if (warp < 6) {
     // ===================== epilogue (warps 2-5): TMEM -> fp64, combine re/im, scale, scatter =====================
-    const double wl[I8_LEV] = {1.0 / 65025.0, 1.0 / 16581375.0, 1.0 / 4228250625.0, 1.0 / 1078203909375.0,
-                               1.0 / 274941996890625.0};   // 255^-t, t = 2..6
+    // Everything the inner loop needs per column (scales, means, level corrections) is staged in shared memory (the
+    // operand ring is free once the accumulators are complete) and the row-side values sit in registers; later
+    // launches add into A with fire-and-forget reductions (RED.ADD.F64) instead of load-add-store round trips -- the
+    // first version of this epilogue was a chain of dependent L2 accesses, ~44 000 cycles = 8 % of a CTA (trace).
+    const double wl[I8_LEV] = {1.0 / 65536.0, 1.0 / 16777216.0, 1.0 / 4294967296.0, 1.0 / 1099511627776.0,
+                               1.0 / 281474976710656.0};   // 256^-t, t = 2..6
+    const int ZP = a.numZGroups * 8;
     const int zrow = RG * 8 + row;
     const int j = zrow >> 1;                              // complex row index; lane parity = re/im part
     const bool isIm = (zrow & 1) != 0;
-    const double srow = (j < a.M) ? a.scale[zrow] : 0.0;
+    const bool jok = j < a.M;
+    const double srow = jok ? a.scale[zrow] : 0.0;
     const long long Pc = (long long)a.R * a.M;
     const bool samePair = (r0 == r1);
+    const bool useMu = a.mu != nullptr && !a.accumulate;
+    const cplx m0j = (useMu && jok) ? a.mu[(long long)r0 * a.M + j] : cmk(0.0, 0.0);
+    const cplx m1j = (useMu && jok) ? a.mu[(long long)r1 * a.M + j] : cmk(0.0, 0.0);
     mbar_wait(accfull, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (warp == 2) I8_TRACE_CTA(3);
+    double* stg = reinterpret_cast<double*>(ring);        // [80] column scales | [40] mu(r0,l) | [40] mu(r1,l) | [5][80] corr
+    double* sSc = stg;
+    cplx* sMu0 = reinterpret_cast<cplx*>(stg + I8_TN);
+    cplx* sMu1 = sMu0 + I8_TN / 2;
+    double* sCorr = stg + I8_TN + 2 * I8_TN;
+    {
+      const int et = (warp - 2) * 32 + lane;              // 0..127
+      for (int c = et; c < I8_TN; c += 128) {
+        const int zc = CG * 8 + c;
+        sSc[c] = (c < NC && (zc >> 1) < a.M) ? a.scale[zc] : 0.0;
+      }
+      for (int i = et; i < I8_TN; i += 128) {              // first half: mu(r0, l), second half: mu(r1, l)
+        const int which = i >= I8_TN / 2, li = which ? i - I8_TN / 2 : i;
+        const int l = CG * 4 + li;
+        const cplx m = (useMu && li < NC / 2 && l < a.M) ? a.mu[(long long)(which ? r1 : r0) * a.M + l] : cmk(0.0, 0.0);
+        (which ? sMu1 : sMu0)[li] = m;
+      }
+      for (int i = et; i < I8_LEV * I8_TN; i += 128) {
+        const int t = i / I8_TN, c = i - t * I8_TN;
+        sCorr[i] = (c < NC) ? a.corr[(size_t)t * ZP + CG * 8 + c] : 0.0;
+      }
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    }
     for (int cb = 0; cb < NC / 16; ++cb) {
       double v[16];
 #pragma unroll
@@ -479,56 +588,60 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = fma((double)(int32_t)r[c], wl[t], v[c]);
+        for (int c = 0; c < 16; ++c)   // + 1/2 sum_n b_n of the level: the half of the half-integer A digits
+          v[c] = fma((double)(int32_t)r[c] + sCorr[t * I8_TN + cb * 16 + c], wl[t], v[c]);
       }
       // C[zrow][zcol] with both column scales; the partner lane (lane ^ 1) holds the other part of the same j
 #pragma unroll
       for (int cc = 0; cc < 8; ++cc) {
-        const int l = CG * 4 + cb * 8 + cc;
-        const bool lok = l < a.M;
-        const double c0 = lok ? v[2 * cc] * srow * a.scale[2 * l] : 0.0;          // column Re Y_l
-        const double c1 = lok ? v[2 * cc + 1] * srow * a.scale[2 * l + 1] : 0.0;  // column Im Y_l
-        const double p0 = __shfl_xor_sync(0xffffffffu, c0, 1);
+        const int li = cb * 8 + cc;
+        const int l = CG * 4 + li;
+        const double c0 = v[2 * cc] * srow * sSc[2 * li];              // column Re Y_l (scale 0 beyond M)
+        const double c1 = v[2 * cc + 1] * srow * sSc[2 * li + 1];      // column Im Y_l
         const double p1 = __shfl_xor_sync(0xffffffffu, c1, 1);
         // even lane (Re row): Re G = C[2j][2l] + C[2j+1][2l+1] = c0 + p1 ; odd lane (Im row): Im G = C[2j][2l+1] - C[2j+1][2l] = p1 - c0
-        (void)p0;
         const double part = isIm ? (p1 - c0) : (c0 + p1);
         const double other = __shfl_xor_sync(0xffffffffu, part, 1);   // even lane receives Im G
-        if (!lok || j >= a.M || j < jlo || j >= jhi || l > j || isIm || padCta) continue;
+        if (l >= a.M || !jok || j < jlo || j >= jhi || l > j || isIm || padCta) continue;
         const double gr = a.alpha * part;
         const double gi = (l == j) ? 0.0 : a.alpha * other;
         const long long a0 = (long long)r0 * a.M + j, b1 = (long long)r1 * a.M + l;
-        cplx v0 = cmk(gr, gi);
+        cplx* pA = a.A + a0 * Pc + b1;
+        cplx* pAt = a.A + b1 * Pc + a0;
+        const bool diagEl = samePair && l == j;
         if (!a.accumulate) {
-          cplx m0j = a.mu ? a.mu[a0] : cmk(0.0, 0.0);
-          cplx m1l = a.mu ? a.mu[b1] : cmk(0.0, 0.0);
-          v0 = cmk(gr - a.kappa * (m0j.x * m1l.x + m0j.y * m1l.y), gi - a.kappa * (m0j.x * m1l.y - m0j.y * m1l.x));
+          const cplx m1l = sMu1[li];
+          const cplx v0 = cmk(gr - a.kappa * (m0j.x * m1l.x + m0j.y * m1l.y),
+                              diagEl ? 0.0 : gi - a.kappa * (m0j.x * m1l.y - m0j.y * m1l.x));
+          *pA = v0;
+          if (!diagEl) *pAt = cconj(v0);
         } else {
-          v0 = cadd(v0, a.A[a0 * Pc + b1]);
+          atomicAdd(&pA->x, gr);
+          if (!diagEl) { atomicAdd(&pA->y, gi); atomicAdd(&pAt->x, gr); atomicAdd(&pAt->y, -gi); }
         }
-        if (samePair && l == j) v0.y = 0.0;
-        a.A[a0 * Pc + b1] = v0;
-        if (!(samePair && l == j)) a.A[b1 * Pc + a0] = cconj(v0);
         if (!samePair && l != j) {
           const long long a1 = (long long)r1 * a.M + j, b0 = (long long)r0 * a.M + l;
-          cplx w0 = cmk(gr, gi);
+          cplx* qA = a.A + a1 * Pc + b0;
+          cplx* qAt = a.A + b0 * Pc + a1;
           if (!a.accumulate) {
-            cplx m1j = a.mu ? a.mu[a1] : cmk(0.0, 0.0);
-            cplx m0l = a.mu ? a.mu[b0] : cmk(0.0, 0.0);
-            w0 = cmk(gr - a.kappa * (m1j.x * m0l.x + m1j.y * m0l.y), gi - a.kappa * (m1j.x * m0l.y - m1j.y * m0l.x));
+            const cplx m0l = sMu0[li];
+            const cplx w0 = cmk(gr - a.kappa * (m1j.x * m0l.x + m1j.y * m0l.y), gi - a.kappa * (m1j.x * m0l.y - m1j.y * m0l.x));
+            *qA = w0;
+            *qAt = cconj(w0);
           } else {
-            w0 = cadd(w0, a.A[a1 * Pc + b0]);
+            atomicAdd(&qA->x, gr); atomicAdd(&qA->y, gi);
+            atomicAdd(&qAt->x, gr); atomicAdd(&qAt->y, -gi);
           }
-          a.A[a1 * Pc + b0] = w0;
-          a.A[b0 * Pc + a1] = cconj(w0);
         }
       }
     }
     }
   }
+  if (warp == 2) I8_TRACE_CTA(4);
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   if (a.cl > 1) cluster_sync_all();   // no peer may still signal this CTA's barriers when it exits
+  if (warp == 2) I8_TRACE_CTA(5);
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem));
 }
 
@@ -536,6 +649,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
 
 static int g_i8_dbg = 0;
 static int g_i8_cluster = 2;
+static int g_i8_max_stages = 0;   // development: stages per launch (0: I8_MAXSTAGES, the int32 head-room)
 static long long* g_i8_trace = nullptr;
 static int g_i8_trace_tile = 0;
 // development: device buffer of 16 * 832 int64 that receives the clock64 time stamps of CTA (pair 0, tile `tile`) of the
@@ -551,6 +665,8 @@ extern "C" int jvmc_i8_set_debug(int flags) {
   g_i8_dbg = flags & 0xFF;
   const int cl = (flags >> 8) & 0xF;
   if (cl == 1 || cl == 2 || cl == 4 || cl == 8) g_i8_cluster = cl;
+  const int ms = (flags >> 12) & 0xFFF;             // bits 12-23: stages per launch (L2 footprint experiments)
+  g_i8_max_stages = (ms > 0 && ms <= I8_MAXSTAGES) ? ms : 0;
   return JVMC_OK;
 }
 
@@ -571,9 +687,12 @@ extern "C" int jvmc_i8_layout(long long B, int M, long long* numChunks, int* num
   int padA = ((twoM + I8_TM - 1) / I8_TM) * I8_TM, padB = ((twoM + I8_TN - 1) / I8_TN) * I8_TN;
   int pad = padA > padB ? padA : padB;
   *numZGroups = pad / 8;
-  *digitBytes = (long long)I8_S * (*numChunks) * (*numZGroups) * 128;
+  // [A encoding | B encoding | scratch of the column-sum correction: int32 SB[5][ZP], double corr[5][ZP] (+ alignment)]
+  const long long half = (long long)I8_S * (*numChunks) * (*numZGroups) * 128;
+  *digitBytes = 2 * half + (long long)I8_S * pad * 4 + (long long)I8_LEV * pad * 8 + 256;
   return JVMC_OK;
 }
+static long long i8_half_bytes(long long numChunks, int numZGroups) { return (long long)I8_S * numChunks * numZGroups * 128; }
 
 // ratios[z] <- max_n|Z_nz| / rms_n(Z_nz) for the 2M real columns Z = [Re Y_j, Im Y_j] (interleaved).  scratch: 4M doubles.
 extern "C" int jvmc_i8_tail_ratios(const double* Y, long long B, int M, double* scratch, double* ratios, void* stream) {
@@ -604,7 +723,8 @@ extern "C" int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long 
   i8_scale_kernel<<<(2 * M + 255) / 256, 256, 0, st>>>(colmax, 2 * M, scale);
   JVMC_CHECK_LAUNCH();
   dim3 g2((2 * M + 255) / 256, (unsigned)((B + 15) / 16));
-  i8_slice_kernel<<<g2, 256, 0, st>>>((const cplx*)Y, B, M, scale, numChunks, numZGroups, (int8_t*)digits);
+  i8_slice_kernel<<<g2, 256, 0, st>>>((const cplx*)Y, B, M, scale, numChunks, numZGroups, (int8_t*)digits,
+                                      (int8_t*)digits + i8_half_bytes(numChunks, numZGroups));
   JVMC_CHECK_LAUNCH();
   return JVMC_OK;
 }
@@ -620,10 +740,16 @@ extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale
   I8Args a;
   long long digitBytes;
   jvmc_i8_layout(B, M, &a.numChunks, &a.numZGroups, &digitBytes);
-  a.dig = (const int8_t*)digits; a.scale = scale; a.sigT = sigT; a.words = (B + 31) / 32;
+  const long long half = i8_half_bytes(a.numChunks, a.numZGroups);
+  const int ZP = a.numZGroups * 8;
+  a.dig = (const int8_t*)digits; a.digB = a.dig + half;
+  int* SB = (int*)((unsigned char*)digits + 2 * half);                                   // 16-byte aligned: half % 128 == 0
+  double* corr = (double*)(((uintptr_t)(SB + (size_t)I8_S * ZP) + 255) & ~(uintptr_t)255);
+  a.corr = corr;
+  a.scale = scale; a.sigT = sigT; a.words = (B + 31) / 32;
   a.tiles = tiles; a.mu = (const cplx*)mu; a.alpha = alpha; a.kappa = kappa; a.A = (cplx*)A;
   a.M = M; a.R = R;
-  size_t smem = (size_t)I8_SLOTS * I8_STAGE_BYTES + 32 * sizeof(uint64_t);
+  size_t smem = (size_t)I8_SLOTS * I8_STAGE_BYTES + 32 * sizeof(uint64_t) + 256 * sizeof(uint2);   // ring | barriers | mask table
   cudaFuncSetAttribute(gram_s_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   long long pairs = (long long)R * (R + 1) / 2;
   if (numTiles > 65535 || pairs > 2147483647LL) return JVMC_ERR_UNSUPPORTED;
@@ -638,14 +764,22 @@ extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)a.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  // one launch per <= 26624 samples (exact int32 accumulation), evenly split; later launches add into A
-  const long long numLaunches = (numStages + I8_MAXSTAGES - 1) / I8_MAXSTAGES;
+  // one launch per <= 25600 samples (exact int32 accumulation), evenly split; later launches add into A
+  const long long maxStages = g_i8_max_stages ? g_i8_max_stages : I8_DEFAULT_STAGES;
+  const long long numLaunches = (numStages + maxStages - 1) / maxStages;
   const long long per = (numStages + numLaunches - 1) / numLaunches;
   for (long long s0 = 0; s0 < numStages; s0 += per) {
     a.stage0 = s0;
     a.stage1 = (s0 + per < numStages) ? s0 + per : numStages;
     a.accumulate = (s0 > 0) ? 1 : 0;
     a.dbg = g_i8_dbg;
+    // 1/2 sum_n b_n per level and column for the samples of this launch (the half of the half-integer A digits)
+    cudaMemsetAsync(SB, 0, sizeof(int) * (size_t)I8_S * ZP, (cudaStream_t)stream);
+    dim3 gc((unsigned)((I8_S * ZP + 127) / 128), (unsigned)((a.stage1 - a.stage0 + 31) / 32));
+    i8_colsum_kernel<<<gc, 128, 0, (cudaStream_t)stream>>>(a.digB, a.numZGroups, a.stage0, a.stage1, SB);
+    JVMC_CHECK_LAUNCH();
+    i8_corr_kernel<<<(I8_LEV * ZP + 127) / 128, 128, 0, (cudaStream_t)stream>>>(SB, ZP, corr);
+    JVMC_CHECK_LAUNCH();
     if (a.cl == 1) {
       gram_s_i8_kernel<<<grid, I8_THREADS, smem, (cudaStream_t)stream>>>(a);
       JVMC_CHECK_LAUNCH();
