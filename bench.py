@@ -510,6 +510,7 @@ def main():
                             "real Gram, executed also the padding of the 128 x 80 tiles that straddle the diagonal; "
                             "the tensor pipe waits on shared-memory bandwidth (TMA writes + sign-pass reads + UTCIMMA "
                             "B reads = 91 KB per 32-sample stage) under the board power cap, see DESIGN.md 4.2"}
+    roofline["gram_backend_last_step"] = dict(K.LAST_GRAM) if hasattr(K, "LAST_GRAM") else None
     tp = os.path.join(ROOT, "profiles", "gram_traffic.json")
     if os.path.exists(tp):
         try:

@@ -117,9 +117,13 @@ int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long long* colma
 /* Heavy-tail diagnostic behind the choice between the int8 and the fp64 DMMA Gram (kernels.py:rbm_gram_S_auto):
  * ratios[z] (device, 2M) <- max_n|Z_nz| / rms_n(Z_nz) per real column of Y.  scratch: 4M doubles (device). */
 int jvmc_i8_tail_ratios(const double* Y, long long B, int M, double* scratch, double* ratios, void* stream);
+/* flag[n] (device bytes) <- 1 where some entry of sample n exceeds T x the rms of its column (scratch of the call above):
+ * these few samples go through the exact fp64 kernel, the rest through the int8 kernel (rbm_gram_S_auto). */
+int jvmc_i8_outlier_rows(const double* Y, long long B, int M, const double* scratch, double T, unsigned char* flag,
+                         void* stream);
 int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale, long long B, int M, int R,
                        const unsigned int* sigT, const int* tiles, int numTiles, const double* mu, double alpha,
-                       double kappa, double* A, void* stream);
+                       double kappa, int accumulate, double* A, void* stream);   /* accumulate != 0: A += alpha G */
 
 /* SampledObs.tangent_kernel (jVMC/stats.py:332-336; MinSR, jVMC/util/minsr.py:59-60), Khatri-Rao form:
  * T[n,m] = scale sqrt(p_n p_m) [ (sum_r sigma_nr sigma_mr)(sum_j tau_nj conj tau_mj) - v_n - conj(v_m) + c ],
@@ -203,6 +207,24 @@ int jvmc_tdvp_solve(int n, int mode, double* S, const double* F, long long B, co
 int jvmc_minsr_solve_workspace(int n, int isComplex, long long* bytes);
 int jvmc_minsr_solve(int n, int isComplex, double* T, const double* e, double rtol, double* x, double* ev, int* info,
                      void* work, long long workBytes, void* stream);
+
+/* ---- building blocks of the Hermitian eigen-decomposition beyond cuSOLVER's dense-eigensolver limit (n <= 32768,
+ * measured), used by kernels.py:eigh_large for the config-2 TDVP solve (P_c = 40 000): one level of Cuppen's divide
+ * and conquer on the tridiagonal matrix (merge after LAPACK dlaed2/dlaed3: deflation on the host, O(n); secular equation
+ * and Gu-Eisenstat vectors on the device).  hetrd / unmtr are cuSOLVER library calls (Zhetrd/Dsytrd, Zunmtr/Dormtr). */
+int jvmc_hetrd_workspace(int n, int isComplex, long long* bytes);
+int jvmc_hetrd(int n, int isComplex, double* A, double* d, double* e, double* tau, void* work, long long bytes, int* info,
+               void* stream);
+int jvmc_unmtr_workspace(int n, int ncols, int isComplex, long long* bytes);
+int jvmc_unmtr(int n, int ncols, int isComplex, double* A, double* tau, double* C, void* work, long long bytes, int* info,
+               void* stream);
+int jvmc_tridiag_dense(int m, const double* d, const double* e, double shiftFirst, double shiftLast, double* T, void* stream);
+int jvmc_real_to_complex(long long count, const double* src, double* dst, void* stream);
+int jvmc_secular_roots(int k, const double* d, const double* z2, double rho, double z2sum, int* orig, double* mu, void* stream);
+int jvmc_secular_vectors(int k, const double* d, const double* z, double rho, const int* orig, const double* mu,
+                         const int* rowIdx, const int* colIdx, double* U, long long ldu, double* zhat, void* stream);
+int jvmc_apply_row_rotations(int ncols, long long ldu, double* U, int nrot, const int* ri, const int* rj, const double* c,
+                             const double* s, void* stream);
 
 /* ---- NCCL plumbing replacing jVMC/mpi_wrapper.py (global_sum/mean/variance/covariance :114-243, gather :278-292,
  * bcast_unknown_size :246-275) on device buffers, in-stream.  NCCL is resolved at run time (libnccl.so.2);

@@ -202,9 +202,10 @@ def check_gram_heavy_tail(N=5, M=40, B=4096, seed=31, tail=3000.0):
     """tau columns whose maximum is far above their typical size (tanh(theta) next to a pole), and a uniformly tiny one.
     The check is entry-wise, |dA_jl| <= 1e-10 sqrt(A_jj A_ll): stricter than the max|A| normalisation of
     check_moments_gram exactly where it matters (small entries of A may not hide behind a large one).  The int8 digits
-    resolve 255^-5 of the column MAXIMUM, so entries BETWEEN two heavy-tailed columns lose accuracy in this metric
-    (error ~ 0.3 * 4 * 255^-5 r_z r_z' / sqrt(B), r = max / rms); the automatic choice must route such a matrix to
-    the fp64 DMMA kernel and a benign one to the int8 kernel, both within the bar; the error model is checked too."""
+    resolve 2^-41 of the column MAXIMUM, so entries BETWEEN two heavy-tailed columns lose accuracy in this metric
+    (error ~ 0.3 * 4 * 2^-40 r_z r_z' / sqrt(B), r = max / rms); the automatic choice must send the few outlier samples of
+    such a matrix through the fp64 DMMA kernel and the bulk (and a benign matrix as a whole) through the int8 kernel, both
+    within the bar; the error model behind the choice is checked too."""
     rng = np.random.default_rng(seed)
     Y = 0.5 * (rng.standard_normal((B, M)) + 1j * rng.standard_normal((B, M)))
     Yb = Y.copy()
@@ -228,14 +229,18 @@ def check_gram_heavy_tail(N=5, M=40, B=4096, seed=31, tail=3000.0):
         r_ref = np.max(np.abs(Zr), axis=0) / np.sqrt(np.mean(Zr ** 2, axis=0))
         assert np.allclose(host(K.i8_tail_ratios(dY)), r_ref, rtol=1e-10)
         err = {}
-        for name, fn in (("auto", K.rbm_gram_S_auto), ("i8", K.rbm_gram_S_i8), ("dmma", K.rbm_gram_S)):
+        for name, fn in (("auto", lambda *a_: K.rbm_gram_S_auto(*a_, s=ds, hasBias=False)), ("i8", K.rbm_gram_S_i8),
+                         ("dmma", K.rbm_gram_S)):
             A = host(fn(dY, sigT, mu0, al, 0.0))
             err[name] = float(np.max(np.abs(A - A_ref) / nat))
             assert np.array_equal(A, A.conj().T)
             if name == "auto":
-                chosen, pred = K.LAST_GRAM["backend"], K.LAST_GRAM["predicted_error"]
-        assert chosen == ("dmma" if tag == "heavy" else "i8"), (tag, K.LAST_GRAM)
+                chosen, nout = K.LAST_GRAM["backend"], K.LAST_GRAM["outlier_rows"]
+                r1, r2 = K.LAST_GRAM["tail_ratios"]
+        assert chosen == ("i8+dmma" if tag == "heavy" else "i8"), (tag, K.LAST_GRAM)
+        assert (1 <= nout <= 4) if tag == "heavy" else nout == 0
         assert err["auto"] < RTOL and err["dmma"] < RTOL, (tag, err)
+        pred = K.i8_predicted_error(r1, r2, B)
         assert err["i8"] < 10.0 * pred, (tag, err, pred)       # the model bounds the measured int8 error
         res[tag] = (err, pred)
     assert res["benign"][0]["i8"] < RTOL

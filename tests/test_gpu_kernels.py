@@ -113,8 +113,9 @@ def test_gram_int8_tensor_cores(N, M, B, bias, uniform):
 
 @pytest.mark.parametrize("B", [4096, 30000])
 def test_gram_heavy_tailed_columns(B):
-    """Columns of tau with max >> rms: entry-wise accuracy |dA_jl| <= 1e-10 sqrt(A_jj A_ll); the automatic backend choice
-    sends the heavy-tailed matrix to the fp64 DMMA Gram and the benign one to the int8 tensor-core Gram (1 / 2 launches)."""
+    """Columns of tau with max >> rms: entry-wise accuracy |dA_jl| <= 1e-10 sqrt(A_jj A_ll); the automatic choice sends the
+    outlier samples of the heavy-tailed matrix through the fp64 DMMA Gram and everything else through the int8 tensor-core
+    Gram (1 / 2 launches, accumulating into the fp64 part)."""
     G.check_gram_heavy_tail(B=B)
 
 

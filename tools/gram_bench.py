@@ -65,6 +65,8 @@ for _ in range(a.reps):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 ms = min(ts)
+if a.reps > 4:
+    print("per-rep ms:", " ".join("%.0f" % x for x in ts))
 if clk is not None:
     print("clocks under load:", clk.stop())
 TS = a.tile or (80 if (a.M % 80 == 0 or a.M == 40) else 64)

@@ -45,6 +45,15 @@ _SIGS = {
                                 c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ll, c_ptr]),
     "jvmc_minsr_solve_workspace": (c_int, [c_int, c_int, ctypes.POINTER(c_ll)]),
     "jvmc_minsr_solve": (c_int, [c_int, c_int, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ll, c_ptr]),
+    "jvmc_hetrd_workspace": (c_int, [c_int, c_int, ctypes.POINTER(c_ll)]),
+    "jvmc_hetrd": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ll, c_ptr, c_ptr]),
+    "jvmc_unmtr_workspace": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_ll)]),
+    "jvmc_unmtr": (c_int, [c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ll, c_ptr, c_ptr]),
+    "jvmc_tridiag_dense": (c_int, [c_int, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr]),
+    "jvmc_real_to_complex": (c_int, [c_ll, c_ptr, c_ptr, c_ptr]),
+    "jvmc_secular_roots": (c_int, [c_int, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr]),
+    "jvmc_secular_vectors": (c_int, [c_int, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ll, c_ptr, c_ptr]),
+    "jvmc_apply_row_rotations": (c_int, [c_int, c_ll, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "jvmc_comm_nccl_version": (c_int, []),
     "jvmc_comm_unique_id": (c_int, [c_ptr]),
     "jvmc_comm_init": (c_int, [c_ptr, c_int, c_int, ctypes.POINTER(c_ptr)]),
@@ -72,7 +81,8 @@ _SIGS = {
                                  c_ull, c_ll, c_dbl, c_int, c_ll, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "jvmc_i8_slice": (c_int, [c_ptr, c_ll, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "jvmc_i8_tail_ratios": (c_int, [c_ptr, c_ll, c_int, c_ptr, c_ptr, c_ptr]),
-    "jvmc_rbm_gram_S_i8": (c_int, [c_ptr, c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_dbl, c_dbl, c_ptr,
+    "jvmc_i8_outlier_rows": (c_int, [c_ptr, c_ll, c_int, c_ptr, c_dbl, c_ptr, c_ptr]),
+    "jvmc_rbm_gram_S_i8": (c_int, [c_ptr, c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_dbl, c_dbl, c_int, c_ptr,
                                    c_ptr]),
     "jvmc_pack_sigma_rows": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr]),
     "jvmc_rbm_gram_T": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr]),
@@ -138,7 +148,8 @@ def check(rc, what=""):
 
 # kernels launched per entry point (for the gpu_launches figure of bench.py)
 _KERNELS_PER_CALL = {"jvmc_bfo_matels": 2, "jvmc_rbm_moments": 2, "jvmc_i8_slice": 3, "jvmc_i8_tail_ratios": 2, "jvmc_eigh": 0,
-                     "jvmc_tdvp_solve": 6, "jvmc_minsr_solve": 3}
+                     "jvmc_tdvp_solve": 6, "jvmc_minsr_solve": 3,
+                     "jvmc_hetrd": 0, "jvmc_unmtr": 0, "jvmc_secular_vectors": 2}
 LAUNCHES = 0
 
 

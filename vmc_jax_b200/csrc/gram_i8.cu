@@ -215,6 +215,23 @@ __global__ void i8_tail_ratio_kernel(const double* __restrict__ colsq, const uns
   ratio[z] = ms > 0.0 ? __longlong_as_double((long long)colmax[z]) / sqrt(ms) : 0.0;
 }
 
+// flag[n] = 1 if any entry of sample n exceeds T times the rms of its real column (one warp per sample)
+__global__ void i8_rowflag_kernel(const cplx* __restrict__ Y, long long B, int M, const double* __restrict__ colsq, double invB,
+                                  double T, unsigned char* __restrict__ flag) {
+  const long long n = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= B) return;
+  const double* Yd = reinterpret_cast<const double*>(Y) + n * 2 * M;
+  const double T2 = T * T * invB;
+  bool hit = false;
+  for (int z = lane; z < 2 * M; z += 32) {
+    const double v = Yd[z];
+    hit |= v * v > T2 * colsq[z];
+  }
+  const unsigned any = __ballot_sync(0xffffffffu, hit);
+  if (lane == 0) flag[n] = any ? 1 : 0;
+}
+
 // one thread per (16-sample chunk, real column z): 16 strided loads, 2 x 5 x 16 B stores (A and B encodings)
 __global__ void __launch_bounds__(256)
 i8_slice_kernel(const cplx* __restrict__ Y, long long B, int M, const double* __restrict__ scale, long long numChunks,
@@ -708,6 +725,15 @@ extern "C" int jvmc_i8_tail_ratios(const double* Y, long long B, int M, double* 
   return JVMC_OK;
 }
 
+// flag[n] (device bytes) <- 1 where |Z_nz| > T rms_z for some real column z.  scratch: the buffer jvmc_i8_tail_ratios filled.
+extern "C" int jvmc_i8_outlier_rows(const double* Y, long long B, int M, const double* scratch, double T, unsigned char* flag,
+                                    void* stream) {
+  if (!Y || !scratch || !flag || B <= 0 || M <= 0 || !(T > 0.0)) return JVMC_ERR_ARG;
+  i8_rowflag_kernel<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const cplx*)Y, B, M, scratch, 1.0 / (double)B, T, flag);
+  JVMC_CHECK_LAUNCH();
+  return JVMC_OK;
+}
+
 // digits must be zero-initialised by the caller (padding rows/columns stay zero); colmax: 2M uint64 zeroed scratch.
 extern "C" int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long long* colmax, double* scale,
                              signed char* digits, void* stream) {
@@ -735,7 +761,7 @@ extern "C" int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long 
 // launches add into A); digit rows up to 8 colGroup + NC must lie inside the padded layout of jvmc_i8_layout.
 extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale, long long B, int M, int R,
                                   const unsigned int* sigT, const int* tiles, int numTiles, const double* mu,
-                                  double alpha, double kappa, double* A, void* stream) {
+                                  double alpha, double kappa, int accumulate, double* A, void* stream) {
   if (!digits || !scale || !sigT || !tiles || !A || B <= 0 || M <= 0 || R <= 0 || numTiles <= 0) return JVMC_ERR_ARG;
   I8Args a;
   long long digitBytes;
@@ -771,7 +797,7 @@ extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale
   for (long long s0 = 0; s0 < numStages; s0 += per) {
     a.stage0 = s0;
     a.stage1 = (s0 + per < numStages) ? s0 + per : numStages;
-    a.accumulate = (s0 > 0) ? 1 : 0;
+    a.accumulate = (s0 > 0 || accumulate) ? 1 : 0;   // accumulate != 0: A += alpha G (no mean correction), from the first launch on
     a.dbg = g_i8_dbg;
     // 1/2 sum_n b_n per level and column for the samples of this launch (the half of the half-integer A digits)
     cudaMemsetAsync(SB, 0, sizeof(int) * (size_t)I8_S * ZP, (cudaStream_t)stream);

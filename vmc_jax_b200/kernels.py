@@ -325,8 +325,9 @@ def _i8_tiles(M, device):
     return _I8_TILES[key]
 
 
-def rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out=None):
-    """A (as rbm_gram_S) on the tcgen05 INT8 tensor cores via error-free splitting of Y (fp64-equivalent)."""
+def rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out=None, accumulate=False):
+    """A (as rbm_gram_S) on the tcgen05 INT8 tensor cores via error-free splitting of Y (fp64-equivalent).
+    accumulate: A += alpha G (no mean correction) into ``out``."""
     Y = _c(Y, CPX)
     B, M = Y.shape
     R = sigT.shape[0]
@@ -343,45 +344,66 @@ def rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out=None):
     if out is None:
         out = torch.empty((R * M, R * M), dtype=CPX, device=dev)
     call("jvmc_rbm_gram_S_i8", ptr(digits), ptr(scale), B, M, R, ptr(sigT), ptr(tiles), int(tiles.shape[0]), ptr(mu),
-         float(alpha), float(kappa), ptr(out))
+         float(alpha), float(kappa), int(bool(accumulate)), ptr(out))
     return out
 
 
-# ---- which Gram kernel.  The int8 digits resolve 255^-5 of each column's MAXIMUM c_z/2, and the dropped digit pairs
-# (level >= 7) are ~255^-5 c_z c_z' per sample; summed over B samples with random signs, the error of A_zz' relative to
-# its natural size sqrt(A_zz A_z'z') is ~ 0.3 * 4 * 255^-5 * r_z r_z' / sqrt(B) with r_z = max_n|Z_nz| / rms_n(Z_nz)
-# (prefactor measured on B200: 3-8e-14 at config 2 where r ~ 2.5, 2e-10 for two columns with r ~ 200 at B = 30000).
-# Benign tau (|theta| = O(1)) has r of a few; next to a pole of tanh r reaches the hundreds, and entries BETWEEN two such
-# columns lose relative accuracy.  Above I8_MAX_PREDICTED_ERROR the exact fp64 DMMA kernel (4x slower) is used.
-I8_MAX_PREDICTED_ERROR = float(os.environ.get("JVMC_I8_MAX_ERROR", "2e-11"))
-LAST_GRAM = {"backend": None, "tail_ratios": None, "predicted_error": None}
+# ---- which Gram kernel.  The int8 digits resolve 2^-41 of each column's MAXIMUM, and the dropped digit pairs (level >= 7)
+# are ~2^-40 c_z c_z' per sample; summed over B samples with random signs, the error of A_zz' relative to its natural size
+# sqrt(A_zz A_z'z') is ~ 0.3 * 4 * 2^-40 * r_z r_z' / sqrt(B) with r_z = max_n|Z_nz| / rms_n(Z_nz) (prefactor measured on
+# B200: 3-8e-14 on uniform test data with r ~ 2, 2e-10 for two columns with r ~ 200 at B = 30000).  tau = tanh(theta) is
+# heavy-tailed next to the poles of tanh: at config 2 (synthetic weights) r reaches 40-60 and the prediction 1e-11.  Above
+# I8_MAX_PREDICTED_ERROR the few samples that carry the outliers (an entry above I8_OUTLIER_T column rms; ~150 of 66 304 at
+# config 2) are taken out and go through the exact fp64 DMMA kernel, the bulk (r <= I8_OUTLIER_T) through the int8 kernel;
+# if more than 1/16 of the samples are outliers the whole Gram runs in fp64.
+I8_MAX_PREDICTED_ERROR = float(os.environ.get("JVMC_I8_MAX_ERROR", "2e-12"))
+I8_OUTLIER_T = 16.0
+LAST_GRAM = {"backend": None, "tail_ratios": None, "predicted_error": None, "outlier_rows": 0}
 
 
-def i8_tail_ratios(Y):
+def i8_tail_ratios(Y, return_scratch=False):
     """max_n |Z_nz| / rms_n(Z_nz) for the 2M real columns of Y (device tensor)."""
     Y = _c(Y, CPX)
     B, M = Y.shape
     scratch = torch.empty(4 * M, dtype=F64, device=Y.device)
     ratios = torch.empty(2 * M, dtype=F64, device=Y.device)
     call("jvmc_i8_tail_ratios", ptr(Y), B, M, ptr(scratch), ptr(ratios))
-    return ratios
+    return (ratios, scratch) if return_scratch else ratios
 
 
 def i8_predicted_error(r1, r2, B):
-    return 0.3 * 4.0 * 255.0 ** -5 * r1 * r2 / max(B, 1) ** 0.5
+    return 0.3 * 4.0 * 2.0 ** -40 * r1 * r2 / max(B, 1) ** 0.5
 
 
-def rbm_gram_S_auto(Y, sigT, mu, alpha, kappa, out=None):
-    """A by the int8 tensor-core kernel when its predicted entry-wise splitting error is below I8_MAX_PREDICTED_ERROR, by
-    the fp64 DMMA kernel otherwise.  Costs one pass over Y and one 16-byte read-back per Gram."""
+def rbm_gram_S_auto(Y, sigT, mu, alpha, kappa, out=None, s=None, hasBias=False):
+    """A by the int8 tensor-core kernel; heavy-tailed data (see above) is split: outlier samples through the fp64 DMMA
+    kernel, the bulk through the int8 kernel, so that the entry-wise error stays below I8_MAX_PREDICTED_ERROR.
+    s: configurations [B, N] (needed to re-pack the signs of the outlier samples; without it the whole matrix falls back to
+    fp64 when the prediction is too large).  Costs one pass over Y and one small read-back per Gram."""
     Y = _c(Y, CPX)
-    r = i8_tail_ratios(Y)
+    B, M = Y.shape
+    r, scratch = i8_tail_ratios(Y, return_scratch=True)
     top = torch.topk(r, 2 if r.numel() > 1 else 1).values.tolist()
     r1, r2 = top[0], top[-1]
-    err = i8_predicted_error(r1, r2, Y.shape[0])
-    use_i8 = err <= I8_MAX_PREDICTED_ERROR
-    LAST_GRAM.update(backend="i8" if use_i8 else "dmma", tail_ratios=(r1, r2), predicted_error=err)
-    return (rbm_gram_S_i8 if use_i8 else rbm_gram_S)(Y, sigT, mu, alpha, kappa, out)
+    err = i8_predicted_error(r1, r2, B)
+    LAST_GRAM.update(backend="i8", tail_ratios=(r1, r2), predicted_error=err, outlier_rows=0)
+    if err <= I8_MAX_PREDICTED_ERROR:
+        return rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out)
+    if s is not None:
+        flag = torch.empty(B, dtype=torch.uint8, device=Y.device)
+        call("jvmc_i8_outlier_rows", ptr(Y), B, M, ptr(scratch), float(I8_OUTLIER_T), ptr(flag))
+        idx = torch.nonzero(flag).reshape(-1)
+        nout = int(idx.numel())
+        bulk_err = i8_predicted_error(I8_OUTLIER_T, I8_OUTLIER_T, B)
+        if 0 < nout <= B // 16 and bulk_err <= max(I8_MAX_PREDICTED_ERROR, 2e-11):
+            LAST_GRAM.update(backend="i8+dmma", outlier_rows=nout, predicted_error=bulk_err)
+            sig_out = pack_sigma(_c(s, I32)[idx].contiguous(), hasBias)
+            A = rbm_gram_S(Y[idx].contiguous(), sig_out, mu, alpha, kappa, out)      # exact, with the mean correction
+            Yb = Y.clone()
+            Yb[idx] = 0
+            return rbm_gram_S_i8(Yb, sigT, mu, alpha, kappa, A, accumulate=True)
+    LAST_GRAM.update(backend="dmma")
+    return rbm_gram_S(Y, sigT, mu, alpha, kappa, out)
 
 
 def rbm_gram_T(s, tau, p, mu, hasBias, scale=1.0):
@@ -432,6 +454,8 @@ def expand_S(A, M, N, hasBias, mode, shift):
 
 
 EIGH_MAX_N = 32768     # largest n accepted by cuSOLVER 11.7 (CUDA 12.9) dense eigensolvers, probed with tools/eigh_probe.cu
+# above this size eigh_inplace tears the problem in two (eigh_large); JVMC_EIGH_TEAR_ABOVE lowers it for tests
+EIGH_TEAR_ABOVE = int(os.environ.get("JVMC_EIGH_TEAR_ABOVE", str(EIGH_MAX_N)))
 
 
 def eigh_inplace(St, check=True):
@@ -444,11 +468,10 @@ def eigh_inplace(St, check=True):
     d = ctypes.c_longlong(0)
     h = ctypes.c_longlong(0)
     _lib.require_cuda()
-    if n > EIGH_MAX_N:
-        raise NotImplementedError(
-            "dense Hermitian eigen-decomposition of size %d: every cuSOLVER dense eigensolver (Xsyevd, Xsyevdx, XsyevBatched, "
-            "Zheevd, Xgesvdp) rejects n > %d (CUSOLVER_STATUS_INVALID_VALUE, measured on B200: profiles/r2_eigh_probe.txt); "
-            "a distributed / two-stage solver is needed at this size" % (n, EIGH_MAX_N))
+    if n > EIGH_TEAR_ABOVE:
+        # cuSOLVER's dense eigensolvers stop at n = 32768: one level of Cuppen tearing on the tridiagonal matrix
+        w, Vt = eigh_large(St)
+        return w, Vt, torch.zeros(1, dtype=I32, device=St.device)
     _lib.check(lib.jvmc_eigh_workspace(n, int(isC), ctypes.byref(d), ctypes.byref(h)), "jvmc_eigh_workspace")
     work = torch.empty(max(d.value, 8), dtype=torch.uint8, device=St.device)
     w = torch.empty(n, dtype=F64, device=St.device)
@@ -536,3 +559,151 @@ def minsr_solve(Tt, e, rtol):
     if bad != 0:
         raise RuntimeError("cuSOLVER eigen-decomposition failed inside jvmc_minsr_solve (n = %d, devInfo = %d)" % (n, bad))
     return x, ev
+
+
+def _deflate_host(d, z, rho):
+    """Deflation scan of the rank-one update diag(d) + rho z z^T (d ascending), after LAPACK dlaed2: components with a
+    negligible z are eigenpairs already; two close poles are rotated so that one of them drops out.  O(n), sequential,
+    on the host (NumPy).  Returns (d, z after rotations, deflated mask, rotations [(i, j, c, s)])."""
+    n = d.size
+    eps = np.finfo(np.float64).eps
+    tol = 8.0 * eps * max(float(np.max(np.abs(d))), float(np.max(np.abs(z))))
+    d = d.copy()
+    z = z.copy()
+    defl = np.zeros(n, bool)
+    rots = []
+    small = rho * np.abs(z) <= tol
+    prev = -1
+    for j in range(n):
+        if small[j]:
+            defl[j] = True
+            continue
+        if prev >= 0:
+            s_, c_ = z[prev], z[j]
+            tau = float(np.hypot(c_, s_))
+            t = d[j] - d[prev]
+            c_, s_ = c_ / tau, -s_ / tau
+            if abs(t * c_ * s_) <= tol:
+                z[j], z[prev] = tau, 0.0
+                rots.append((prev, j, c_, s_))
+                tt = d[prev] * c_ * c_ + d[j] * s_ * s_
+                d[j] = d[prev] * s_ * s_ + d[j] * c_ * c_
+                d[prev] = tt
+                defl[prev] = True
+        prev = j
+    return d, z, defl, rots
+
+
+def eigh_large(St):
+    """Hermitian eigen-decomposition by one level of Cuppen's divide and conquer (csrc/eigh_large.cu) for matrices beyond
+    cuSOLVER's n <= 32768: St is the column-major image (lower triangle referenced) and is destroyed; returns
+    (ev ascending, Vt) with row k of Vt = eigenvector k, like eigh_inplace.  Replaces jnp.linalg.eigh of the reference
+    (jVMC/util/tdvp.py:153-171) at the config-2 size P_c = 40 000."""
+    n = St.shape[0]
+    isC = St.is_complex()
+    dev = St.device
+    lib = _lib.load()
+    _lib.require_cuda()
+    m = n // 2
+    if max(m, n - m) > EIGH_MAX_N:
+        raise NotImplementedError("eigh_large tears once: n <= %d" % (2 * EIGH_MAX_N))
+    info = torch.zeros(1, dtype=I32, device=dev)
+
+    def chk(what):
+        bad = int(info.item())
+        if bad != 0:
+            raise RuntimeError("cuSOLVER %s failed (n = %d, devInfo = %d)" % (what, n, bad))
+    # 1. tridiagonalisation A = H T H^dagger
+    nb = ctypes.c_longlong(0)
+    _lib.check(lib.jvmc_hetrd_workspace(n, int(isC), ctypes.byref(nb)), "jvmc_hetrd_workspace")
+    work = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    dg = torch.empty(n, dtype=F64, device=dev)
+    e = torch.empty(max(n - 1, 1), dtype=F64, device=dev)
+    tau = torch.empty(max(n - 1, 1), dtype=CPX if isC else F64, device=dev)
+    call("jvmc_hetrd", n, int(isC), ptr(St), ptr(dg), ptr(e), ptr(tau), ptr(work), nb.value, ptr(info))
+    chk("hetrd")
+    del work
+    # 2. tear: T = diag(T1', T2') + rho v v^T, v = (0..0, 1, sg, 0..0)
+    beta = float(e[m - 1].item())
+    rho, sg = abs(beta), (1.0 if beta >= 0 else -1.0)
+    halves = []
+    for lo, hi, sf, sl in ((0, m, 0.0, -rho), (m, n, -rho, 0.0)):
+        k = hi - lo
+        T = torch.zeros((k, k), dtype=F64, device=dev)
+        call("jvmc_tridiag_dense", k, ptr(dg[lo:hi].contiguous()), ptr(e[lo:hi - 1].contiguous()) if k > 1 else None,
+             sf, sl, ptr(T))
+        w, Qt, _ = eigh_inplace(T)            # row r of Qt = eigenvector r  (k <= EIGH_MAX_N: cuSOLVER)
+        halves.append((w, Qt))
+    (w1, Q1t), (w2, Q2t) = halves
+    if rho == 0.0:                            # decoupled already
+        D = torch.cat([w1, w2])
+        order = torch.argsort(D)
+        Zt = torch.zeros((n, n), dtype=F64, device=dev)
+        Zt[:m, :m] = Q1t
+        Zt[m:, m:] = Q2t
+        lam, Zt = D[order], Zt[order]
+    else:
+        # 3. rank-one update D + rho z z^T with z = (last row of Q1, sg * first row of Q2)
+        D = torch.cat([w1, w2])
+        z = torch.cat([Q1t[:, m - 1], sg * Q2t[:, 0]])
+        nz = float(torch.linalg.norm(z))
+        z = z / nz
+        rho = rho * nz * nz
+        perm = torch.argsort(D, stable=True)
+        d_s, z_s, defl, rots = _deflate_host(D[perm].cpu().numpy(), z[perm].cpu().numpy(), rho)
+        keep = np.where(~defl)[0]
+        o = np.argsort(d_s[keep], kind="stable")    # rotations may have perturbed the order of the kept poles
+        keep = keep[o]
+        k = keep.size
+        lam_s = d_s.copy()
+        U = torch.zeros((n, n), dtype=F64, device=dev)       # as a row-major tensor: U[c, r] = (column c, row r) of U
+        perm_h = perm.cpu().numpy()
+        if k > 0:
+            dk = torch.as_tensor(d_s[keep]).to(dev)
+            zk = torch.as_tensor(z_s[keep]).to(dev)
+            z2 = (zk * zk).contiguous()
+            orig = torch.empty(k, dtype=I32, device=dev)
+            mu = torch.empty(k, dtype=F64, device=dev)
+            call("jvmc_secular_roots", k, ptr(dk), ptr(z2), float(rho), float(z2.sum().item()), ptr(orig), ptr(mu))
+            lam_s[keep] = (dk[orig.long()] + mu).cpu().numpy()
+        order = np.argsort(lam_s, kind="stable")              # ascending eigenvalues: column position of sorted index
+        colpos = np.empty(n, np.int64)
+        colpos[order] = np.arange(n)
+        # deflated eigenvectors: unit vectors (rotated below)
+        dfl = np.where(defl)[0]
+        if dfl.size:
+            U[torch.as_tensor(colpos[dfl]).to(dev), torch.as_tensor(perm_h[dfl]).to(dev)] = 1.0
+        if k > 0:
+            rowIdx = torch.as_tensor(perm_h[keep].astype(np.int32)).to(dev)
+            colIdx = torch.as_tensor(colpos[keep].astype(np.int32)).to(dev)
+            zhat = torch.empty(k, dtype=F64, device=dev)
+            call("jvmc_secular_vectors", k, ptr(dk), ptr(zk), float(rho), ptr(orig), ptr(mu), ptr(rowIdx), ptr(colIdx),
+                 ptr(U), n, ptr(zhat))
+        if rots:
+            # U = G_1 .. G_m U': the rotations acted on columns (i, j) of the basis, apply them to the rows in reverse
+            ri = torch.as_tensor(np.array([perm_h[r[0]] for r in reversed(rots)], np.int32)).to(dev)
+            rj = torch.as_tensor(np.array([perm_h[r[1]] for r in reversed(rots)], np.int32)).to(dev)
+            cc = torch.as_tensor(np.array([r[2] for r in reversed(rots)], np.float64)).to(dev)
+            ss = torch.as_tensor(np.array([r[3] for r in reversed(rots)], np.float64)).to(dev)
+            call("jvmc_apply_row_rotations", n, n, ptr(U), len(rots), ptr(ri), ptr(rj), ptr(cc), ptr(ss))
+        lam = torch.as_tensor(lam_s[order]).to(dev)
+        # 4. Z = diag(Q1, Q2) U   (cuBLAS dgemm through torch.matmul; row-major images: Zt[:, :m] = Ut[:, :m] Q1t)
+        Zt = torch.empty((n, n), dtype=F64, device=dev)
+        torch.matmul(U[:, :m], Q1t, out=Zt[:, :m])
+        torch.matmul(U[:, m:], Q2t, out=Zt[:, m:])
+        del U
+    del Q1t, Q2t
+    # 5. back-transformation V = H Z in column panels (Z real -> complex for the Hermitian case)
+    Vt = torch.empty((n, n), dtype=CPX if isC else F64, device=dev)
+    panel = min(n, 4096)
+    _lib.check(lib.jvmc_unmtr_workspace(n, panel, int(isC), ctypes.byref(nb)), "jvmc_unmtr_workspace")
+    work = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    for c0 in range(0, n, panel):
+        c1 = min(n, c0 + panel)
+        if isC:
+            call("jvmc_real_to_complex", (c1 - c0) * n, ptr(Zt[c0:c1]), ptr(Vt[c0:c1]))
+        else:
+            Vt[c0:c1] = Zt[c0:c1]
+        call("jvmc_unmtr", n, c1 - c0, int(isC), ptr(St), ptr(tau), ptr(Vt[c0:c1]), ptr(work), nb.value, ptr(info))
+    chk("unmtr")
+    return lam, Vt

@@ -250,10 +250,11 @@ class RBMGradientObs(SampledObs):
             # backend: "i8" = tcgen05 INT8 tensor cores with error-free splitting (fp64-equivalent, default; the fp64 DMMA
             #          kernel takes over for heavy-tailed tau columns, kernels.rbm_gram_S_auto), "i8only", "dmma"
             gram = _gram_backend()
+            kw = {"s": self._s, "hasBias": self.hasBias} if gram is K.rbm_gram_S_auto else {}
             if self._uniform is not None:
-                A = gram(self._tau, self._sigT, mu, float(self._uniform), kappa)
+                A = gram(self._tau, self._sigT, mu, float(self._uniform), kappa, **kw)
             else:
-                A = gram(self._tau * torch.sqrt(p)[:, None], self._sigT, mu, 1.0, kappa)
+                A = gram(self._tau * torch.sqrt(p)[:, None], self._sigT, mu, 1.0, kappa, **kw)
             # Hermitian: from 8 ranks on communicate the upper block triangle only (half the bytes) and rebuild the
             # rest; below that the pack / unpack / mirror passes cost more than the saved NVLink time (measured)
             half = os.environ.get("JVMC_HERMITIAN_ALLREDUCE")
@@ -268,7 +269,8 @@ class RBMGradientObs(SampledObs):
             self._sigT = K.pack_sigma(self._s, self.hasBias)
         gram = _gram_backend()
         Y = self._tau * torch.sqrt(w2.to(torch.float64))[:, None]
-        A2 = gram(Y, self._sigT, torch.zeros((self.R, self.M), dtype=torch.complex128, device=Y.device), 1.0, 0.0)
+        kw = {"s": self._s, "hasBias": self.hasBias} if gram is K.rbm_gram_S_auto else {}
+        A2 = gram(Y, self._sigT, torch.zeros((self.R, self.M), dtype=torch.complex128, device=Y.device), 1.0, 0.0, **kw)
         half = os.environ.get("JVMC_HERMITIAN_ALLREDUCE")
         half = (mpi.commSize >= 8) if half is None else (half == "1")
         return mpi.all_reduce_hermitian_blocks(A2, self.M) if half else mpi._all_reduce_sum(A2)
