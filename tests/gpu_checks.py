@@ -247,6 +247,41 @@ def check_gram_heavy_tail(N=5, M=40, B=4096, seed=31, tail=3000.0):
     return res
 
 
+def check_eigh_large(n=700, cplx=True, kind="gram", seed=3):
+    """kernels.eigh_large (hetrd -> Cuppen tearing -> secular equation -> unmtr; the path for n > 32768) against the
+    direct cuSOLVER decomposition at a size where both run: spectrum, residual, orthonormality, on spectra that exercise
+    the deflation (clusters, numerically rank-deficient Gram matrices, decoupled halves)."""
+    rng = np.random.default_rng(seed)
+    if kind == "gram":                     # S-like: Gram matrix of fewer samples than parameters, decaying column scales
+        X = rng.standard_normal((n // 2, n)) + (1j * rng.standard_normal((n // 2, n)) if cplx else 0.0)
+        X = X * np.logspace(0, -7, n)[None, :]
+        A = X.conj().T @ X / (n // 2)
+    elif kind == "clustered":
+        Q, _ = np.linalg.qr(rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cplx else 0.0))
+        ev = np.concatenate([np.ones(n // 3), 1.0 + 1e-9 * rng.standard_normal(n // 3), np.linspace(2, 3, n - 2 * (n // 3))])
+        A = (Q * ev[None, :]) @ Q.conj().T
+    elif kind == "blockdiag":               # beta = 0 at the tearing point
+        A = np.zeros((n, n), complex if cplx else float)
+        for lo, hi in ((0, n // 2), (n // 2, n)):
+            Bk = rng.standard_normal((hi - lo, hi - lo)) + (1j * rng.standard_normal((hi - lo, hi - lo)) if cplx else 0.0)
+            A[lo:hi, lo:hi] = Bk + Bk.conj().T
+    else:
+        Bk = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cplx else 0.0)
+        A = Bk + Bk.conj().T
+    A = 0.5 * (A + A.conj().T)
+    dA = dev(A, torch.complex128 if cplx else torch.float64)
+    St = dA.T.clone(memory_format=torch.contiguous_format)
+    w_ref, Vt_ref, _ = K.eigh_inplace(St.clone())
+    w, Vt = K.eigh_large(St.clone())
+    scale = float(w_ref.abs().max())
+    assert float((w - w_ref).abs().max()) < 1e-12 * scale * n ** 0.5, float((w - w_ref).abs().max()) / scale
+    V = Vt.T
+    resid = float((dA @ V - V * w[None, :].to(V.dtype)).abs().max()) / scale
+    orth = float((V.conj().T @ V - torch.eye(n, dtype=V.dtype, device=V.device)).abs().max())
+    assert resid < 1e-11 and orth < 1e-11, (resid, orth)
+    return resid, orth
+
+
 def check_gram_T(N=7, M=24, B=211, bias=True, seed=21, uniform=False):
     """Khatri-Rao tangent kernel T = 2 Obar Obar^dagger and O.x mat-vec vs the dense oracle (stats.py:332-336)."""
     W, b = orbm.init_o1(N, M, bias, seed)

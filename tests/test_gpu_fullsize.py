@@ -250,3 +250,50 @@ def test_cfg3_chain_L40_bias_eloc_F_parity():
     pn = G.host(ps)[0]
     oF = ostats.SampledObs(orbm.gradients_holomorphic(sn, W, b), pn).covar(ostats.SampledObs(G.host(E[0])[idx], pn)).ravel()
     assert G.relerr(G.host(Fk), oF) < 1e-10
+
+
+def test_tdvp_solve_parity_6x6_alpha4():
+    """TDVP solve at 6x6, alpha = 4 (P_c = 5184, P = 10 368) on 4144 sampled configurations against the oracle's
+    reference-layout solve (reference jVMC/util/tdvp.py:153-213; NumPy eigh of the 10 368 x 10 368 matrix, ~30 s):
+    spectrum, F, Var E, the eigenspace-summed SNR ingredients, and -- with the SNR weighting switched off on both sides,
+    where the update is unique -- residual, cutoff and update."""
+    from oracle import solve as osolve, stats as ostats
+    L, alpha = 6, 4
+    N, M = L * L, alpha * L * L
+    psi = jVMC.vqs.NQS(jVMC.nets.CpxRBM(numHidden=M, bias=False), seed=1)
+    psi(torch.zeros((1, 1, L, L), dtype=torch.int32, device="cuda"))
+    W, b = orbm.init_o1(N, M, False, 4321)
+    psi.set_parameters(torch.as_tensor(orbm.flatten_params(W, b)))
+    H = tfim2d(L, L, 3.04)
+    smp = jVMC.sampler.MCSampler(psi, (L, L), 4321, updateProposer=jVMC.sampler.propose_spin_flip, numChains=296,
+                                 sweepSteps=N, thermalizationSweeps=10, numSamples=4096)
+    s, logPsi, p = smp.sample()
+    B = s.shape[1]
+    Eloc = H.get_O_loc(s, psi, logPsi)
+    import jVMC.mpi_wrapper as mpi
+    res = {}
+    for snrTol in (0.0, 2.0):
+        td = jVMC.util.TDVP(smp, snrTol=snrTol, pinvTol=1e-8, pinvCutoff=1e-8, rhsPrefactor=1., diagonalShift=1e-3,
+                            makeReal='real')
+        upd, r, c = td.solve(SampledObs(Eloc, p), RBMGradientObs(psi, s, p))
+        res[snrTol] = (td, upd, float(r), float(c))
+    sn, pn, En = G.host(s[0]).reshape(B, -1), G.host(p[0]), G.host(Eloc[0])
+    oE, oG = ostats.SampledObs(En, pn), ostats.SampledObs(orbm.gradients_holomorphic(sn, W, b), pn)
+    otd = osolve.TDVP(snrTol=2, pinvTol=1e-8, pinvCutoff=1e-8, rhsPrefactor=1., diagonalShift=1e-3, makeReal='real',
+                      exact_sampler=True)                      # exact_sampler: SNR computed but not applied (tdvp.py:203)
+    upd_ref, res_ref, cut_ref = otd.solve(oE, oG, mpi.globNumSamples)
+    td0, upd0, r0, c0 = res[0.0]
+    scale = np.abs(otd.ev).max()
+    assert np.allclose(G.host(td0.ev), otd.ev, atol=1e-9 * scale)
+    assert np.allclose(G.host(td0.F0), otd.F0, rtol=1e-10, atol=1e-13)
+    assert np.isclose(float(td0.ElocVar), otd.ElocVar, rtol=1e-10)
+    assert c0 == cut_ref and np.isclose(r0, res_ref, rtol=1e-5, atol=1e-9)
+    assert np.allclose(G.host(upd0), upd_ref, rtol=1e-5, atol=1e-6 * np.abs(upd_ref).max())
+    # SNR ingredients summed over each doubly degenerate eigenspace (basis independent)
+    td2 = res[2.0][0]
+    vtf2 = (np.abs(otd.VtF) ** 2).reshape(-1, 2).sum(1)
+    rv = otd.rhoVar.reshape(-1, 2).sum(1)
+    ok = otd.ev.reshape(-1, 2)[:, 0] > 1e-9 * scale
+    snr_pair = np.sqrt(np.abs(mpi.globNumSamples * vtf2 / rv))
+    assert np.allclose(G.host(td2.snr).reshape(-1, 2)[:, 0][ok], snr_pair[ok], rtol=1e-4)
+    assert np.isfinite(res[2.0][2]) and bool(torch.isfinite(res[2.0][1]).all())

@@ -111,6 +111,24 @@ def test_gram_int8_tensor_cores(N, M, B, bias, uniform):
     G.check_moments_gram(N, M, B, bias, uniform=uniform, backend="i8")
 
 
+@pytest.mark.parametrize("n,cplx,kind", [(700, True, "gram"), (701, True, "random"), (512, False, "gram"),
+                                         (600, True, "clustered"), (400, True, "blockdiag"), (333, False, "random")])
+def test_eigh_large_cuppen_tearing(n, cplx, kind):
+    """The eigen-decomposition path for n > 32768 (cuSOLVER's limit), exercised at sizes where the direct solver runs."""
+    G.check_eigh_large(n, cplx, kind)
+
+
+def test_eigh_inplace_tears_above_threshold():
+    """eigh_inplace routes to the tearing path above kernels.EIGH_TEAR_ABOVE; the TDVP solve on top of it is unchanged."""
+    from vmc_jax_b200 import kernels as K
+    old = K.EIGH_TEAR_ABOVE
+    try:
+        K.EIGH_TEAR_ABOVE = 16
+        G.check_tdvp_solve()
+    finally:
+        K.EIGH_TEAR_ABOVE = old
+
+
 @pytest.mark.parametrize("B", [4096, 30000])
 def test_gram_heavy_tailed_columns(B):
     """Columns of tau with max >> rms: entry-wise accuracy |dA_jl| <= 1e-10 sqrt(A_jj A_ll); the automatic choice sends the

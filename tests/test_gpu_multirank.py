@@ -22,8 +22,9 @@ def _free_port():
     return p
 
 
-def _run(world, out, chains, samples, mu, wscale):
+def _run(world, out, chains, samples, mu, wscale, gram):
     env = dict(os.environ)
+    env["JVMC_GRAM_BACKEND"] = gram
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
     worker = [os.path.join(HERE, "multirank_worker.py"), out, str(chains), str(samples), str(mu), str(wscale)]
@@ -38,12 +39,15 @@ def _run(world, out, chains, samples, mu, wscale):
     return [np.load(out + ".rank%d.npz" % k) for k in range(world)]
 
 
-@pytest.mark.parametrize("mu,wscale", [(2.0, 0.08), (1.0, 0.3)])
-def test_two_ranks_equal_one_rank(tmp_path, mu, wscale):
-    """wscale 0.08: benign tau; wscale 0.3: theta reaches the poles of tanh, heavy-tailed tau columns."""
+@pytest.mark.parametrize("mu,wscale,gram", [(2.0, 0.08, "i8"), (1.0, 0.3, "dmma")])
+def test_two_ranks_equal_one_rank(tmp_path, mu, wscale, gram):
+    """wscale 0.08, Born weights, int8 tensor-core Gram: its column scales follow the rank-local maxima, so A of the 1- and
+    2-rank runs agrees to the splitting accuracy; wscale 0.3, mu = 1 (non-uniform weights), fp64 Gram: theta reaches the
+    poles of tanh and the 3840 samples of this 12-site chain repeat configurations many times (coherent digit errors),
+    so the rank-equality is asserted on the exact kernel, to round-off."""
     chains, samples = 96, 96 * 40
-    one = _run(1, str(tmp_path / "w1"), chains, samples, mu, wscale)[0]
-    two = _run(2, str(tmp_path / "w2"), chains, samples, mu, wscale)
+    one = _run(1, str(tmp_path / "w1"), chains, samples, mu, wscale, gram)[0]
+    two = _run(2, str(tmp_path / "w2"), chains, samples, mu, wscale, gram)
     assert int(one["nglob"][0]) == int(two[0]["nglob"][0]) == samples
     N = one["configs"].shape[-1]
     c1 = one["configs"].reshape(-1, chains, N)                         # time-major, chain-minor (sampler.py:323)
@@ -62,7 +66,7 @@ def test_two_ranks_equal_one_rank(tmp_path, mu, wscale):
         # the int8 Gram's column scales follow the rank-local maxima: the 1- and 2-rank matrices agree to the splitting
         # accuracy (entry-wise, relative to sqrt(A_jj A_ll)), not to round-off
         nat = np.sqrt(np.outer(np.real(np.diag(one["A"])), np.real(np.diag(one["A"]))))
-        assert np.max(np.abs(t["A"] - one["A"]) / nat) <= 2e-11
+        assert np.max(np.abs(t["A"] - one["A"]) / nat) <= (2e-11 if gram == "i8" else 1e-12)
         assert np.allclose(t["acc"], one["acc"], rtol=1e-12)
         assert float(t["herm_err"][0]) < 1e-12
         assert np.allclose(t["update"], one["update"], rtol=1e-6, atol=1e-8 * np.abs(one["update"]).max())

@@ -1,7 +1,8 @@
 """ONE full TDVP step (sample + E_loc + S/F + eigen-decomposition + SNR + regularised solve) at BASELINE configs[1]:
 2D TFIM 10x10, CpxRBM alpha=4 (P_c = 40 000), 2^16 samples, imaginary time (rhsPrefactor=1, makeReal='real').
-The 40 000 x 40 000 Hermitian eigen-decomposition is a cuSOLVER call of several minutes: a one-off measurement, not
-part of bench.py."""
+The 40 000 x 40 000 Hermitian eigen-decomposition is beyond cuSOLVER's dense solvers (n <= 32768): it runs through
+kernels.eigh_large (hetrd + one level of Cuppen tearing + unmtr), about two minutes: a one-off measurement, not part of
+bench.py.   python tools/tdvp_config2.py [--alpha 4] [--L 10]"""
 import os
 import sys
 import time
@@ -14,8 +15,14 @@ import bench  # noqa: E402
 import vmc_jax_b200 as jVMC  # noqa: E402
 import vmc_jax_b200.operator as op  # noqa: E402
 
-Lx = Ly = 10
-N, M = Lx * Ly, 4 * Lx * Ly
+import argparse  # noqa: E402
+_ap = argparse.ArgumentParser()
+_ap.add_argument("--alpha", type=int, default=4)
+_ap.add_argument("--L", type=int, default=10)
+_args = _ap.parse_args()
+os.environ.setdefault("JVMC_EIGH_VERBOSE", "1")
+Lx = Ly = _args.L
+N, M = Lx * Ly, _args.alpha * Lx * Ly
 dev = jVMC.global_defs.myDevice
 psi = jVMC.vqs.NQS(jVMC.nets.CpxRBM(numHidden=M, bias=False), seed=1234)
 psi(torch.zeros((1, 1, Lx, Ly), dtype=torch.int32, device=dev))

@@ -608,6 +608,14 @@ def eigh_large(St):
     if max(m, n - m) > EIGH_MAX_N:
         raise NotImplementedError("eigh_large tears once: n <= %d" % (2 * EIGH_MAX_N))
     info = torch.zeros(1, dtype=I32, device=dev)
+    verbose = os.environ.get("JVMC_EIGH_VERBOSE", "0") != "0"
+    import time as _time
+    marks = [("start", _time.perf_counter())]
+
+    def mark(name):
+        if verbose:
+            torch.cuda.synchronize()
+            marks.append((name, _time.perf_counter()))
 
     def chk(what):
         bad = int(info.item())
@@ -623,6 +631,7 @@ def eigh_large(St):
     call("jvmc_hetrd", n, int(isC), ptr(St), ptr(dg), ptr(e), ptr(tau), ptr(work), nb.value, ptr(info))
     chk("hetrd")
     del work
+    mark("hetrd")
     # 2. tear: T = diag(T1', T2') + rho v v^T, v = (0..0, 1, sg, 0..0)
     beta = float(e[m - 1].item())
     rho, sg = abs(beta), (1.0 if beta >= 0 else -1.0)
@@ -635,6 +644,7 @@ def eigh_large(St):
         w, Qt, _ = eigh_inplace(T)            # row r of Qt = eigenvector r  (k <= EIGH_MAX_N: cuSOLVER)
         halves.append((w, Qt))
     (w1, Q1t), (w2, Q2t) = halves
+    mark("eigh of the two halves")
     if rho == 0.0:                            # decoupled already
         D = torch.cat([w1, w2])
         order = torch.argsort(D)
@@ -687,11 +697,13 @@ def eigh_large(St):
             ss = torch.as_tensor(np.array([r[3] for r in reversed(rots)], np.float64)).to(dev)
             call("jvmc_apply_row_rotations", n, n, ptr(U), len(rots), ptr(ri), ptr(rj), ptr(cc), ptr(ss))
         lam = torch.as_tensor(lam_s[order]).to(dev)
+        mark("merge: deflation (%d of %d deflated, %d rotations), secular equation, vectors" % (n - k, n, len(rots)))
         # 4. Z = diag(Q1, Q2) U   (cuBLAS dgemm through torch.matmul; row-major images: Zt[:, :m] = Ut[:, :m] Q1t)
         Zt = torch.empty((n, n), dtype=F64, device=dev)
         torch.matmul(U[:, :m], Q1t, out=Zt[:, :m])
         torch.matmul(U[:, m:], Q2t, out=Zt[:, m:])
         del U
+        mark("Z = diag(Q1, Q2) U")
     del Q1t, Q2t
     # 5. back-transformation V = H Z in column panels (Z real -> complex for the Hermitian case)
     Vt = torch.empty((n, n), dtype=CPX if isC else F64, device=dev)
@@ -706,4 +718,8 @@ def eigh_large(St):
             Vt[c0:c1] = Zt[c0:c1]
         call("jvmc_unmtr", n, c1 - c0, int(isC), ptr(St), ptr(tau), ptr(Vt[c0:c1]), ptr(work), nb.value, ptr(info))
     chk("unmtr")
+    mark("back-transformation (unmtr)")
+    if verbose:
+        print("eigh_large n = %d (%s):" % (n, "complex" if isC else "real"), "; ".join(
+            "%s %.2f s" % (marks[i][0], marks[i][1] - marks[i - 1][1]) for i in range(1, len(marks))), flush=True)
     return lam, Vt

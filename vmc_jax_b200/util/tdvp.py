@@ -275,7 +275,7 @@ class TDVP:
             self.rhoVar = torch.cat([rv.flip(0), rv])
             self.snr = torch.sqrt(torch.abs(mpi.globNumSamples * (self.VtF.conj() * self.VtF).real / self.rhoVar)).reshape(-1)
         exact = _is_exact_sampler(self.sampler)
-        pinvEv, scal = K.tdvp_regularize(self.ev, self.VtF, None if exact else self.snr, F.to(torch.complex128),
+        pinvEv, scal = K.tdvp_regularize(self.ev, self.VtF, None if (exact or self.snrTol == 0) else self.snr, F.to(torch.complex128),
                                          float(self.pinvTol), float(self.pinvCutoff), float(self.snrTol))
         self.invEv = torch.where(torch.abs(self.ev / self.ev[-1]) > 1e-14, 1. / self.ev, torch.zeros_like(self.ev))
         coef = pinvEv * self.VtF
@@ -302,7 +302,7 @@ class TDVP:
         D = gradients._data.reshape(-1, P)
         res = K.tdvp_solve(St, F.to(torch.complex128), D, Eloc._data.reshape(-1), gradients._weights.reshape(-1),
                            self.rhsPrefactor, mpi.globNumSamples, self.snrTol, self.pinvTol, self.pinvCutoff,
-                           useSnr=not _is_exact_sampler(self.sampler), comm=mpi.capi_comm())
+                           useSnr=not (_is_exact_sampler(self.sampler) or self.snrTol == 0), comm=mpi.capi_comm())
         self.ev, self._Vt, self.VtF = res["ev"], res["Vt"], res["VtF"]
         self.rhoVar, self.snr = res["rhoVar"], res["snr"]
         self.invEv = torch.where(torch.abs(self.ev / self.ev[-1]) > 1e-14, 1. / self.ev, torch.zeros_like(self.ev))
@@ -320,7 +320,7 @@ class TDVP:
         exact = _is_exact_sampler(self.sampler)
         self._get_snr(Eloc, gradients)      # computed for every sampler, used unless ExactSampler (:203)
         Fc = F.to(torch.complex128)
-        pinvEv, scal = K.tdvp_regularize(self.ev, self.VtF, None if exact else self.snr, Fc, float(self.pinvTol),
+        pinvEv, scal = K.tdvp_regularize(self.ev, self.VtF, None if (exact or self.snrTol == 0) else self.snr, Fc, float(self.pinvTol),
                                          float(self.pinvCutoff), float(self.snrTol))
         self.invEv = torch.where(torch.abs(self.ev / self.ev[-1]) > 1e-14, 1. / self.ev, torch.zeros_like(self.ev))
         update = torch.mv(self._Vt.to(torch.complex128).T, (pinvEv * self.VtF)).real
