@@ -218,6 +218,9 @@ int jvmc_hetrd(int n, int isComplex, double* A, double* d, double* e, double* ta
 int jvmc_unmtr_workspace(int n, int ncols, int isComplex, long long* bytes);
 int jvmc_unmtr(int n, int ncols, int isComplex, double* A, double* tau, double* C, void* work, long long bytes, int* info,
                void* stream);
+int jvmc_unmqr_workspace(int m, int ncols, int k, int isComplex, int lda, int ldc, long long* bytes);
+int jvmc_unmqr(int m, int ncols, int k, int isComplex, double* A, int lda, double* tau, double* C, int ldc, void* work,
+               long long bytes, int* info, void* stream);
 int jvmc_tridiag_dense(int m, const double* d, const double* e, double shiftFirst, double shiftLast, double* T, void* stream);
 int jvmc_real_to_complex(long long count, const double* src, double* dst, void* stream);
 int jvmc_secular_roots(int k, const double* d, const double* z2, double rho, double z2sum, int* orig, double* mu, void* stream);

@@ -193,6 +193,27 @@ int main(int argc, char** argv) {
   if (argc >= 3 && !strcmp(argv[1], "--run")) return run_dn(h, p, atoi(argv[2]), false);
   if (argc >= 3 && !strcmp(argv[1], "--run-legacy")) return run_dn(h, p, atoi(argv[2]), true);
   if (argc >= 3 && !strcmp(argv[1], "--run-mg")) return run_mg(atoi(argv[2]), argc >= 4 ? atoi(argv[3]) : ndev, argc >= 5 ? atoi(argv[4]) : 256);
+  if (argc >= 2 && !strcmp(argv[1], "--unm")) {
+    const int n = argc >= 3 ? atoi(argv[2]) : 40000;
+    const int cols[] = {128, 256, 1024, 4096, 16384};
+    const int ks[] = {128, 256, 1024, 4096, 16384, n - 1};
+    for (int nc : cols) {
+      int lw = -1;
+      cusolverStatus_t s1 = cusolverDnZunmtr_bufferSize(h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, nc, nullptr, n,
+                                                        nullptr, nullptr, n, &lw);
+      printf("Zunmtr n=%d ncols=%d: status %d lwork %d\n", n, nc, (int)s1, lw);
+      for (int k : ks) {
+        lw = -1;
+        cusolverStatus_t s2 = cusolverDnZunmqr_bufferSize(h, CUBLAS_SIDE_LEFT, CUBLAS_OP_N, n - 1, nc, k, nullptr, n, nullptr, nullptr, n, &lw);
+        printf("   Zunmqr m=%d ncols=%d k=%d: status %d lwork %d\n", n - 1, nc, k, (int)s2, lw);
+      }
+      lw = -1;
+      cusolverStatus_t s3 = cusolverDnDormtr_bufferSize(h, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, n, nc, nullptr, n,
+                                                        nullptr, nullptr, n, &lw);
+      printf("   Dormtr n=%d ncols=%d: status %d lwork %d\n", n, nc, (int)s3, lw);
+    }
+    return 0;
+  }
   if (argc >= 3 && !strcmp(argv[1], "--run-svdp")) return run_svdp(h, p, atoi(argv[2]));
   if (argc >= 2 && !strcmp(argv[1], "--other")) {
     probe_other(h, p);

@@ -49,6 +49,8 @@ _SIGS = {
     "jvmc_hetrd": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ll, c_ptr, c_ptr]),
     "jvmc_unmtr_workspace": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_ll)]),
     "jvmc_unmtr": (c_int, [c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ll, c_ptr, c_ptr]),
+    "jvmc_unmqr_workspace": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_ll)]),
+    "jvmc_unmqr": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ll, c_ptr, c_ptr]),
     "jvmc_tridiag_dense": (c_int, [c_int, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr]),
     "jvmc_real_to_complex": (c_int, [c_ll, c_ptr, c_ptr, c_ptr]),
     "jvmc_secular_roots": (c_int, [c_int, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr]),
@@ -149,7 +151,7 @@ def check(rc, what=""):
 # kernels launched per entry point (for the gpu_launches figure of bench.py)
 _KERNELS_PER_CALL = {"jvmc_bfo_matels": 2, "jvmc_rbm_moments": 2, "jvmc_i8_slice": 3, "jvmc_i8_tail_ratios": 2, "jvmc_eigh": 0,
                      "jvmc_tdvp_solve": 6, "jvmc_minsr_solve": 3,
-                     "jvmc_hetrd": 0, "jvmc_unmtr": 0, "jvmc_secular_vectors": 2}
+                     "jvmc_hetrd": 0, "jvmc_unmtr": 0, "jvmc_unmqr": 0, "jvmc_secular_vectors": 2}
 LAUNCHES = 0
 
 

@@ -220,6 +220,36 @@ extern "C" int jvmc_unmtr(int n, int ncols, int isComplex, double* A, double* ta
   return s == CUSOLVER_STATUS_SUCCESS ? JVMC_OK : JVMC_ERR_SOLVER;
 }
 
+// The same back-transformation in chunks of reflectors (cusolverDnZunmtr / Dormtr refuse n > 32768, Zunmqr / Dormqr accept
+// m = 40 000 with k <= 16384 reflectors per call, probed: profiles/r2_eigh_probe.txt): C (m x ncols, leading dimension ldc)
+// <- H_0 .. H_{k-1} C with the k reflectors stored geqrf-style in the columns of A (m x k, leading dimension lda).
+extern "C" int jvmc_unmqr_workspace(int m, int ncols, int k, int isComplex, int lda, int ldc, long long* bytes) {
+  if (m <= 0 || ncols <= 0 || k <= 0 || k > m || !bytes) return JVMC_ERR_ARG;
+  int rc = ensure(0);
+  if (rc) return rc;
+  int lw = 0;
+  cusolverStatus_t s = isComplex
+      ? cusolverDnZunmqr_bufferSize(g_h, CUBLAS_SIDE_LEFT, CUBLAS_OP_N, m, ncols, k, nullptr, lda, nullptr, nullptr, ldc, &lw)
+      : cusolverDnDormqr_bufferSize(g_h, CUBLAS_SIDE_LEFT, CUBLAS_OP_N, m, ncols, k, nullptr, lda, nullptr, nullptr, ldc, &lw);
+  if (s != CUSOLVER_STATUS_SUCCESS || lw <= 0) return JVMC_ERR_SOLVER;
+  *bytes = (long long)lw * (isComplex ? 16 : 8);
+  return JVMC_OK;
+}
+
+extern "C" int jvmc_unmqr(int m, int ncols, int k, int isComplex, double* A, int lda, double* tau, double* C, int ldc, void* work,
+                          long long bytes, int* info, void* stream) {
+  if (m <= 0 || ncols <= 0 || k <= 0 || k > m || !A || !tau || !C || !work || !info) return JVMC_ERR_ARG;
+  int rc = ensure((cudaStream_t)stream);
+  if (rc) return rc;
+  cusolverStatus_t s;
+  if (isComplex)
+    s = cusolverDnZunmqr(g_h, CUBLAS_SIDE_LEFT, CUBLAS_OP_N, m, ncols, k, (cuDoubleComplex*)A, lda, (cuDoubleComplex*)tau,
+                         (cuDoubleComplex*)C, ldc, (cuDoubleComplex*)work, (int)(bytes / 16), info);
+  else
+    s = cusolverDnDormqr(g_h, CUBLAS_SIDE_LEFT, CUBLAS_OP_N, m, ncols, k, A, lda, tau, C, ldc, (double*)work, (int)(bytes / 8), info);
+  return s == CUSOLVER_STATUS_SUCCESS ? JVMC_OK : JVMC_ERR_SOLVER;
+}
+
 extern "C" int jvmc_real_to_complex(long long count, const double* src, double* dst, void* stream) {
   if (count < 0 || !src || !dst) return JVMC_ERR_ARG;
   if (count == 0) return JVMC_OK;

@@ -59,7 +59,8 @@ constexpr int I8_B_BYTES = I8_TN * I8_KS;
 constexpr int I8_STAGE_BYTES = I8_S * (I8_A_BYTES + I8_B_BYTES);
 constexpr int I8_MAXSTAGES = 800;       // stages per launch: 800*32*5*128^2 < 2^31 (int32 head-room in TMEM)
 constexpr int I8_DEFAULT_STAGES = 800;  // default: as many as the head-room allows (see jvmc_rbm_gram_S_i8)
-constexpr int I8_THREADS = 64 + 32 * I8_SW;   // warp 0 producer, 1 MMA issuer, then the sign warps (2-5 also epilogue)
+constexpr int I8_THREADS = 96 + 32 * I8_SW;   // warp 0 A producer, 1 MMA issuer, 2-9 sign warps (2-5 also epilogue), 10 B producer
+constexpr int I8_BPROD_WARP = 2 + I8_SW;
 constexpr int I8_ACOL = I8_LEV * I8_TN;   // first TMEM column of the A operand buffers (I8_NB x 5 digits x 8 columns)
 static_assert(I8_LEV * JVMC_I8_TN + JVMC_I8_NB * 5 * 8 <= 512, "TMEM columns");
 
@@ -72,6 +73,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset of CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, unsigned rank) {
+  unsigned raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+  // relaxed: the shared-memory loads this arrive stands for have returned their data already (it was consumed), so
+  // no release fence over the cluster is needed (a release.cluster arrive cost ~1500 cycles here)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(raddr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   asm volatile(
@@ -335,9 +344,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* ring = smem_raw;                                                     // [slot][A digits | B digits]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)I8_SLOTS * I8_STAGE_BYTES);
-  uint64_t* full = bars;                    // TMA bytes landed in the slot
-  uint64_t* empty = bars + I8_SLOTS;        // MMAs reading the slot retired
-  uint64_t* aready = bars + 2 * I8_SLOTS;   // [2] signed A digits of a stage are in TMEM buffer b
+  // The A and the B half of a ring slot are recycled independently: the A digits are free as soon as the sign warps
+  // (of every CTA of the cluster: the copies are multicast) hold them in registers, ~2 stages before the MMAs that
+  // read the B digits of the same stage retire.  With one barrier pair per slot the A copies were issued only ~2000
+  // cycles before their use and every L2 miss (~1200 instead of ~900 cycles) stalled the sign warps: 20 % of the
+  // stages took 1100 instead of 700 cycles (trace).
+  uint64_t* fullA = bars;                   // A digits of the slot landed
+  uint64_t* emptyA = bars + I8_SLOTS;       // sign warps of all CTAs of the cluster have loaded them
+  uint64_t* full = bars + 2 * I8_SLOTS;     // B digits of the slot landed
+  uint64_t* empty = bars + 3 * I8_SLOTS;    // MMAs reading them retired (in every CTA of the cluster)
+  uint64_t* aready = bars + 4 * I8_SLOTS;   // [2] signed A digits of a stage are in TMEM buffer b
   uint64_t* afree = aready + I8_NB;         // [NB] MMAs reading TMEM buffer b retired
   uint64_t* accfull = afree + I8_NB;
   uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(accfull + 1);
@@ -362,13 +378,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   if (warp == 2) I8_TRACE_CTA(0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < I8_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, (unsigned)a.cl); }
+    for (int s = 0; s < I8_SLOTS; ++s) {
+      mbar_init(full + s, 1); mbar_init(empty + s, (unsigned)a.cl);
+      mbar_init(fullA + s, 1); mbar_init(emptyA + s, (unsigned)(a.cl * (I8_SW / 2)));
+    }
     for (int b = 0; b < I8_NB; ++b) { mbar_init(aready + b, I8_SW / 2); mbar_init(afree + b, 1); }   // 4 warps per buffer
     mbar_init(accfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (threadIdx.x >= 64) {
-    for (unsigned v = threadIdx.x - 64; v < 256; v += I8_THREADS - 64) {
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {
+    for (unsigned v = threadIdx.x - 64; v < 256; v += 256) {
       const unsigned lo = v & 0xFu, hi = v >> 4;
       lut[v] = make_uint2(((lo * 0x00204081u) & 0x01010101u) * 0xFFu, ((hi * 0x00204081u) & 0x01010101u) * 0xFFu);
     }
@@ -384,24 +403,30 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   const uint32_t tmem = *tmem_base_p;
   if (warp == 2) I8_TRACE_CTA(1);
 
-  if (warp == 0) {
-    // ===================== producer: one bulk copy per (operand, digit) and stage =====================
-    for (long long g = 0; g < ((a.dbg & 1) ? 0 : numStages); ++g) {
-      const int slot = (int)(g % I8_SLOTS);
-      if (g >= I8_SLOTS) mbar_wait(empty + slot, (unsigned)((g / I8_SLOTS - 1) & 1));
-      unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES;
-      if (lane == 0) mbar_expect_tx(full + slot, (unsigned)(I8_S * I8_A_BYTES) + I8_S * bBytes);
+  if (warp == 0 || warp == I8_BPROD_WARP) {
+    // ===================== producers: one bulk copy per digit and stage; warp 0 the A tiles, warp 10 the B tiles =====
+    const bool isA = warp == 0;
+    uint64_t* fullBar = isA ? fullA : full;
+    uint64_t* emptyBar = isA ? emptyA : empty;
+    const unsigned bytes = isA ? (unsigned)I8_A_BYTES : bBytes;
+    const int8_t* srcBase = isA ? a.dig + (size_t)RG * 256 : a.digB + (size_t)CG * 256;
+    long long nProd = (a.dbg & 1) ? 0 : numStages;
+    if (isA && (a.dbg & 3)) nProd = 0;               // ablation modes without a sign pass: nobody consumes the A tiles
+    uint32_t slot = 0, par = 0;
+    for (long long g = 0; g < nProd; ++g) {
+      if (g >= I8_SLOTS) mbar_wait(emptyBar + slot, par ^ 1u);
+      unsigned char* st = ring + (size_t)slot * I8_STAGE_BYTES + (isA ? 0 : I8_S * I8_A_BYTES);
+      if (lane == 0) mbar_expect_tx(fullBar + slot, (unsigned)I8_S * bytes);
       __syncwarp();
-      if (lane < 2 * I8_S) {
-        const int k = lane >> 1, which = lane & 1;
-        const size_t base = ((size_t)(a.stage0 + g) * I8_S + k) * a.numZGroups;
-        unsigned char* dst = which == 0 ? st + k * I8_A_BYTES : st + I8_S * I8_A_BYTES + k * bBytes;   // B digits packed
-        const int8_t* src = (which == 0 ? a.dig + (base + (size_t)RG) * 256 : a.digB + (base + (size_t)CG) * 256);
-        const unsigned bytes = which == 0 ? (unsigned)I8_A_BYTES : bBytes;
-        if (a.cl == 1) bulk_g2s(dst, src, bytes, full + slot);
-        else if ((unsigned)lane % (unsigned)a.cl == crank) bulk_g2s_mc(dst, src, bytes, full + slot, cmask);   // my share
+      if (lane < I8_S) {
+        const size_t base = ((size_t)(a.stage0 + g) * I8_S + lane) * a.numZGroups;
+        unsigned char* dst = st + lane * bytes;                                       // digit tiles packed
+        const int8_t* src = srcBase + base * 256;
+        if (a.cl == 1) bulk_g2s(dst, src, bytes, fullBar + slot);
+        else if ((unsigned)lane % (unsigned)a.cl == crank) bulk_g2s_mc(dst, src, bytes, fullBar + slot, cmask);   // my share
       }
-      I8_TRACE(0);
+      if (isA) I8_TRACE(0);
+      if (++slot == I8_SLOTS) { slot = 0; par ^= 1u; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: warp 1, convergent; one elected lane issues =====================
@@ -421,7 +446,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       const uint32_t idesc1 = ibase | (((1u * NCu) >> 3) << 17);
       const uint32_t idesc2 = ibase | (((2u * NCu) >> 3) << 17);
       const uint32_t idesc3 = ibase | (((3u * NCu) >> 3) << 17);
-      const bool useFull = (a.dbg & 3) != 0 && !(a.dbg & 1);     // ablation modes without a sign pass
+      const bool useFull = !(a.dbg & 1);                         // B digits of the stage landed
       const bool useReady = !(a.dbg & 3);
       uint32_t slot = 0, fullPar = 0, bufPar = 0, b = 0;       // bufPar bit q: parity of the next use of TMEM A buffer q
       const uint32_t ring0 = smem_u32(ring) + I8_S * I8_A_BYTES;
@@ -510,7 +535,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
         }
         // The signed digits are prepared in registers BEFORE waiting for the TMEM buffer, so that only the
         // TMEM store sits on the MMA(g-2) -> sign(g) -> MMA(g) dependency chain.
-        mbar_wait(full + slot, fullPar);
+        mbar_wait(fullA + slot, fullPar);
         if (warp == 2) I8_TRACE(4);
         const unsigned char* st = aBase + slot * (uint32_t)I8_STAGE_BYTES;
         uint32_t w[I8_S][8];
@@ -523,6 +548,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
             w[k][ch * 4 + 0] = v.x ^ msk[ch * 4 + 0]; w[k][ch * 4 + 1] = v.y ^ msk[ch * 4 + 1];
             w[k][ch * 4 + 2] = v.z ^ msk[ch * 4 + 2]; w[k][ch * 4 + 3] = v.w ^ msk[ch * 4 + 3];
           }
+        }
+        __syncwarp();
+        if (lane == 0) {                                      // the A half of the slot may be refilled
+          if (a.cl == 1) mbar_arrive(emptyA + slot);
+          else for (unsigned rk = 0; rk < (unsigned)a.cl; ++rk) mbar_arrive_cluster(emptyA + slot, rk);
         }
         if (warp == 2) I8_TRACE(5);
         if (g >= I8_NB) { mbar_wait(afree + grp, freePar); freePar ^= 1u; }

@@ -705,20 +705,32 @@ def eigh_large(St):
         del U
         mark("Z = diag(Q1, Q2) U")
     del Q1t, Q2t
-    # 5. back-transformation V = H Z in column panels (Z real -> complex for the Hermitian case)
+    # 5. back-transformation V = H Z.  H = H_0 .. H_{n-2} acts on rows 1..n-1; the reflectors sit geqrf-style in the
+    #    (n-1) x (n-1) block A[1:, :n-1].  cuSOLVER's unmtr refuses n > 32768, unmqr takes <= 16384 reflectors per call:
+    #    chunks of reflectors (last chunk first), column panels of Z (real -> complex for the Hermitian case).
     Vt = torch.empty((n, n), dtype=CPX if isC else F64, device=dev)
+    el = 16 if isC else 8
     panel = min(n, 4096)
-    _lib.check(lib.jvmc_unmtr_workspace(n, panel, int(isC), ctypes.byref(nb)), "jvmc_unmtr_workspace")
-    work = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    chunk = min(n - 1, 4096)
+    if n > 1:
+        _lib.check(lib.jvmc_unmqr_workspace(n - 1, panel, chunk, int(isC), n, n, ctypes.byref(nb)), "jvmc_unmqr_workspace")
+        work = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    starts = list(range(0, n - 1, chunk))
     for c0 in range(0, n, panel):
         c1 = min(n, c0 + panel)
         if isC:
             call("jvmc_real_to_complex", (c1 - c0) * n, ptr(Zt[c0:c1]), ptr(Vt[c0:c1]))
         else:
             Vt[c0:c1] = Zt[c0:c1]
-        call("jvmc_unmtr", n, c1 - c0, int(isC), ptr(St), ptr(tau), ptr(Vt[c0:c1]), ptr(work), nb.value, ptr(info))
-    chk("unmtr")
-    mark("back-transformation (unmtr)")
+        for i0 in reversed(starts):
+            i1 = min(n - 1, i0 + chunk)
+            # reflectors i0..i1-1: columns i0.. of A[1:, :], acting on rows i0+1.. of the panel
+            Ap = ctypes.c_void_p(St.data_ptr() + ((i0 + 1) + i0 * n) * el)
+            taup = ctypes.c_void_p(tau.data_ptr() + i0 * el)
+            Cp = ctypes.c_void_p(Vt.data_ptr() + (c0 * n + i0 + 1) * el)
+            call("jvmc_unmqr", n - 1 - i0, c1 - c0, i1 - i0, int(isC), Ap, n, taup, Cp, n, ptr(work), nb.value, ptr(info))
+    chk("unmqr")
+    mark("back-transformation (unmqr, %d reflector chunks x %d column panels)" % (len(starts), (n + panel - 1) // panel))
     if verbose:
         print("eigh_large n = %d (%s):" % (n, "complex" if isC else "real"), "; ".join(
             "%s %.2f s" % (marks[i][0], marks[i][1] - marks[i - 1][1]) for i in range(1, len(marks))), flush=True)
