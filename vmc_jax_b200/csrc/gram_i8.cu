@@ -448,59 +448,65 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
       const uint32_t idesc3 = ibase | (((3u * NCu) >> 3) << 17);
       const bool useFull = !(a.dbg & 1);                         // B digits of the stage landed
       const bool useReady = !(a.dbg & 3);
-      uint32_t slot = 0, fullPar = 0, bufPar = 0, b = 0;       // bufPar bit q: parity of the next use of TMEM A buffer q
       const uint32_t ring0 = smem_u32(ring) + I8_S * I8_A_BYTES;
       const uint32_t bStep = (NCu * (uint32_t)I8_KS) >> 4;       // one B digit tile in 16-byte units
       auto wait_stage = [&](uint32_t sl, uint32_t fp, uint32_t bb, uint32_t bp) {
-        if (useFull && !mbar_test(full + sl, fp)) mbar_wait(full + sl, fp);
-        if (useReady && !mbar_test(aready + bb, bp)) mbar_wait(aready + bb, bp);
+        // both probes are issued before either result is consumed: their ~100-cycle latencies overlap
+        const bool okF = !useFull || mbar_test(full + sl, fp);
+        const bool okR = !useReady || mbar_test(aready + bb, bp);
+        if (!okF) mbar_wait(full + sl, fp);
+        if (!okR) mbar_wait(aready + bb, bp);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       };
       if (numStages > 0) wait_stage(0u, 0u, 0u, 0u);
-      for (long long g = 0; g < numStages; ++g) {
-        I8_TRACE(2);
-        // K-major SWIZZLE_NONE descriptor of B digit tile k': low word = (address >> 4) | LBO(128 B) << 16,
-        // high word = SBO(256 B) | version bit
-        const uint32_t dlo = (((ring0 + slot * (uint32_t)I8_STAGE_BYTES) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
-        const uint32_t ta = tmemU + (uint32_t)I8_ACOL + b * (uint32_t)(I8_S * 8);
-        // (digit k, first k', count n): level column = (k + k' - 2) * NC
-        auto mma = [&](uint32_t k, uint32_t kp, uint32_t idesc, uint32_t accumulate) {
-          const uint64_t db = ((uint64_t)((256u >> 4) | (1u << 14)) << 32) | (uint64_t)(dlo + (kp - 1u) * bStep);
-          umma_i8_ts(tmemU + (k + kp - 2u) * NCu, ta + (k - 1u) * 8u, db, idesc, accumulate);
-        };
-        uint32_t nslot = slot + 1, nfullPar = fullPar;
-        if (nslot == I8_SLOTS) { nslot = 0; nfullPar ^= 1u; }
-        uint32_t nb = b + 1;
-        if (nb == I8_NB) nb = 0;
-        bufPar ^= 1u << b;                                       // parity of this buffer's NEXT use
-        const bool leader = elect_one();
-        if (leader) {
-          if (g == 0) {
-            mma(1, 1, idesc3, 0u);       // levels 2,3,4 (first writer)
-            mma(1, 4, idesc2, 0u);       // levels 5,6   (first writer)
-          } else {
-            mma(1, 1, idesc3, 1u);
-            mma(1, 4, idesc2, 1u);
+      const bool leader = elect_one();
+      // The loop over stages is unrolled over the six ring slots (six is even: the TMEM A buffer is slot & 1), so the
+      // slot's shared-memory descriptor and every TMEM address are loop-invariant values the compiler keeps in uniform
+      // registers; only the barrier phases depend on the round q.
+      static_assert(I8_SLOTS % I8_NB == 0, "ring slots cycle through the TMEM A buffers");
+      for (long long q = 0; q * I8_SLOTS < numStages; ++q) {
+#pragma unroll
+        for (uint32_t slot = 0; slot < (uint32_t)I8_SLOTS; ++slot) {
+          const long long g = q * I8_SLOTS + slot;
+          if (g >= numStages) break;
+          I8_TRACE(2);
+          const uint32_t b = slot % (uint32_t)I8_NB;
+          // K-major SWIZZLE_NONE descriptor of B digit tile k': low word = (address >> 4) | LBO(128 B) << 16,
+          // high word = SBO(256 B) | version bit
+          const uint32_t dlo = (((ring0 + slot * (uint32_t)I8_STAGE_BYTES) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
+          const uint32_t ta = tmemU + (uint32_t)I8_ACOL + b * (uint32_t)(I8_S * 8);
+          // (digit k, first k', count n): level column = (k + k' - 2) * NC
+          auto mma = [&](uint32_t k, uint32_t kp, uint32_t idesc, uint32_t accumulate) {
+            const uint64_t db = ((uint64_t)((256u >> 4) | (1u << 14)) << 32) | (uint64_t)(dlo + (kp - 1u) * bStep);
+            umma_i8_ts(tmemU + (k + kp - 2u) * NCu, ta + (k - 1u) * 8u, db, idesc, accumulate);
+          };
+          if (leader) {
+            const uint32_t acc = (g == 0) ? 0u : 1u;
+            mma(1, 1, idesc3, acc);        // levels 2,3,4 (first writer at g = 0)
+            mma(1, 4, idesc2, acc);        // levels 5,6   (first writer at g = 0)
+            mma(2, 1, idesc3, 1u);         // levels 3,4,5
+            mma(2, 4, idesc1, 1u);         // level 6
+            mma(3, 1, idesc3, 1u);         // levels 4,5,6
           }
-          mma(2, 1, idesc3, 1u);         // levels 3,4,5
-          mma(2, 4, idesc1, 1u);         // level 6
-          mma(3, 1, idesc3, 1u);         // levels 4,5,6
+          __syncwarp();
+          I8_TRACE(1);
+          if (g + 1 < numStages) {           // barriers of the next stage, polled while the MMAs above are queued
+            const uint32_t nslot = (slot + 1 == (uint32_t)I8_SLOTS) ? 0u : slot + 1;
+            const uint32_t nfullPar = (uint32_t)((slot + 1 == (uint32_t)I8_SLOTS) ? (q + 1) : q) & 1u;
+            wait_stage(nslot, nfullPar, nslot % (uint32_t)I8_NB, (uint32_t)((g + 1) / I8_NB) & 1u);
+          }
+          I8_TRACE(8);
+          if (leader) {
+            mma(4, 1, idesc2, 1u);         // levels 5,6
+            mma(5, 1, idesc1, 1u);         // level 6
+            if (a.cl == 1) umma_commit(empty + slot);        // smem slot reusable once these MMAs retire
+            else umma_commit_mc(empty + slot, cmask);        // ... in every CTA of the cluster (they all write into it)
+            umma_commit(afree + b);                          // ... and so is the TMEM A buffer
+            if (g + 1 == numStages) umma_commit(accfull);
+          }
+          __syncwarp();
+          I8_TRACE(3);
         }
-        __syncwarp();
-        I8_TRACE(1);
-        if (g + 1 < numStages) wait_stage(nslot, nfullPar, nb, (bufPar >> nb) & 1u);   // overlapped with the queued MMAs
-        I8_TRACE(8);
-        if (leader) {
-          mma(4, 1, idesc2, 1u);         // levels 5,6
-          mma(5, 1, idesc1, 1u);         // level 6
-          if (a.cl == 1) umma_commit(empty + slot);        // smem slot reusable once these MMAs retire
-          else umma_commit_mc(empty + slot, cmask);        // ... in every CTA of the cluster (they all write into it)
-          umma_commit(afree + b);                          // ... and so is the TMEM A buffer
-          if (g + 1 == numStages) umma_commit(accfull);
-        }
-        __syncwarp();
-        I8_TRACE(3);
-        slot = nslot; fullPar = nfullPar; b = nb;
       }
       I8_TRACE_CTA(2);
     }

@@ -235,9 +235,10 @@ class TDVP:
         #           basis LAPACK happens to return inside the 2-d eigenspace.  The eigenspace-invariant
         #           definition is used for both members: SNR^2 = N (|Re zeta|^2 + |Im zeta|^2) / (Var Re zeta + Var Im zeta)
         #           -- it equals the reference's value whenever that is basis independent (equal member SNRs).
-        if Pc >= 256 and Bglob >= 2 * Pc:
+        if Pc >= 256 and (Bglob >= 2 * Pc or (Pc >= 8192 and Bglob >= Pc)):
             # sum_n w_n |zeta_kn|^2 = |x|^2 sum_n w'_n |v_k^T (O_n - mu)|^2, w'_n = w_n |dE_n|^2: a second Gram matrix
-            # A' = sum w' conj(O) O^T (same tensor-core kernel) and P_c^3 instead of N_s P_c^2 projection flops
+            # A' = sum w' conj(O) O^T (same tensor-core kernel) and P_c^3 instead of N_s P_c^2 projection flops (large P_c:
+            # already from N_s >= P_c on, the second Gram costs a small fraction of either product there)
             w2 = (G._p * (dE.conj() * dE).real).contiguous()
             Ap = G.weighted_second_moment(w2)
             m1 = mpi._all_reduce_sum(K.rbm_moments(G._s, G._tau, w2.to(torch.complex128), G.hasBias, 0)).reshape(-1)
