@@ -121,9 +121,11 @@ int jvmc_i8_tail_ratios(const double* Y, long long B, int M, double* scratch, do
  * these few samples go through the exact fp64 kernel, the rest through the int8 kernel (rbm_gram_S_auto). */
 int jvmc_i8_outlier_rows(const double* Y, long long B, int M, const double* scratch, double T, unsigned char* flag,
                          void* stream);
+/* accumulate != 0: A += alpha G.  [pair0, pair0 + npairs): range of site pairs in the order (r0 ascending, r1 = r0..R-1),
+ * npairs <= 0: all R(R+1)/2 -- block row r0 of the upper block triangle of A is final once its pairs are done. */
 int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale, long long B, int M, int R,
                        const unsigned int* sigT, const int* tiles, int numTiles, const double* mu, double alpha,
-                       double kappa, int accumulate, double* A, void* stream);   /* accumulate != 0: A += alpha G */
+                       double kappa, int accumulate, long long pair0, long long npairs, double* A, void* stream);
 
 /* SampledObs.tangent_kernel (jVMC/stats.py:332-336; MinSR, jVMC/util/minsr.py:59-60), Khatri-Rao form:
  * T[n,m] = scale sqrt(p_n p_m) [ (sum_r sigma_nr sigma_mr)(sum_j tau_nj conj tau_mj) - v_n - conj(v_m) + c ],
@@ -141,6 +143,7 @@ int jvmc_rbm_gram_T(const double* Y, long long B, int M, int R, const unsigned i
 int jvmc_hermitian_mirror_blocks(double* A, int Pc, int M, void* stream);
 long long jvmc_hermitian_packed_elems(int Pc, int M);   /* complex elements of the packed upper block triangle */
 int jvmc_hermitian_pack_blocks(double* A, int Pc, int M, double* packed, int unpack, void* stream);
+int jvmc_hermitian_pack_rows(double* A, int Pc, int M, int row0, int nrows, double* packed, int unpack, void* stream);
 
 int jvmc_expand_S(const double* A, int M, int N, int hasBias, int mode, double shift, double* out, void* stream);
 

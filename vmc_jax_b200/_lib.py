@@ -69,6 +69,7 @@ _SIGS = {
     "jvmc_hermitian_mirror_blocks": (c_int, [c_ptr, c_int, c_int, c_ptr]),
     "jvmc_hermitian_packed_elems": (c_ll, [c_int, c_int]),
     "jvmc_hermitian_pack_blocks": (c_int, [c_ptr, c_int, c_int, c_ptr, c_int, c_ptr]),
+    "jvmc_hermitian_pack_rows": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_int, c_ptr]),
     "jvmc_i8_tile_shape": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "jvmc_mcmc_set_generic": (c_int, [c_int]),
     "jvmc_cnn_num_parameters": (c_int, [c_ptr, c_int, ctypes.POINTER(c_int)]),
@@ -84,8 +85,8 @@ _SIGS = {
     "jvmc_i8_slice": (c_int, [c_ptr, c_ll, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "jvmc_i8_tail_ratios": (c_int, [c_ptr, c_ll, c_int, c_ptr, c_ptr, c_ptr]),
     "jvmc_i8_outlier_rows": (c_int, [c_ptr, c_ll, c_int, c_ptr, c_dbl, c_ptr, c_ptr]),
-    "jvmc_rbm_gram_S_i8": (c_int, [c_ptr, c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_dbl, c_dbl, c_int, c_ptr,
-                                   c_ptr]),
+    "jvmc_rbm_gram_S_i8": (c_int, [c_ptr, c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_dbl, c_dbl, c_int, c_ll, c_ll,
+                                   c_ptr, c_ptr]),
     "jvmc_pack_sigma_rows": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr]),
     "jvmc_rbm_gram_T": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr]),
     "jvmc_pack_sigma": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr]),

@@ -331,7 +331,9 @@ struct I8Args {
   int dbg;                    // development ablations: 1 = MMA issue only, 2 = TMA + MMA (no sign pass), 4 = no TMEM store,
                               // 32 = no shared-memory reads in the sign pass, 64 = no sign arithmetic
   int cl;                     // thread-block cluster size along the pair axis (operand tiles are TMA-multicast)
-  long long pairs;            // R (R + 1) / 2; CTAs beyond it only pad the last cluster
+  long long pairs;            // R (R + 1) / 2 site pairs in total
+  long long pair0, npairs;    // this launch covers pairs [pair0, pair0 + npairs) in the order r0 ascending, r1 = r0 .. R-1
+                              // (CTAs beyond it only pad the last cluster)
   long long* trace;           // development: clock64 time stamps of one CTA, 8 events per stage (jvmc_i8_set_trace)
   int traceTile;
 };
@@ -365,9 +367,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) gram_s_i8_kernel(I8Args a) {
   // operand traffic (the binding resource of the single-CTA version) drops by the cluster size.
   const unsigned crank = (a.cl > 1) ? cluster_ctarank() : 0u;
   const unsigned short cmask = (unsigned short)((1u << a.cl) - 1u);
-  const bool padCta = (long long)blockIdx.x >= a.pairs;
+  const bool padCta = (long long)blockIdx.x >= a.npairs;
   int r1, r0;
-  tri_decode(padCta ? 0 : blockIdx.x, r1, r0);   // r0 <= r1
+  {
+    // pair p <-> (r0 ascending, r1 >= r0): block row r0 of the upper block triangle of A is complete once the pairs of
+    // r0 are done, so a launch over a range of pairs finishes a range of rows (overlapped reduction over ranks)
+    int hi, lo;
+    tri_decode(a.pairs - 1 - (padCta ? a.pair0 : a.pair0 + blockIdx.x), hi, lo);
+    r0 = a.R - 1 - hi;
+    r1 = a.R - 1 - lo;
+  }
   const int* tile = a.tiles + 8 * (size_t)blockIdx.y;
   // tile rows start at real column 8 RG, its NC columns at real column 8 CG; tiles that end at the diagonal are
   // narrower than I8_TN so that less of the rectangle above the diagonal is computed
@@ -797,7 +806,8 @@ extern "C" int jvmc_i8_slice(const double* Y, long long B, int M, unsigned long 
 // launches add into A); digit rows up to 8 colGroup + NC must lie inside the padded layout of jvmc_i8_layout.
 extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale, long long B, int M, int R,
                                   const unsigned int* sigT, const int* tiles, int numTiles, const double* mu,
-                                  double alpha, double kappa, int accumulate, double* A, void* stream) {
+                                  double alpha, double kappa, int accumulate, long long pair0, long long npairs, double* A,
+                                  void* stream) {
   if (!digits || !scale || !sigT || !tiles || !A || B <= 0 || M <= 0 || R <= 0 || numTiles <= 0) return JVMC_ERR_ARG;
   I8Args a;
   long long digitBytes;
@@ -817,8 +827,11 @@ extern "C" int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale
   if (numTiles > 65535 || pairs > 2147483647LL) return JVMC_ERR_UNSUPPORTED;
   // (tile descriptors are device data: NC in {16, 32, ..., I8_TN} and the padding bound are the caller's contract)
   a.cl = g_i8_cluster; a.pairs = pairs;
+  if (npairs <= 0) { pair0 = 0; npairs = pairs; }
+  if (pair0 < 0 || pair0 + npairs > pairs) return JVMC_ERR_ARG;
+  a.pair0 = pair0; a.npairs = npairs;
   a.trace = g_i8_trace; a.traceTile = g_i8_trace_tile;
-  dim3 grid((unsigned)((pairs + a.cl - 1) / a.cl * a.cl), (unsigned)numTiles);
+  dim3 grid((unsigned)((npairs + a.cl - 1) / a.cl * a.cl), (unsigned)numTiles);
   const long long numStages = a.numChunks / 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(I8_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;

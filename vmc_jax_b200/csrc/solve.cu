@@ -111,8 +111,8 @@ int ensure_handle() {
 
 
 // packed <-> A: the suffix [r M, Pc) of every matrix row i = (r, j), rows back to back (direction 0: pack, 1: unpack)
-__global__ void hermitian_pack_kernel(cplx* __restrict__ A, int Pc, int M, cplx* __restrict__ packed, int unpack) {
-  const int i = blockIdx.y;
+__global__ void hermitian_pack_kernel(cplx* __restrict__ A, int Pc, int M, cplx* __restrict__ packed, int unpack, int row0) {
+  const int i = row0 + blockIdx.y;
   const int r = i / M, j = i - r * M;
   const long long c0 = (long long)r * M;
   const long long off = (long long)M * ((long long)r * Pc - (long long)M * r * (r - 1) / 2) + (long long)j * (Pc - c0);
@@ -221,7 +221,19 @@ extern "C" long long jvmc_hermitian_packed_elems(int Pc, int M) {
 extern "C" int jvmc_hermitian_pack_blocks(double* A, int Pc, int M, double* packed, int unpack, void* stream) {
   if (!A || !packed || Pc <= 0 || M <= 0 || Pc % M != 0 || Pc > 65535) return JVMC_ERR_ARG;
   unsigned gx = (unsigned)((Pc + 1023) / 1024);
-  hermitian_pack_kernel<<<dim3(gx, (unsigned)Pc), 256, 0, (cudaStream_t)stream>>>((cplx*)A, Pc, M, (cplx*)packed, unpack);
+  hermitian_pack_kernel<<<dim3(gx, (unsigned)Pc), 256, 0, (cudaStream_t)stream>>>((cplx*)A, Pc, M, (cplx*)packed, unpack, 0);
+  JVMC_CHECK_LAUNCH();
+  return JVMC_OK;
+}
+
+/* the same for matrix rows [row0, row0 + nrows) only (packed: base of the WHOLE packed buffer; block rows are contiguous in
+ * it, elements [jvmc_hermitian_packed_offset(row0 / M), ...)): lets a finished range of block rows be reduced over ranks
+ * while the Gram kernel still works on the others */
+extern "C" int jvmc_hermitian_pack_rows(double* A, int Pc, int M, int row0, int nrows, double* packed, int unpack, void* stream) {
+  if (!A || !packed || Pc <= 0 || M <= 0 || Pc % M != 0 || Pc > 65535 || row0 < 0 || nrows <= 0 || row0 + nrows > Pc)
+    return JVMC_ERR_ARG;
+  unsigned gx = (unsigned)((Pc + 1023) / 1024);
+  hermitian_pack_kernel<<<dim3(gx, (unsigned)nrows), 256, 0, (cudaStream_t)stream>>>((cplx*)A, Pc, M, (cplx*)packed, unpack, row0);
   JVMC_CHECK_LAUNCH();
   return JVMC_OK;
 }

@@ -325,9 +325,12 @@ def _i8_tiles(M, device):
     return _I8_TILES[key]
 
 
-def rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out=None, accumulate=False):
+def rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out=None, accumulate=False, pair_groups=None, after_group=None):
     """A (as rbm_gram_S) on the tcgen05 INT8 tensor cores via error-free splitting of Y (fp64-equivalent).
-    accumulate: A += alpha G (no mean correction) into ``out``."""
+    accumulate: A += alpha G (no mean correction) into ``out``.
+    pair_groups: list of (pair0, npairs) ranges of site pairs (order: r0 ascending, r1 = r0..R-1) launched one after the
+    other; ``after_group(k)`` is called when the launches of group k are enqueued -- block rows of the upper block
+    triangle of A are final group by group, which lets the caller reduce them over ranks while the next group runs."""
     Y = _c(Y, CPX)
     B, M = Y.shape
     R = sigT.shape[0]
@@ -343,9 +346,18 @@ def rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out=None, accumulate=False):
     tiles = _i8_tiles(M, dev)
     if out is None:
         out = torch.empty((R * M, R * M), dtype=CPX, device=dev)
-    call("jvmc_rbm_gram_S_i8", ptr(digits), ptr(scale), B, M, R, ptr(sigT), ptr(tiles), int(tiles.shape[0]), ptr(mu),
-         float(alpha), float(kappa), int(bool(accumulate)), ptr(out))
+    groups = [(0, 0)] if pair_groups is None else list(pair_groups)
+    for k, (p0, npairs) in enumerate(groups):
+        call("jvmc_rbm_gram_S_i8", ptr(digits), ptr(scale), B, M, R, ptr(sigT), ptr(tiles), int(tiles.shape[0]), ptr(mu),
+             float(alpha), float(kappa), int(bool(accumulate)), int(p0), int(npairs), ptr(out))
+        if after_group is not None:
+            after_group(k)
     return out
+
+
+def pairs_before_row(R, r0):
+    """number of site pairs (r, r' >= r) with r < r0 in the launch order of jvmc_rbm_gram_S_i8"""
+    return r0 * R - r0 * (r0 - 1) // 2
 
 
 # ---- which Gram kernel.  The int8 digits resolve 2^-41 of each column's MAXIMUM, and the dropped digit pairs (level >= 7)
@@ -358,7 +370,7 @@ def rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out=None, accumulate=False):
 # if more than 1/16 of the samples are outliers the whole Gram runs in fp64.
 I8_MAX_PREDICTED_ERROR = float(os.environ.get("JVMC_I8_MAX_ERROR", "2e-12"))
 I8_OUTLIER_T = 16.0
-LAST_GRAM = {"backend": None, "tail_ratios": None, "predicted_error": None, "outlier_rows": 0}
+LAST_GRAM = {"backend": None, "tail_ratios": None, "predicted_error": None, "outlier_rows": 0, "grouped": False}
 
 
 def i8_tail_ratios(Y, return_scratch=False):
@@ -375,7 +387,7 @@ def i8_predicted_error(r1, r2, B):
     return 0.3 * 4.0 * 2.0 ** -40 * r1 * r2 / max(B, 1) ** 0.5
 
 
-def rbm_gram_S_auto(Y, sigT, mu, alpha, kappa, out=None, s=None, hasBias=False):
+def rbm_gram_S_auto(Y, sigT, mu, alpha, kappa, out=None, s=None, hasBias=False, pair_groups=None, after_group=None):
     """A by the int8 tensor-core kernel; heavy-tailed data (see above) is split: outlier samples through the fp64 DMMA
     kernel, the bulk through the int8 kernel, so that the entry-wise error stays below I8_MAX_PREDICTED_ERROR.
     s: configurations [B, N] (needed to re-pack the signs of the outlier samples; without it the whole matrix falls back to
@@ -386,9 +398,9 @@ def rbm_gram_S_auto(Y, sigT, mu, alpha, kappa, out=None, s=None, hasBias=False):
     top = torch.topk(r, 2 if r.numel() > 1 else 1).values.tolist()
     r1, r2 = top[0], top[-1]
     err = i8_predicted_error(r1, r2, B)
-    LAST_GRAM.update(backend="i8", tail_ratios=(r1, r2), predicted_error=err, outlier_rows=0)
+    LAST_GRAM.update(backend="i8", tail_ratios=(r1, r2), predicted_error=err, outlier_rows=0, grouped=pair_groups is not None)
     if err <= I8_MAX_PREDICTED_ERROR:
-        return rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out)
+        return rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out, pair_groups=pair_groups, after_group=after_group)
     if s is not None:
         flag = torch.empty(B, dtype=torch.uint8, device=Y.device)
         call("jvmc_i8_outlier_rows", ptr(Y), B, M, ptr(scratch), float(I8_OUTLIER_T), ptr(flag))
@@ -401,8 +413,9 @@ def rbm_gram_S_auto(Y, sigT, mu, alpha, kappa, out=None, s=None, hasBias=False):
             A = rbm_gram_S(Y[idx].contiguous(), sig_out, mu, alpha, kappa, out)      # exact, with the mean correction
             Yb = Y.clone()
             Yb[idx] = 0
-            return rbm_gram_S_i8(Yb, sigT, mu, alpha, kappa, A, accumulate=True)
-    LAST_GRAM.update(backend="dmma")
+            return rbm_gram_S_i8(Yb, sigT, mu, alpha, kappa, A, accumulate=True, pair_groups=pair_groups,
+                                 after_group=after_group)
+    LAST_GRAM.update(backend="dmma", grouped=False)
     return rbm_gram_S(Y, sigT, mu, alpha, kappa, out)
 
 
@@ -435,6 +448,18 @@ def hermitian_pack_blocks(A, M, packed=None, unpack=False):
     assert packed.numel() == n
     call("jvmc_hermitian_pack_blocks", ptr(A), Pc, int(M), ptr(packed), int(bool(unpack)))
     return packed
+
+
+def hermitian_pack_rows(A, M, row0, nrows, packed, unpack=False):
+    """rows [row0, row0 + nrows) of the upper block triangle <-> their slice of the packed buffer (packed: the WHOLE buffer)."""
+    assert A.dtype == CPX and A.is_contiguous() and A.shape[0] == A.shape[1]
+    call("jvmc_hermitian_pack_rows", ptr(A), int(A.shape[0]), int(M), int(row0), int(nrows), ptr(packed), int(bool(unpack)))
+    return packed
+
+
+def hermitian_packed_offset(Pc, M, r):
+    """first element of block row r in the packed upper block triangle"""
+    return M * (r * Pc - M * r * (r - 1) // 2)
 
 
 def hermitian_mirror_blocks(A, M):

@@ -239,6 +239,65 @@ class RBMGradientObs(SampledObs):
             return torch.cat(parts)[:, None]
         return Fk.reshape(-1)[:, None]
 
+    def _gram_over_ranks(self, Y, mu, alpha, kappa):
+        """The Hermitian Gram matrix of this rank's samples, summed over ranks.  With several ranks and the int8 kernel
+        the site pairs are launched in groups of block rows (r0 ascending): as soon as the launches of a group are
+        enqueued its rows of the upper block triangle are final on this rank, and a side stream packs, all-reduces
+        (NCCL) and unpacks them while the next group is computed; the lower triangle is rebuilt by conjugate
+        transposition at the end.  Replaces the host-staged MPI.Allreduce of S inside covar()
+        (reference jVMC/mpi_wrapper.py:114-147 via stats.py:245)."""
+        gram = _gram_backend()
+        kw = {"s": self._s, "hasBias": self.hasBias} if gram is K.rbm_gram_S_auto else {}
+        overlap = mpi.commSize > 1 and gram is not K.rbm_gram_S and os.environ.get("JVMC_GRAM_OVERLAP", "1") != "0"
+        if not overlap:
+            A = gram(Y, self._sigT, mu, alpha, kappa, **kw)
+            # Hermitian: from 8 ranks on communicate the upper block triangle only (half the bytes) and rebuild the
+            # rest; below that the pack / unpack / mirror passes cost more than the saved NVLink time (measured)
+            half = os.environ.get("JVMC_HERMITIAN_ALLREDUCE")
+            half = (mpi.commSize >= 8) if half is None else (half == "1")
+            return mpi.all_reduce_hermitian_blocks(A, self.M) if half else mpi._all_reduce_sum(A)
+        import torch.distributed as dist
+        R, M = self.R, self.M
+        Pc = R * M
+        # block-row groups with shrinking numbers of pairs: the reduction of the last group is the only exposed one
+        fr, bounds, acc = (0.4, 0.7, 0.9, 1.0), [0], 0
+        total = R * (R + 1) // 2
+        for f in fr:
+            r = bounds[-1]
+            while r < R and K.pairs_before_row(R, r) < f * total:
+                r += 1
+            if r > bounds[-1]:
+                bounds.append(r)
+        if bounds[-1] != R:
+            bounds.append(R)
+        groups = [(K.pairs_before_row(R, a), K.pairs_before_row(R, b) - K.pairs_before_row(R, a))
+                  for a, b in zip(bounds[:-1], bounds[1:])]
+        packed = torch.empty(K.hermitian_packed_offset(Pc, M, R), dtype=torch.complex128, device=Y.device)
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=Y.device, priority=-1)
+        holder = {}
+
+        def after_group(k):
+            A_ = holder["A"]
+            ev = torch.cuda.Event()
+            ev.record(main)
+            ra, rb = bounds[k], bounds[k + 1]
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                K.hermitian_pack_rows(A_, M, ra * M, (rb - ra) * M, packed)
+                sl = packed[K.hermitian_packed_offset(Pc, M, ra):K.hermitian_packed_offset(Pc, M, rb)]
+                dist.all_reduce(torch.view_as_real(sl), op=dist.ReduceOp.SUM)
+                K.hermitian_pack_rows(A_, M, ra * M, (rb - ra) * M, packed, unpack=True)
+        A = torch.empty((Pc, Pc), dtype=torch.complex128, device=Y.device)
+        holder["A"] = A
+        A = gram(Y, self._sigT, mu, alpha, kappa, A, pair_groups=groups, after_group=after_group, **kw)
+        if not K.LAST_GRAM.get("grouped", False) and gram is K.rbm_gram_S_auto:
+            # the whole matrix went through the fp64 kernel (no groups ran): plain reduction
+            return mpi._all_reduce_sum(A)
+        main.wait_stream(side)
+        K.hermitian_mirror_blocks(A, M)
+        return A
+
     def gram_A(self):
         """A[(r,j),(r',l)] = <conj(O) O>_c, complex Hermitian [R*M, R*M] (global)."""
         if self._A is None:
@@ -247,19 +306,13 @@ class RBMGradientObs(SampledObs):
                 self._sigT = K.pack_sigma(self._s, self.hasBias)
             p = self._p
             kappa = 1.0 / mpi.commSize
-            # backend: "i8" = tcgen05 INT8 tensor cores with error-free splitting (fp64-equivalent, default; the fp64 DMMA
-            #          kernel takes over for heavy-tailed tau columns, kernels.rbm_gram_S_auto), "i8only", "dmma"
-            gram = _gram_backend()
-            kw = {"s": self._s, "hasBias": self.hasBias} if gram is K.rbm_gram_S_auto else {}
+            # backend: "i8" = tcgen05 INT8 tensor cores with error-free splitting (fp64-equivalent, default; outlier
+            #          samples of heavy-tailed tau columns go through the fp64 kernel, kernels.rbm_gram_S_auto),
+            #          "i8only", "dmma" = fp64 DMMA
             if self._uniform is not None:
-                A = gram(self._tau, self._sigT, mu, float(self._uniform), kappa, **kw)
+                self._A = self._gram_over_ranks(self._tau, mu, float(self._uniform), kappa)
             else:
-                A = gram(self._tau * torch.sqrt(p)[:, None], self._sigT, mu, 1.0, kappa, **kw)
-            # Hermitian: from 8 ranks on communicate the upper block triangle only (half the bytes) and rebuild the
-            # rest; below that the pack / unpack / mirror passes cost more than the saved NVLink time (measured)
-            half = os.environ.get("JVMC_HERMITIAN_ALLREDUCE")
-            half = (mpi.commSize >= 8) if half is None else (half == "1")
-            self._A = mpi.all_reduce_hermitian_blocks(A, self.M) if half else mpi._all_reduce_sum(A)
+                self._A = self._gram_over_ranks(self._tau * torch.sqrt(p)[:, None], mu, 1.0, kappa)
         return self._A
 
     def weighted_second_moment(self, w2):
@@ -267,13 +320,8 @@ class RBMGradientObs(SampledObs):
         w2 >= 0 -- the same Gram kernel as gram_A with another weight vector (SNR second moments, util/tdvp.py)."""
         if self._sigT is None:
             self._sigT = K.pack_sigma(self._s, self.hasBias)
-        gram = _gram_backend()
         Y = self._tau * torch.sqrt(w2.to(torch.float64))[:, None]
-        kw = {"s": self._s, "hasBias": self.hasBias} if gram is K.rbm_gram_S_auto else {}
-        A2 = gram(Y, self._sigT, torch.zeros((self.R, self.M), dtype=torch.complex128, device=Y.device), 1.0, 0.0, **kw)
-        half = os.environ.get("JVMC_HERMITIAN_ALLREDUCE")
-        half = (mpi.commSize >= 8) if half is None else (half == "1")
-        return mpi.all_reduce_hermitian_blocks(A2, self.M) if half else mpi._all_reduce_sum(A2)
+        return self._gram_over_ranks(Y, torch.zeros((self.R, self.M), dtype=torch.complex128, device=Y.device), 1.0, 0.0)
 
     def _expand_S0(self):
         A = self.gram_A()
