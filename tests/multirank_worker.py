@@ -90,4 +90,8 @@ def main(out, total_chains, total_samples, mu, wscale):
 
 
 if __name__ == "__main__":
+    import faulthandler
+    import signal
+    faulthandler.register(signal.SIGALRM, all_threads=True, chain=False)
+    faulthandler.dump_traceback_later(200, exit=True)        # a hung collective must not outlive the test (frees the GPU)
     main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4]), float(sys.argv[5]))

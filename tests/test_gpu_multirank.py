@@ -34,8 +34,16 @@ def _run(world, out, chains, samples, mu, wscale, gram):
         env["JVMC_DIST_BACKEND"] = "nccl" if torch.cuda.device_count() >= world else "gloo"
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                "--master-addr", "127.0.0.1", "--master-port", str(_free_port())] + worker
-    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:]
+    # own process group: a timeout kills the launcher AND the ranks
+    proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, start_new_session=True)
+    try:
+        out_, _ = proc.communicate(timeout=300)
+    except subprocess.TimeoutExpired:
+        import signal
+        os.killpg(proc.pid, signal.SIGKILL)
+        out_, _ = proc.communicate()
+        raise AssertionError("multi-rank worker timed out:\n" + out_[-3000:])
+    assert proc.returncode == 0, out_[-3000:]
     return [np.load(out + ".rank%d.npz" % k) for k in range(world)]
 
 

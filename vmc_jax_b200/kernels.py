@@ -407,6 +407,10 @@ def rbm_gram_S_auto(Y, sigT, mu, alpha, kappa, out=None, s=None, hasBias=False, 
         idx = torch.nonzero(flag).reshape(-1)
         nout = int(idx.numel())
         bulk_err = i8_predicted_error(I8_OUTLIER_T, I8_OUTLIER_T, B)
+        if nout == 0 and bulk_err <= max(I8_MAX_PREDICTED_ERROR, 2e-11):
+            # nothing stands out by more than I8_OUTLIER_T column rms (small B: the prediction is dominated by 1/sqrt(B))
+            LAST_GRAM.update(predicted_error=bulk_err)
+            return rbm_gram_S_i8(Y, sigT, mu, alpha, kappa, out, pair_groups=pair_groups, after_group=after_group)
         if 0 < nout <= B // 16 and bulk_err <= max(I8_MAX_PREDICTED_ERROR, 2e-11):
             LAST_GRAM.update(backend="i8+dmma", outlier_rows=nout, predicted_error=bulk_err)
             sig_out = pack_sigma(_c(s, I32)[idx].contiguous(), hasBias)

@@ -292,8 +292,10 @@ class RBMGradientObs(SampledObs):
         holder["A"] = A
         A = gram(Y, self._sigT, mu, alpha, kappa, A, pair_groups=groups, after_group=after_group, **kw)
         if not K.LAST_GRAM.get("grouped", False) and gram is K.rbm_gram_S_auto:
-            # the whole matrix went through the fp64 kernel (no groups ran): plain reduction
-            return mpi._all_reduce_sum(A)
+            # this rank sent the whole matrix through the fp64 kernel (no groups ran).  The backend choice is rank-local
+            # (it depends on the rank's samples), the sequence of collectives must not be: reduce the same row groups
+            for k in range(len(groups)):
+                after_group(k)
         main.wait_stream(side)
         K.hermitian_mirror_blocks(A, M)
         return A
