@@ -291,8 +291,16 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
   double* elc = reinterpret_cast<double*>(bufAll + (size_t)NW * 2 * JT * 32);
   double* part = elc + N;                          // [2][WPCH] partial products (WPCH > 1)
   uint32_t* sbitsAll = reinterpret_cast<uint32_t*>(part + 2 * WPCH);
+  // two mbarriers per warp: "row of the even / odd step has landed" (TMA bulk copy, complete_tx)
+  uint64_t* barAll = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sbitsAll + NW * 32) + 7) & ~(uintptr_t)7);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(barAll + 2 * warp)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(barAll + 2 * warp + 1)));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   for (int i = threadIdx.x; i < N; i += NW * 32) elc[i] = exp(a.mu * a.lc[i].x);
   for (int i = threadIdx.x; i < 2 * NW * JT * 32; i += NW * 32) bufAll[i] = cmk(0.0, 0.0);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // zero fill (generic proxy) before the TMA writes
   __syncthreads();
   if (chain >= a.C) return;  // WPCH == 1 only (whole warp exits together; no further block-wide barriers there)
   cplx* buf0 = bufAll + (size_t)warp * 2 * JT * 32;
@@ -336,16 +344,33 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
     }
     __syncwarp();
   };
-  // stage this warp's slice of row T_site into buffer `which`: a lane copies the elements it will read back itself
+  // stage this warp's slice of row T_site into buffer `which`: ONE bulk copy by the TMA engine (cp.async.bulk, SASS
+  // UBLKCP) that completes on the buffer's mbarrier -- no per-lane copy instructions and no L1 involvement (the
+  // per-lane cp.async version kept the L1/shared pipe at 82 %).  The elements beyond M stay zero.
+  const unsigned rowBytes = (unsigned)(min(32 * JT, M - jbase) * (int)sizeof(cplx));
+  const unsigned barAddr = (unsigned)__cvta_generic_to_shared(barAll + 2 * warp);
   auto prefetch_row = [&](int site, int which) {
-    const cplx* src = a.T + (size_t)site * M + jbase + lane;
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(buf0 + which * JT * 32 + lane);
-#pragma unroll
-    for (int k = 0; k < JT; ++k)
-      if (jbase + lane + 32 * k < M)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + (unsigned)(k * 32 * sizeof(cplx))),
-                     "l"(src + 32 * k) : "memory");
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    __syncwarp();                                    // every lane is done reading this buffer (step st - 1)
+    if (lane == 0) {
+      const cplx* src = a.T + (size_t)site * M + jbase;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(buf0 + which * JT * 32);
+      const unsigned bar = barAddr + 8u * (unsigned)which;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(rowBytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                   "l"(src), "r"(rowBytes), "r"(bar) : "memory");
+    }
+  };
+  auto wait_row = [&](int which, unsigned parity) {
+    const unsigned bar = barAddr + 8u * (unsigned)which;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MC_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni MC_WAIT_DONE;\n"
+        "bra.uni MC_WAIT_LOOP;\n"
+        "MC_WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
   };
   // product over all hidden units of the chain from this warp's partial product
   auto chain_prod = [&](double p, long long st) {
@@ -391,7 +416,7 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
     const bool g = (a.proposer == 1) && (__umulhi(rc.y, 5u) == 0u);
     const double u = u01_from_bits(rc.z, rc.w);
     const cplx* tv = buf0 + (int)(st & 1) * JT * 32 + lane;   // row of this step; the other buffer receives the next one
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    wait_row((int)(st & 1), (unsigned)((st >> 1) & 1));   // buffer st & 1 is used every second step: phase st / 2
     uint4 rn = rc;
     if (st + 1 < total) {
       draw(st + 1, rn);
@@ -505,7 +530,8 @@ template <int JT, int WPCH>
 int launch_flip(const McmcArgs& a, cudaStream_t stream) {
   constexpr int CPB = (WPCH == 1) ? MC_WPC : 1;
   constexpr int NW = CPB * WPCH;
-  size_t smem = (size_t)2 * NW * JT * 32 * sizeof(cplx) + (size_t)(a.N + 2 * WPCH) * sizeof(double) + NW * 32 * sizeof(uint32_t);
+  size_t smem = (size_t)2 * NW * JT * 32 * sizeof(cplx) + (size_t)(a.N + 2 * WPCH) * sizeof(double) + NW * 32 * sizeof(uint32_t) +
+                8 + (size_t)2 * NW * sizeof(uint64_t);
   if (smem > 227 * 1024) return JVMC_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(rbm_mcmc_flip_kernel<JT, WPCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
