@@ -46,7 +46,11 @@ WORKLOADS = {
     "tfim1d_L20_cpxrbm_a2_2p12": ((20,), -0.7, 2, False, 2 ** 12, 500),
     "tfim1d_L40_cpxrbm_a2_bias_2p16": ((40,), -0.7, 2, True, 2 ** 16, 2368),
     "tfim2d_6x6_cpxrbm_a4_2p14": ((6, 6), 3.04, 4, False, 2 ** 14, 1184),
+    # BASELINE configs[4]: 2^17 samples per GPU (2^20 on 8), MinSR step (run_minsr_workload)
+    "tfim2d_20x20_cpxrbm_a4_2p20": ((20, 20), 3.04, 4, False, 2 ** 17, 1184),
 }
+MINSR_WORKLOAD = "tfim2d_20x20_cpxrbm_a4_2p20"
+MINSR_METRIC = "MinSR step samples/sec (sample + E_loc + tangent kernel T + pinv + update)"
 DEFAULT_WORKLOAD = "tfim2d_10x10_cpxrbm_a4_2p16"
 _REAL_STDOUT = 1
 METRIC = "VMC step samples/sec (sample + E_loc + S/F)"
@@ -203,6 +207,34 @@ def cpu_tdvp_step(L=20, alpha=2, nsamp=4096, chains=500, seed=0):
                      "residual": float(res), "update_norm": float(np.linalg.norm(upd))}
 
 
+def cpu_minsr_step(shape, g, alpha, nsamp, chains, rng_seed=0):
+    """One MinSR step of BASELINE configs[4] by the reference's algorithm on the host (oracle port), bounded sample:
+    Metropolis with a full forward pass per proposal, s' -> psi(s') E_loc, dense holomorphic gradients [n, 2 P_c],
+    T = Obar Obar^dagger, pinv(T) e, update = -Obar^dagger x (jVMC/util/minsr.py:53-80).  Returns (seconds, detail)."""
+    from oracle import rbm as orbm, bfo as obfo, sampling as osamp, stats as ostats, solve as osolve
+    N = int(np.prod(shape))
+    M = alpha * N
+    W, b = o1_weights(N, M, False)
+    ham = obfo.Tables(obfo.tfim_strings(shape, g, -1.0))
+    f = lambda s: orbm.cpx_rbm_logpsi(s, W, b)
+    spc = max(1, nsamp // chains)
+    therm = max(1, int(round(25.0 * spc / 110.0)))      # 25 sweeps per 110 emitted samples per chain, as in the workload
+    smp = osamp.MCSampler(lambda s: np.real(f(s)), N, numChains=chains, proposer="spin_flip",
+                          thermalizationSweeps=therm, sweepSteps=N, seed=rng_seed)
+    t0 = time.perf_counter()
+    cfg, _ = smp.sample(spc * chains)
+    lp = f(cfg)
+    t1 = time.perf_counter()
+    E = obfo.get_O_loc(ham, cfg, f, 0.0, logPsiS=lp)
+    t2 = time.perf_counter()
+    p = np.ones(cfg.shape[0]) / cfg.shape[0]
+    oE, oG = ostats.SampledObs(E, p), ostats.SampledObs(orbm.gradients_holomorphic(cfg, W, b), p)
+    upd = osolve.minsr_solve(oE, oG, True, pinvTol=1e-8)
+    t3 = time.perf_counter()
+    return t3 - t0, {"samples": int(cfg.shape[0]), "t_sample_s": t1 - t0, "t_eloc_s": t2 - t1, "t_minsr_s": t3 - t2,
+                     "update_max_abs": float(np.abs(upd).max())}
+
+
 def run_reference_arm(args, wl):
     """`--impl reference`: the reference's own algorithm for the path, on the host cores (jax cannot be installed in this
     image, so this is the oracle port, kind = "port").  Rank 0 alone works; every step is a bounded sample."""
@@ -230,6 +262,26 @@ def run_reference_arm(args, wl):
         return
     shape, g, alpha, bias, nsamp_gpu, chains_gpu = WORKLOADS[wl]
     nsamp, chains = REF_SAMPLES, REF_CHAINS
+    if wl == MINSR_WORKLOAD:
+        for _ in range(min(args.warmup, 1)):
+            cpu_minsr_step(shape, g, alpha, nsamp, chains, rng_seed=1000)
+        times = []
+        for k in range(args.steps):
+            t, detail = cpu_minsr_step(shape, g, alpha, nsamp, chains, rng_seed=k)
+            times.append(t)
+        sec = float(np.mean(times))
+        value = nsamp / sec
+        sample = ("oracle port of the reference algorithm (jax not installable): %d samples/step from %d chains, full forward "
+                  "pass per proposal, s'->psi(s') E_loc, dense holomorphic gradients, MinSR on all %d samples" % (nsamp, chains, nsamp))
+        line = {"metric": MINSR_METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl, "samples_per_step": nsamp, "bounded_sample": True},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "detail": detail}
+        print(json.dumps(line), flush=True)
+        return
     for _ in range(args.warmup):
         cpu_reference_step(shape, g, alpha, bias, nsamp, chains, rng_seed=1000)
     times = []
@@ -277,6 +329,8 @@ def main():
                     help="vmc: samples/s of sample + E_loc + S/F at configs[1] (headline); tdvp: ms of one complete "
                          "TDVP/SR step at configs[0], the size the reference's CPU path runs in full")
     ap.add_argument("--samples", type=int, default=0, help="override samples per GPU")
+    ap.add_argument("--minsr-samples", type=int, default=16384,
+                    help="config-5 workload: global number N_T of samples the MinSR kernel T is formed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tdvp", action="store_true")
     ap.add_argument("--gram", default="i8", choices=["i8", "dmma"], help="Gram backend: tcgen05 INT8 (default) or fp64 DMMA")
@@ -289,6 +343,9 @@ def main():
 
     if args.metric == "tdvp":
         run_tdvp_metric(args)
+        return
+    if wl == MINSR_WORKLOAD:
+        run_minsr_workload(args)
         return
     os.environ["JVMC_GRAM_BACKEND"] = args.gram
     # stdout carries exactly ONE JSON line: everything libraries print to fd 1 (e.g. "NCCL version ..." at communicator
@@ -681,6 +738,202 @@ def run_tdvp_metric(args):
         os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
     if mpi.commSize > 1:
         import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_minsr_workload(args):
+    """BASELINE configs[4] / north_star target lattice: 2D TFIM 20x20, CpxRBM alpha=4 (P_c = 640 000 complex parameters),
+    2^17 samples per GPU (2^20 on 8 GPUs), one MinSR step (reference jVMC/util/minsr.py:82-165):
+      sample + E_loc over ALL samples (<E>, Var E global), then the params > samples solve on N_T = --minsr-samples of
+      them (every (N_s/N_T)-th sample of each rank, uniform weights): T = 2 Obar Obar^dagger formed ONCE over the ranks
+      (all-gathered Khatri-Rao factors, rank k computes the k-th range of tile pairs, SUM all-reduce), pinv(T) e
+      (replicated eigen-decomposition), update = -Obar^dagger x (local moments, all-reduced).
+    The dense kernel on all 2^20 samples is 17.6 TB -- infeasible on any number of B200s, as it is for the reference."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    import torch.distributed as dist
+    import vmc_jax_b200 as jVMC
+    from vmc_jax_b200 import kernels as K, mpi_wrapper as mpi, _lib as _jl
+    from vmc_jax_b200.stats import SampledObs, RBMGradientObs
+    from vmc_jax_b200.util.minsr import pinv_hermitian_apply
+    import vmc_jax_b200.operator as op
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    mpi.init_distributed()
+    rank, world = mpi.rank, mpi.commSize
+    dev = jVMC.global_defs.myDevice
+    wl = args.workload
+    shape, g, alpha, bias, nsamp, chains = WORKLOADS[wl]
+    if args.samples:
+        nsamp = args.samples
+    Lx, Ly = shape
+    N = Lx * Ly
+    M = alpha * N
+    Pc = N * M
+    nT_loc = max(64, args.minsr_samples // world)
+    psi = jVMC.vqs.NQS(jVMC.nets.CpxRBM(numHidden=M, bias=bias), seed=1234)
+    psi(torch.zeros((1, 1) + shape, dtype=torch.int32, device=dev))
+    W, b = o1_weights(N, M, bias)
+    P_host = torch.as_tensor(flat_params(W, b)).pin_memory()
+    psi.set_parameters(P_host.to(dev))
+    H = op.BranchFreeOperator()
+    for x in range(Lx):
+        for y in range(Ly):
+            l = x * Ly + y
+            H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz(x * Ly + (y + 1) % Ly))))
+            H.add(op.scal_opstr(-1., (op.Sz(l), op.Sz(((x + 1) % Lx) * Ly + y))))
+            H.add(op.scal_opstr(g, (op.Sx(l),)))
+    smp = jVMC.sampler.MCSampler(psi, shape, 4321, updateProposer=jVMC.sampler.propose_spin_flip, numChains=chains,
+                                 sweepSteps=N, thermalizationSweeps=25, numSamples=nsamp * world)
+    smp.refreshEvery = 8
+    minsr = jVMC.util.MinSR(smp, pinvTol=1e-8)
+
+    def subset(s, Eloc):
+        nl = s.shape[1]
+        idx = torch.arange(nT_loc, device=dev) * (nl // nT_loc) if nl >= nT_loc else torch.arange(nl, device=dev)
+        ps = torch.full((1, idx.numel()), 1.0 / (idx.numel() * world), dtype=torch.float64, device=dev)
+        return s[:, idx].contiguous(), Eloc[:, idx].contiguous(), ps
+
+    def step():
+        s, logPsi, p = smp.sample()
+        Eloc = H.get_O_loc(s, psi, logPsi, 0.0)
+        E = SampledObs(Eloc, p)
+        Emean, Evar = E.mean()[0], E.var()[0]
+        ss, Es, ps = subset(s, Eloc)
+        upd = minsr.solve(SampledObs(Es, ps), RBMGradientObs(psi, ss, ps), holomorphic=True)
+        return s, Emean, Evar, upd
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    nLocal, nGlobal = out[0].shape[1], smp.get_last_number_of_samples()
+    del out
+    clocks = ClockSampler(dev.index if dev.index is not None else 0)
+    clocks.start()
+    time.sleep(0.3)
+    launches0 = _jl.LAUNCHES
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    launches = _jl.LAUNCHES - launches0
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    energy = complex(out[1].item())
+    upd_norm = float(out[3].abs().max())
+    del out
+    # e2e: parameters from pinned host memory, <E>, Var E and the update read back every step
+    res_host = torch.empty(2 + 4 * Pc, dtype=torch.float64).pin_memory()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        psi.set_parameters(P_host.to(dev, non_blocking=True))
+        s, Emean, Evar, upd = step()
+        res = torch.cat([Emean.real.reshape(1).to(torch.float64), Evar.reshape(1).to(torch.float64),
+                         torch.view_as_real(upd.to(torch.complex128).contiguous()).reshape(-1)])
+        res_host.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    del s, Emean, Evar, upd, res
+
+    # per-phase breakdown (diagnostic): the pieces of MinSR.solve called one by one, max over ranks
+    def timed(fn):
+        barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); r = fn(); b_.record(); torch.cuda.synchronize()
+        return r, max_over_ranks(a.elapsed_time(b_))
+    ph = {}
+    (s, logPsi, p), ph["sampling_ms"] = timed(lambda: smp.sample())
+    Eloc, ph["eloc_ms"] = timed(lambda: H.get_O_loc(s, psi, logPsi, 0.0))
+    ss, Es, ps = subset(s, Eloc)
+    G, ph["tau_of_subset_ms"] = timed(lambda: RBMGradientObs(psi, ss, ps))
+    Eo = SampledObs(Es, ps)
+    mu, _ = timed(lambda: G.kr_mean())
+    if world > 1:
+        (s_all, tau_all, p_all, v_all), ph["gather_factors_ms"] = timed(
+            lambda: (mpi.gather(G._s[None]), mpi.gather(G._tau[None]), mpi.gather(G._p[None]),
+                     mpi.gather(K.rbm_krmatvec(G._s, G._tau, mu.conj().contiguous(), False)[None])))
+        T, ph["tangent_kernel_tiles_ms"] = timed(
+            lambda: K.rbm_gram_T(s_all, tau_all, p_all, mu, False, 2.0, part=(rank, world), v=v_all))
+        T, ph["allreduce_T_ms"] = timed(lambda: mpi._all_reduce_sum(T))
+        del s_all, tau_all, p_all, v_all
+    else:
+        T, ph["tangent_kernel_tiles_ms"] = timed(lambda: K.rbm_gram_T(G._s, G._tau, G._p, mu, False, 2.0))
+    e_all = mpi.gather(Eo._data).reshape(-1).to(T.dtype)
+    x, ph["pinv_eigh_replicated_ms"] = timed(lambda: pinv_hermitian_apply(T, 1e-8, e_all))
+    del T
+    _, ph["update_contraction_ms"] = timed(lambda: G.minsr_contract(x))
+    ph["acceptance"] = float(smp.acceptance_ratio())
+    NT = nT_loc * world
+    t_k = ph["tangent_kernel_tiles_ms"]
+    ph["tangent_kernel_tflops_per_gpu"] = 4.0 * NT * NT * M / world / (t_k * 1e-3) / 1e12
+    # roofline of the dominant OWN kernel (the sampler sweep; the replicated cuSOLVER eigen-decomposition is library code)
+    try:
+        n = 8192
+        a_ = torch.randn(n, n, dtype=torch.float64, device=dev)
+        c_ = torch.empty_like(a_)
+        best = 1e9
+        for _ in range(4):
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record(); torch.matmul(a_, a_, out=c_); x1.record(); torch.cuda.synchronize()
+            best = min(best, x0.elapsed_time(x1))
+        fp64_peak, peak_src = 2.0 * n ** 3 / (best * 1e-3) / 1e12, "cuBLAS DGEMM 8192^3 measured live (best of 4)"
+        del a_, c_
+    except Exception as ex:  # pragma: no cover
+        fp64_peak, peak_src = 37.0, "fallback 37 TF/s (tools/fp64_probe.cu); live DGEMM failed: %r" % (ex,)
+    acc = ph["acceptance"]
+    props = chains * N * (25 + nLocal // chains)
+    flop = props * M * (14.0 + 30.0 * acc)
+    tf = flop / (ph["sampling_ms"] * 1e-3) / 1e12
+    roofline = {"bound": "fp64", "kernel": "rbm_mcmc_flip_kernel (sampler sweep, 4 warps per chain) + logpsi of the emitted samples",
+                "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak, "traffic": None,
+                "peak_source": peak_src, "launch_ms": ph["sampling_ms"],
+                "note": "K M (14 + 30 acc) flop per proposal; the weight rows (10.2 MB) are L2-resident, HBM traffic is "
+                        "4N + 16 bytes per emitted sample -- the fp64 pipe, not HBM or the tensor pipe, bounds this workload's "
+                        "own kernels; the step is dominated by the replicated cuSOLVER eigen-decomposition of T"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            ref = reference_arm_subprocess(["--workload", wl, "--steps", "2", "--warmup", "0"])
+            cpu = dict(ref["cpu_baseline"], steps=ref["steps"], ms_per_step=ref["ms_per_step"], detail=ref.get("detail"))
+        except Exception as ex:  # pragma: no cover
+            cpu = {"error": repr(ex)}
+    if rank == 0:
+        line = {"metric": MINSR_METRIC, "value": nGlobal / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl, "lattice": list(shape), "g": g, "numHidden": M, "P_complex": Pc,
+                           "samples_per_gpu": nLocal, "samples_global": nGlobal, "numChains_per_gpu": chains,
+                           "minsr_samples_global": NT, "minsr_samples_per_gpu": nT_loc, "pinvTol": 1e-8,
+                           "l2": "inputs_exceed_L2 (tau of the MinSR subset %.0f MB, T %.1f GB)" % (NT * M * 16 / 1e6, NT * NT * 16 / 1e9),
+                           "parallelism": "chains sharded over %d rank(s); T tile pairs sharded + SUM all-reduce; eigh replicated" % world},
+                "e2e": {"value": nGlobal / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(P_host.numel() * 8),
+                        "d2h_bytes_per_step": int(res_host.numel() * 8), "steps": args.steps,
+                        "note": "parameters H2D from pinned memory; <E>, Var E and the MinSR update D2H"},
+                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+                "phases_ms": ph, "energy_mean": [energy.real, energy.imag], "update_max_abs": upd_norm}
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    if world > 1:
         dist.destroy_process_group()
 
 

@@ -133,8 +133,11 @@ int jvmc_rbm_gram_S_i8(const signed char* digits, const double* scale, long long
  * ([B][ceil(R/32)] words).  T row-major [B,B] complex128, fully populated Hermitian.  scale = 2: reference's doubled
  * holomorphic layout. */
 int jvmc_pack_sigma_rows(const int32_t* s, long long B, int N, int hasBias, unsigned int* sigR, void* stream);
+long long jvmc_rbm_gram_T_tiles(long long B);   /* tile pairs of the Hermitian half */
+/* [tile0, tile0 + ntiles) of them (ntiles <= 0: all): disjoint ranges on different ranks + one SUM all-reduce form T once */
 int jvmc_rbm_gram_T(const double* Y, long long B, int M, int R, const unsigned int* sigR, const double* p,
-                    const double* v, const double* c, double scale, double* T, void* stream);
+                    const double* v, const double* c, double scale, long long tile0, long long ntiles, double* T,
+                    void* stream);
 
 /* S = q(S0) (+ diagonal shift) in the reference's flat layout from A: jVMC/util/tdvp.py:140-146.
  * mode 0: Re -> double[P,P]; mode 1: i*Im -> complex128[P,P]; column-major. */

@@ -66,6 +66,12 @@ def main(out, total_chains, total_samples, mu, wscale):
         _lib.call("jvmc_comm_reduce_scatter_sum_f64", comm, _lib.ptr(sb), _lib.ptr(rb), 8)
         tot = sum(torch.arange(8 * world, dtype=torch.float64, device="cuda") + r for r in range(world))
         comm_err = max(comm_err, float((rb - tot[8 * rank:8 * rank + 8]).abs().max()))
+    # MinSR on the same samples (reference jVMC/util/minsr.py:53-80): the tangent kernel is formed once over the ranks
+    # (rank k computes the k-th range of tile pairs, SUM all-reduce), pinv replicated, -Obar^dagger x all-reduced
+    Gh = RBMGradientObs(psi, s, p)
+    Tk = Gh.tangent_kernel()
+    minsr = jVMC.util.MinSR(smp, pinvTol=1e-8)
+    upd_minsr = minsr.solve(E, Gh, holomorphic=True)
     acc = smp.acceptance_ratio()
     # the half-volume Hermitian all-reduce (default from 8 ranks on) against the plain one, on rank-dependent data
     g = torch.Generator(device="cuda").manual_seed(100 + rank)
@@ -82,7 +88,8 @@ def main(out, total_chains, total_samples, mu, wscale):
              A=A.cpu().numpy(), update=upd.cpu().numpy(), update2=upd2.cpu().numpy(), comm_err=np.array([comm_err]),
              capi_comm=np.array([comm is not None]), residual=np.array([float(res)]), acc=np.array([float(acc)]),
              nglob=np.array([smp.get_last_number_of_samples()]), herm_err=np.array([herm_err]),
-             world=np.array([world]))
+             world=np.array([world]), T=Tk.cpu().numpy(), update_minsr=upd_minsr.cpu().numpy(),
+             params=psi.get_parameters().cpu().numpy())
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -84,4 +84,21 @@ def test_two_ranks_equal_one_rank(tmp_path, mu, wscale, gram):
         assert np.allclose(t["update2"], one["update2"], rtol=1e-6, atol=1e-7 * np.abs(one["update2"]).max())
         assert float(t["comm_err"][0]) == 0.0
         assert bool(t["capi_comm"][0]) == (torch.cuda.device_count() >= 2)
+        # MinSR: T rows / columns are ordered rank-major (gather), the one-rank run is time-major over all chains
+        assert t["T"].shape == (samples, samples)
+        i1 = np.arange(samples).reshape(-1, chains)
+        perm = np.concatenate([i1[:, k * (chains // 2):(k + 1) * (chains // 2)].reshape(-1) for k in range(2)])
+        T1 = one["T"][np.ix_(perm, perm)]
+        assert np.abs(t["T"] - T1).max() <= 1e-12 * np.abs(T1).max()
+        assert np.allclose(t["update_minsr"], one["update_minsr"], rtol=1e-6, atol=1e-8 * np.abs(one["update_minsr"]).max())
     assert np.array_equal(two[0]["A"], two[1]["A"])
+    assert np.array_equal(two[0]["T"], two[1]["T"])
+    # ... and the two-rank tangent kernel against the oracle (stats.py:332-336 on dense holomorphic gradients) on the
+    # gathered (rank-major) samples
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import rbm as orbm, stats as ostats
+    W, b = orbm.unflatten_params(two[0]["params"], N, 20, bias=True)
+    s_all = np.concatenate([t["configs"].reshape(-1, N) for t in two])
+    p_all = np.concatenate([t["p"].reshape(-1) for t in two])
+    T_ref = ostats.SampledObs(orbm.gradients_holomorphic(s_all, W, b), p_all).tangent_kernel()
+    assert np.abs(two[0]["T"] - T_ref).max() <= 1e-10 * np.abs(T_ref).max()

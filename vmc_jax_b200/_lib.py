@@ -88,7 +88,8 @@ _SIGS = {
     "jvmc_rbm_gram_S_i8": (c_int, [c_ptr, c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_dbl, c_dbl, c_int, c_ll, c_ll,
                                    c_ptr, c_ptr]),
     "jvmc_pack_sigma_rows": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr]),
-    "jvmc_rbm_gram_T": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr]),
+    "jvmc_rbm_gram_T_tiles": (c_ll, [c_ll]),
+    "jvmc_rbm_gram_T": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ll, c_ll, c_ptr, c_ptr]),
     "jvmc_pack_sigma": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr]),
     "jvmc_rbm_gram_S": (c_int, [c_ptr, c_ll, c_int, c_int, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_int, c_ptr]),
     "jvmc_expand_S": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_dbl, c_ptr, c_ptr]),

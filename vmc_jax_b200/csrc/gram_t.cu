@@ -86,13 +86,13 @@ __global__ void pack_sigma_rows_kernel(const int32_t* __restrict__ s, long long 
 __global__ void __launch_bounds__(32 * (T_NCW + 1), 1)
 gram_t_kernel(const cplx* __restrict__ Y, long long B, int M, int R, const uint32_t* __restrict__ sigR, int wordsR,
               const double* __restrict__ p, const cplx* __restrict__ v, const double* __restrict__ cptr, double scale,
-              cplx* __restrict__ T) {
+              cplx* __restrict__ T, long long tile0) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cplx* tiles = reinterpret_cast<cplx*>(smem_raw);  // [stage][2][T_TS][T_LD]
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)T_STAGES * 2 * T_TS * T_LD);
   uint64_t* empty = full + T_STAGES;
   int nb, mb;
-  tri_decode(blockIdx.x, nb, mb);   // mb <= nb
+  tri_decode(tile0 + blockIdx.x, nb, mb);   // mb <= nb
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long rowA0 = (long long)nb * T_TS, rowB0 = (long long)mb * T_TS;
   const int KT = (M + T_KC - 1) / T_KC;
@@ -210,8 +210,17 @@ extern "C" int jvmc_pack_sigma_rows(const int32_t* s, long long B, int N, int ha
 
 // T: [B, B] complex128 row-major, fully populated Hermitian.  scale = 2 reproduces the reference's doubled
 // holomorphic layout (tangent_kernel of [g, i g] data), scale = 1 the plain complex-parameter kernel.
+extern "C" long long jvmc_rbm_gram_T_tiles(long long B) {
+  const long long nT = (B + T_TS - 1) / T_TS;
+  return nT * (nT + 1) / 2;
+}
+
+// [tile0, tile0 + ntiles) of the jvmc_rbm_gram_T_tiles(B) tile pairs of the Hermitian half (ntiles <= 0: all): every
+// element of T is written by exactly one tile pair (both images), so ranks that take disjoint ranges into zero-initialised
+// buffers obtain the full kernel by one SUM all-reduce -- T is formed once over the ranks, not once per rank.
 extern "C" int jvmc_rbm_gram_T(const double* Y, long long B, int M, int R, const unsigned int* sigR, const double* p,
-                               const double* v, const double* c, double scale, double* T, void* stream) {
+                               const double* v, const double* c, double scale, long long tile0, long long ntiles, double* T,
+                               void* stream) {
   if (B == 0) return JVMC_OK;
   if (!Y || !sigR || !p || !v || !c || !T || B < 0 || M <= 0 || R <= 0) return JVMC_ERR_ARG;
   const int wordsR = (R + 31) / 32;
@@ -219,9 +228,11 @@ extern "C" int jvmc_rbm_gram_T(const double* Y, long long B, int M, int R, const
   cudaFuncSetAttribute(gram_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   long long nT = (B + T_TS - 1) / T_TS;
   long long tiles = nT * (nT + 1) / 2;
-  if (tiles > 2147483647LL) return JVMC_ERR_UNSUPPORTED;
-  gram_t_kernel<<<(unsigned)tiles, 32 * (T_NCW + 1), smem, (cudaStream_t)stream>>>(
-      (const cplx*)Y, B, M, R, sigR, wordsR, p, (const cplx*)v, c, scale, (cplx*)T);
+  if (ntiles <= 0) { tile0 = 0; ntiles = tiles; }
+  if (tile0 < 0 || tile0 + ntiles > tiles) return JVMC_ERR_ARG;
+  if (ntiles > 2147483647LL) return JVMC_ERR_UNSUPPORTED;
+  gram_t_kernel<<<(unsigned)ntiles, 32 * (T_NCW + 1), smem, (cudaStream_t)stream>>>(
+      (const cplx*)Y, B, M, R, sigR, wordsR, p, (const cplx*)v, c, scale, (cplx*)T, tile0);
   JVMC_CHECK_LAUNCH();
   return JVMC_OK;
 }

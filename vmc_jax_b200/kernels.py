@@ -423,8 +423,11 @@ def rbm_gram_S_auto(Y, sigT, mu, alpha, kappa, out=None, s=None, hasBias=False, 
     return rbm_gram_S(Y, sigT, mu, alpha, kappa, out)
 
 
-def rbm_gram_T(s, tau, p, mu, hasBias, scale=1.0):
-    """Centred tangent kernel T = scale * Obar Obar^dagger [B,B] from the Khatri-Rao factors (no dense O)."""
+def rbm_gram_T(s, tau, p, mu, hasBias, scale=1.0, part=None, v=None):
+    """Centred tangent kernel T = scale * Obar Obar^dagger [B,B] from the Khatri-Rao factors (no dense O).
+    part = (k, n): only the k-th of n equal ranges of the tile pairs is computed, into a zero-initialised T (the ranks'
+    parts add up to the full kernel: one SUM all-reduce).  v = O . conj(mu) per sample, if the caller has it already
+    (ranks evaluate it for their own samples and gather it)."""
     s = _c(s, I32)
     tau = _c(tau, CPX)
     p = _c(p, F64)
@@ -435,10 +438,20 @@ def rbm_gram_T(s, tau, p, mu, hasBias, scale=1.0):
     wordsR = (R + 31) // 32
     sigR = torch.empty((B, wordsR), dtype=I32, device=s.device)
     call("jvmc_pack_sigma_rows", ptr(s), B, N, int(hasBias), ptr(sigR))
-    v = rbm_krmatvec(s, tau, mu.conj().contiguous(), hasBias)
+    v = rbm_krmatvec(s, tau, mu.conj().contiguous(), hasBias) if v is None else _c(v, CPX)
     c = (mu.conj() * mu).real.sum().reshape(1).contiguous()
-    T = torch.empty((B, B), dtype=CPX, device=s.device)
-    call("jvmc_rbm_gram_T", ptr(tau), B, M, R, ptr(sigR), ptr(p), ptr(v), ptr(c), float(scale), ptr(T))
+    if part is None:
+        T = torch.empty((B, B), dtype=CPX, device=s.device)
+        t0, nt = 0, 0
+    else:
+        T = torch.zeros((B, B), dtype=CPX, device=s.device)
+        tiles = int(_lib.load().jvmc_rbm_gram_T_tiles(B))
+        k, n = part
+        t0 = tiles * k // n
+        nt = tiles * (k + 1) // n - t0
+        if nt == 0:
+            return T
+    call("jvmc_rbm_gram_T", ptr(tau), B, M, R, ptr(sigR), ptr(p), ptr(v), ptr(c), float(scale), int(t0), int(nt), ptr(T))
     return T
 
 

@@ -199,17 +199,19 @@ def gather(data):
         return flat
     global communicationTime
     t0 = time.perf_counter()
-    sizes = [torch.zeros(1, dtype=torch.int64, device=flat.device) for _ in range(commSize)]
-    dist.all_gather(sizes, torch.tensor([flat.shape[0]], dtype=torch.int64, device=flat.device))
+    # gloo (ranks sharing one GPU in the tests) has no all_gather of device tensors: its ranks exchange host copies
+    xdev = flat.device if dist.get_backend() == "nccl" else torch.device("cpu")
+    sizes = [torch.zeros(1, dtype=torch.int64, device=xdev) for _ in range(commSize)]
+    dist.all_gather(sizes, torch.tensor([flat.shape[0]], dtype=torch.int64, device=xdev))
     nmax = int(max(int(s.item()) for s in sizes))
     isC = flat.is_complex()
     buf = torch.view_as_real(flat) if isC else flat
-    pad = torch.zeros((nmax,) + tuple(buf.shape[1:]), dtype=buf.dtype, device=buf.device)
+    pad = torch.zeros((nmax,) + tuple(buf.shape[1:]), dtype=buf.dtype, device=xdev)
     pad[:buf.shape[0]] = buf
     outs = [torch.empty_like(pad) for _ in range(commSize)]
     dist.all_gather(outs, pad)
     parts = [o[:int(s.item())] for o, s in zip(outs, sizes)]
-    res = torch.cat(parts, dim=0)
+    res = torch.cat(parts, dim=0).to(flat.device)
     communicationTime += time.perf_counter() - t0
     return torch.view_as_complex(res.contiguous()) if isC else res
 
@@ -219,7 +221,7 @@ def gather_offset(nLocal):
     _refresh()
     if commSize == 1:
         return 0
-    dev = global_defs.myDevice
+    dev = global_defs.myDevice if dist.get_backend() == "nccl" else torch.device("cpu")
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(commSize)]
     dist.all_gather(sizes, torch.tensor([nLocal], dtype=torch.int64, device=dev))
     return int(sum(int(s.item()) for s in sizes[:rank]))

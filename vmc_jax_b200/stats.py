@@ -406,13 +406,17 @@ class RBMGradientObs(SampledObs):
         """Obar Obar^dagger over the samples of all ranks (reference stats.py:332-336) from the gathered
         Khatri-Rao factors (configs, tau, weights) -- O itself is never formed or communicated."""
         mu = self.kr_mean()
-        if mpi.commSize > 1:
-            s_all = mpi.gather(self._s[None])
-            tau_all = mpi.gather(self._tau[None])
-            p_all = mpi.gather(self._p[None])
-        else:
-            s_all, tau_all, p_all = self._s, self._tau, self._p
-        return K.rbm_gram_T(s_all, tau_all, p_all, mu, self.hasBias, 2.0 if self.holomorphic else 1.0)
+        scale = 2.0 if self.holomorphic else 1.0
+        if mpi.commSize == 1:
+            return K.rbm_gram_T(self._s, self._tau, self._p, mu, self.hasBias, scale)
+        # every rank needs all Khatri-Rao factors (N_T (4N + 16M + 8) bytes in total), but T itself is formed ONCE over
+        # the ranks: rank k computes the k-th range of the Hermitian tile pairs, one SUM all-reduce assembles the kernel
+        s_all = mpi.gather(self._s[None])
+        tau_all = mpi.gather(self._tau[None])
+        p_all = mpi.gather(self._p[None])
+        v_all = mpi.gather(K.rbm_krmatvec(self._s, self._tau, mu.conj().contiguous(), self.hasBias)[None])
+        T = K.rbm_gram_T(s_all, tau_all, p_all, mu, self.hasBias, scale, part=(mpi.rank, mpi.commSize), v=v_all)
+        return mpi._all_reduce_sum(T)
 
     def minsr_contract(self, x):
         """-Obar^dagger x in the reference flat layout (jVMC/util/minsr.py:65) for the gathered vector x,
