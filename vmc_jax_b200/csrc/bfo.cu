@@ -142,7 +142,23 @@ __global__ void oloc_reduce_kernel(const cplx* __restrict__ matEl, const cplx* _
 //  * the warps of a CTA are re-aligned at every block of 32 strings, so that they request the same rows at about
 //    the same time and share them through L1 (ld.global.nc);
 //  * exp(lc_a) is tabulated once per CTA instead of one complex exponential per string and sample.
-constexpr int EL_MAXWPC = 8;
+// tunables (tools/build_variants.py compiles alternatives for A/B timing)
+#ifndef JVMC_EL_MAXWPC
+#define JVMC_EL_MAXWPC 8        // warps per CTA, one sample per warp
+#endif
+#ifndef JVMC_EL_MAXW_SPLIT
+#define JVMC_EL_MAXW_SPLIT 16   // warps per CTA when WPS warps share a sample
+#endif
+#ifndef JVMC_EL_MINB
+#define JVMC_EL_MINB 2          // minimum CTAs per SM promised to the compiler: 128 registers, 16 warps per SM
+#endif                          // (with 1 the compiler takes 212 registers and the kernel is 30 % slower)
+#ifndef JVMC_EL_MINB_SPLIT
+#define JVMC_EL_MINB_SPLIT 1    // the same for the kernels with several warps per sample (512-thread CTAs)
+#endif
+#ifndef JVMC_EL_WPS1_MAXM
+#define JVMC_EL_WPS1_MAXM 512   // largest M handled by one warp per sample
+#endif
+constexpr int EL_MAXWPC = JVMC_EL_MAXWPC;
 
 template <bool TWO, int SPW>
 __device__ __forceinline__ void flip_ratio(const cplx* __restrict__ T0, const cplx* __restrict__ T1,
@@ -175,6 +191,11 @@ __device__ __forceinline__ void flip_ratio(const cplx* __restrict__ T0, const cp
   for (int q = 0; q < SPW; ++q) p[q] = warp_cprod(cmul(pa[q], pb[q]));
 }
 
+// sign * x with sign = +-1 given as a sign-bit mask (0 / 0x80000000): one integer-pipe LOP3 instead of a DMUL
+__device__ __forceinline__ double xor_sign(double x, int mask) {
+  return __hiloint2double(__double2hiint(x) ^ mask, __double2loint(x));
+}
+
 // Same product with the sample's tau row held in registers (lane l owns the hidden units l + 32 k): no shared-memory
 // traffic at all in the inner loop, which otherwise binds before the fp64 pipe does (16 B of tau + 16 B of T per
 // ten DFMA).  JT = ceil(M / 32) exactly, so only the last k can run past the row: its index is clamped (jl) and its
@@ -185,18 +206,20 @@ template <bool TWO, int JT, int WPS>
 __device__ __forceinline__ cplx flip_ratio_reg(const cplx* __restrict__ T0, const cplx* __restrict__ T1,
                                                const cplx (&tr)[JT], double sg0, double sg1, int lane, int j0, int jl) {
   cplx pa = cmk(1.0, 0.0), pb = cmk(1.0, 0.0);
+  const int m0 = sg0 < 0.0 ? (int)0x80000000 : 0, m1 = sg1 < 0.0 ? (int)0x80000000 : 0;
   const cplx* p0 = T0 + j0;
   const cplx* p1 = TWO ? T1 + j0 : nullptr;
 #pragma unroll
   for (int k = 0; k < JT; ++k) {
     const cplx t0 = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? p0 + 32 * WPS * k : T0 + jl));
     const cplx tj = tr[k];
+    const cplx ta = cmk(xor_sign(t0.x, m0), xor_sign(t0.y, m0));   // sg0 * t0
     cplx f;
     if (!TWO) {
-      f = cmk(fma(sg0, fma(tj.x, t0.x, -tj.y * t0.y), 1.0), sg0 * fma(tj.x, t0.y, tj.y * t0.x));
+      f = cmk(fma(tj.x, ta.x, fma(-tj.y, ta.y, 1.0)), fma(tj.x, ta.y, tj.y * ta.x));
     } else {
       const cplx t1 = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? p1 + 32 * WPS * k : T1 + jl));
-      const cplx ta = cscale(t0, sg0), tb = cscale(t1, sg1);
+      const cplx tb = cmk(xor_sign(t1.x, m1), xor_sign(t1.y, m1));
       f = cadd(cadd(cmk(1.0, 0.0), cmul(ta, tb)), cmul(tj, cadd(ta, tb)));
       if (k == JT - 1 && j0 + 32 * WPS * k != jl) f = cmk(1.0, 0.0);   // padding lane of the ragged tail
     }
@@ -213,6 +236,7 @@ __device__ __forceinline__ cplx flip_ratio_reg_dual(const cplx* __restrict__ Ta,
                                                     const cplx (&tr)[JT], double sga, double sgb, int lane, int j0,
                                                     int jl) {
   cplx pa0 = cmk(1.0, 0.0), pa1 = cmk(1.0, 0.0), pb0 = cmk(1.0, 0.0), pb1 = cmk(1.0, 0.0);
+  const int ma = sga < 0.0 ? (int)0x80000000 : 0, mb = sgb < 0.0 ? (int)0x80000000 : 0;
   const cplx* qa = Ta + j0;
   const cplx* qb = Tb + j0;
 #pragma unroll
@@ -220,8 +244,12 @@ __device__ __forceinline__ cplx flip_ratio_reg_dual(const cplx* __restrict__ Ta,
     const cplx ta = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? qa + 32 * WPS * k : Ta + jl));
     const cplx tb = __ldg(reinterpret_cast<const double2*>(k < JT - 1 ? qb + 32 * WPS * k : Tb + jl));
     const cplx tj = tr[k];
-    const cplx fa = cmk(fma(sga, fma(tj.x, ta.x, -tj.y * ta.y), 1.0), sga * fma(tj.x, ta.y, tj.y * ta.x));
-    const cplx fb = cmk(fma(sgb, fma(tj.x, tb.x, -tj.y * tb.y), 1.0), sgb * fma(tj.x, tb.y, tj.y * tb.x));
+    // f = 1 + (sg t) tau_j: the sign goes onto the row entry by an XOR of the sign bits (integer pipe), which leaves
+    // 4 fp64 instructions per factor (3 DFMA + 1 DMUL) instead of 6
+    const cplx sa = cmk(xor_sign(ta.x, ma), xor_sign(ta.y, ma));
+    const cplx sb = cmk(xor_sign(tb.x, mb), xor_sign(tb.y, mb));
+    const cplx fa = cmk(fma(tj.x, sa.x, fma(-tj.y, sa.y, 1.0)), fma(tj.x, sa.y, tj.y * sa.x));
+    const cplx fb = cmk(fma(tj.x, sb.x, fma(-tj.y, sb.y, 1.0)), fma(tj.x, sb.y, tj.y * sb.x));
     if (k & 1) { pa1 = cmul(pa1, fa); pb1 = cmul(pb1, fb); } else { pa0 = cmul(pa0, fa); pb0 = cmul(pb0, fb); }
   }
   const cplx A = cmul(pa0, pa1), Bv = cmul(pb0, pb1);
@@ -236,7 +264,7 @@ __device__ __forceinline__ cplx flip_ratio_reg_dual(const cplx* __restrict__ Ta,
 }
 
 template <int SPW, int JT, int WPS>
-__global__ void __launch_bounds__(WPS > 1 ? 512 : EL_MAXWPC * 32)
+__global__ void __launch_bounds__(WPS > 1 ? JVMC_EL_MAXW_SPLIT * 32 : EL_MAXWPC * 32, WPS > 1 ? JVMC_EL_MINB_SPLIT : JVMC_EL_MINB)
 rbm_eloc_kernel(BfoTables t, const int32_t* __restrict__ s, const cplx* __restrict__ tauG, long long B, int N, int M,
                 const cplx* __restrict__ T, const cplx* __restrict__ lc, const cplx* __restrict__ pref,
                 int numDiag, cplx* __restrict__ out, int* __restrict__ errFlag) {
@@ -427,7 +455,7 @@ int launch_eloc(BfoTables t, const int32_t* s, const cplx* tau, long long B, int
   size_t smem;
   if (JT > 0) {
     // register path: shared memory only holds the configurations (per warp), exp(lc) and the exchange slots
-    const int maxw = WPS > 1 ? 16 : EL_MAXWPC;
+    const int maxw = WPS > 1 ? JVMC_EL_MAXW_SPLIT : EL_MAXWPC;
     long long groups = maxw / WPS;
     if (B < groups) groups = B;
     wpc = (int)groups * WPS;
@@ -545,7 +573,8 @@ extern "C" int jvmc_rbm_eloc_bfo(const int32_t* s, const double* tau, long long 
   // tau in registers: one warp per sample up to M = 512, then 2 / 4 / 8 warps per sample (M <= 4096); the weight
   // rows are shared through L1 by the warps of a CTA
   if (M <= 256) { JVMC_ELOC_LO(1) }
-  else if (M <= 512) { JVMC_ELOC_JT(1) }
+  else if (M <= JVMC_EL_WPS1_MAXM) { JVMC_ELOC_JT(1) }
+  else if (M <= 512) { JVMC_ELOC_LO(2) }
   else if (M <= 1024) { JVMC_ELOC_JT(2) }
   else if (M <= 2048) { JVMC_ELOC_JT(4) }
   else if (M <= 4096) { JVMC_ELOC_JT(8) }

@@ -24,6 +24,16 @@
 namespace {
 
 constexpr int MC_WPC = 4;  // warps (= chains) per CTA
+// largest M handled by 1 / 2 / 4 warps per chain (tunables, tools/build_variants.py)
+#ifndef JVMC_MC_MAXM1
+#define JVMC_MC_MAXM1 512
+#endif
+#ifndef JVMC_MC_MAXM2
+#define JVMC_MC_MAXM2 1024
+#endif
+#ifndef JVMC_MC_MAXM4
+#define JVMC_MC_MAXM4 2048
+#endif
 
 struct McmcArgs {
   int32_t* states;
@@ -270,6 +280,42 @@ rbm_mcmc_kernel(McmcArgs a) {
 // WPCH > 1 (large M): one chain per CTA, its hidden units split over WPCH warps (slices of 32 JT units); the
 // partial products meet in shared memory (one __syncthreads per Metropolis step, double-buffered slots) and every
 // warp takes the same accept decision from the same RNG counters.
+// Code size is what this kernel has to watch: its Metropolis loop must stay inside the 32 KB L1.5 instruction cache
+// (ncu: 14 % of the warp samples were "no instruction" stalls with two inlined copies of the 13-times unrolled
+// refresh and IEEE divisions in the accept path -- 17.7 k SASS instructions).
+//  * the log-cosh / tanh evaluation of the (rare) refresh is an out-of-line call;
+//  * the accept path divides by Newton iterations on the hardware reciprocal seed (MUFU.RCP64H): 1 + tau n is
+//    O(1) there, so the IEEE slow paths (denormals, overflow) that `1.0 / x` carries along are dead weight.
+// tau_j = tanh(b_j + sum_i sigma_i W_ij) of one hidden unit from the bit-packed configuration in shared memory
+__device__ __noinline__ void refresh_unit(const cplx* __restrict__ W, const cplx* __restrict__ bias,
+                                          const uint32_t* sbits, int N, int M, int j, double* out2) {
+  cplx acc = bias ? bias[j] : cmk(0.0, 0.0);
+#pragma unroll 4
+  for (int i = 0; i < N; ++i) {
+    const double sg = ((sbits[i >> 5] >> (i & 31)) & 1u) ? 1.0 : -1.0;
+    const cplx w = W[(size_t)i * M + j];
+    acc.x = fma(sg, w.x, acc.x);
+    acc.y = fma(sg, w.y, acc.y);
+  }
+  cplx l, t;
+  lncosh_tanh(acc, l, t);
+  out2[0] = t.x; out2[1] = t.y;
+}
+__device__ __forceinline__ double rcp_newton(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // ~2^-20 relative
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);                                    // third step: below 1 ulp whatever the seed quality
+  return fma(r, e, r);
+}
+__device__ __forceinline__ cplx cdiv_fast(cplx a, cplx b) {
+  const double inv = rcp_newton(cabs2(b));
+  return cmk(fma(a.x, b.x, a.y * b.y) * inv, fma(a.y, b.x, -a.x * b.y) * inv);
+}
+
 template <int JT, int WPCH>
 __global__ void __launch_bounds__(WPCH == 1 ? MC_WPC * 32 : WPCH * 32)
 rbm_mcmc_flip_kernel(McmcArgs a) {
@@ -330,15 +376,9 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
       const int j = jbase + lane + 32 * k;
       cplx t = cmk(0.0, 0.0);
       if (j < M) {
-        cplx acc = hasBias ? a.bias[j] : cmk(0.0, 0.0);
-        for (int i = 0; i < N; ++i) {
-          double sg = ((sbits[i >> 5] >> (i & 31)) & 1u) ? 1.0 : -1.0;
-          cplx w = a.W[(size_t)i * M + j];
-          acc.x = fma(sg, w.x, acc.x);
-          acc.y = fma(sg, w.y, acc.y);
-        }
-        cplx l;
-        lncosh_tanh(acc, l, t);
+        double o2[2];
+        refresh_unit(a.W, a.bias, sbits, N, M, j, o2);
+        t = cmk(o2[0], o2[1]);
       }
       tau[k] = t;
     }
@@ -429,13 +469,16 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
     if (!gb) {
       // |1 + sga tau t|^2 = (1 + sga Re)^2 + Im^2, two independent partial products
       double p0 = 1.0, p1 = 1.0;
+      const int smask = sga < 0.0 ? (int)0x80000000 : 0;
 #pragma unroll
       for (int k = 0; k < JT; ++k) {
         const cplx tj = tau[k];
         const cplx t = tv[32 * k];
-        const double re = fma(tj.x, t.x, -tj.y * t.y);
+        // 1 + sga Re(tau t): the sign is XORed into the row entry (integer pipe), 2 DFMA instead of DMUL + 2 DFMA
+        const double tsx = __hiloint2double(__double2hiint(t.x) ^ smask, __double2loint(t.x));
+        const double tsy = __hiloint2double(__double2hiint(t.y) ^ smask, __double2loint(t.y));
+        const double fr = fma(tj.x, tsx, fma(-tj.y, tsy, 1.0));
         const double im = fma(tj.x, t.y, tj.y * t.x);
-        const double fr = fma(sga, re, 1.0);
         const double f2 = fma(fr, fr, im * im);
         if (k & 1) p1 *= f2; else p0 *= f2;
       }
@@ -450,7 +493,7 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
         for (int k = 0; k < JT; ++k) {
           const cplx tj = tau[k];
           const cplx n = cscale(tv[32 * k], sga);
-          const cplx tn = cdiv(cadd(tj, n), cadd(cmk(1.0, 0.0), cmul(tj, n)));
+          const cplx tn = cdiv_fast(cadd(tj, n), cadd(cmk(1.0, 0.0), cmul(tj, n)));
           tau[k] = cscale(tn, gsn);
         }
       }
@@ -464,7 +507,7 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
           const cplx tj = tau[k];
           const cplx n = cscale(tv[32 * k], sga);
           cplx f = cadd(cmk(1.0, 0.0), cmul(tj, n));
-          const cplx t1 = cdiv(cadd(tj, n), f);
+          const cplx t1 = cdiv_fast(cadd(tj, n), f);
           f = cmul(f, csub(cmk(1.0, 0.0), cmul(t1, a.tb2[j])));
           prod *= cabs2(f);
         }
@@ -482,9 +525,9 @@ rbm_mcmc_flip_kernel(McmcArgs a) {
           if (j < M) {
             const cplx tj = tau[k];
             const cplx n = cscale(tv[32 * k], sga);
-            cplx tn = cdiv(cadd(tj, n), cadd(cmk(1.0, 0.0), cmul(tj, n)));
+            cplx tn = cdiv_fast(cadd(tj, n), cadd(cmk(1.0, 0.0), cmul(tj, n)));
             const cplx b2 = a.tb2[j];
-            tn = cdiv(csub(b2, tn), csub(cmk(1.0, 0.0), cmul(b2, tn)));
+            tn = cdiv_fast(csub(b2, tn), csub(cmk(1.0, 0.0), cmul(b2, tn)));
             tau[k] = tn;
           }
         }
@@ -552,6 +595,14 @@ int dispatch_flip(const McmcArgs& a, cudaStream_t stream) {
       default: break;
     }
   }
+#ifdef JVMC_MC_LOWJT   // variants that split smaller M over several warps (tools/build_variants.py)
+  else {
+    switch (jt) {
+      JVMC_FLIP(5); JVMC_FLIP(6); JVMC_FLIP(7); JVMC_FLIP(8);
+      default: break;
+    }
+  }
+#endif
   switch (jt) {
     JVMC_FLIP(9); JVMC_FLIP(10); JVMC_FLIP(11); JVMC_FLIP(12); JVMC_FLIP(13); JVMC_FLIP(14); JVMC_FLIP(15); JVMC_FLIP(16);
     default: return JVMC_ERR_UNSUPPORTED;
@@ -587,9 +638,9 @@ extern "C" int jvmc_rbm_mcmc(int32_t* states, long long C, int N, int M, const d
   if (proposer != 2 && !g_mcmc_generic) {
     // single-flip fast path: one warp per chain up to M = 512, then 2 / 4 / 8 warps per chain (M <= 4096)
     int rc = JVMC_ERR_UNSUPPORTED;
-    if (M <= 512) rc = dispatch_flip<1>(a, (cudaStream_t)stream);
-    else if (M <= 1024) rc = dispatch_flip<2>(a, (cudaStream_t)stream);
-    else if (M <= 2048) rc = dispatch_flip<4>(a, (cudaStream_t)stream);
+    if (M <= JVMC_MC_MAXM1) rc = dispatch_flip<1>(a, (cudaStream_t)stream);
+    else if (M <= JVMC_MC_MAXM2) rc = dispatch_flip<2>(a, (cudaStream_t)stream);
+    else if (M <= JVMC_MC_MAXM4) rc = dispatch_flip<4>(a, (cudaStream_t)stream);
     else if (M <= 4096) rc = dispatch_flip<8>(a, (cudaStream_t)stream);
     if (rc != JVMC_ERR_UNSUPPORTED) return rc;
   }
