@@ -198,6 +198,19 @@ int jvmc_cnn_mcmc(const int* desc, int ndesc, const double* theta, int32_t* stat
                   unsigned long long seed, unsigned long long step0, long long chain0, int proposer, double mu,
                   int sweepSteps, long long thermSteps, int numSamplesPerChain, int32_t* out,
                   unsigned long long* counters, void* stream);
+/* Incremental fast paths for stride-1 nets (csrc/cnn_inc.cu): a move changing one or two sites only re-evaluates the
+ * (l (F-1) + 1)^d affected positions of layer l from activations cached in shared memory.  Both answer
+ * JVMC_ERR_UNSUPPORTED for nets outside their scope (stride > 1, > 4 layers, state beyond shared memory); jvmc_cnn_mcmc
+ * tries jvmc_cnn_mcmc_inc first.  jvmc_cnn_eloc_bfo: fused local energy for nets.CNN <- Operator.get_O_loc
+ * (base.py:166-192); operator tables as for jvmc_rbm_eloc_bfo.  jvmc_cnn_set_generic(1) disables both (A/B knob). */
+int jvmc_cnn_mcmc_inc(const int* desc, int ndesc, const double* theta, int32_t* states, long long C,
+                  unsigned long long seed, unsigned long long step0, long long chain0, int proposer, double mu,
+                  int sweepSteps, long long thermSteps, int numSamplesPerChain, int32_t* out,
+                  unsigned long long* counters, void* stream);
+int jvmc_cnn_eloc_bfo(const int* desc, int ndesc, const double* theta, const int32_t* s, long long B, int numOps, int len,
+                      int lDim, const int32_t* idx, const int32_t* map, const double* matEls, const int32_t* fermi,
+                      const uint8_t* isDiag, int numDiag, const double* pref, double* out, int* errFlag, void* stream);
+int jvmc_cnn_set_generic(int on);
 
 /* ---- the whole regularised solve of one step as single entry points (so that a binding without Python between
  * kernels can call it): TDVP.solve, reference jVMC/util/tdvp.py:153-213, and MinSR.solve, jVMC/util/minsr.py:59-78.

@@ -574,6 +574,62 @@ def check_cnn_sampler(shape=(6,), F=(3,), channels=(2,), proposer="spin_flip", C
     return pval
 
 
+def check_cnn_inc_sampler(shape=(6, 6), F=(3, 3), channels=(3, 2), act=("elu",), proposer="spin_flip_zeroMag", C=37,
+                          sweeps=6, seed=77, mu=2.0):
+    """Incremental CNN sampler (csrc/cnn_inc.cu, one warp per chain, cached activations) against the generic kernel
+    (full forward pass per proposal, the reference's algorithm sampler.py:327-356): same Philox counters and proposal
+    rules, so the chains coincide bit for bit unless an acceptance probability sits within rounding of its uniform
+    number (probability ~1e-13 per step)."""
+    from vmc_jax_b200 import _lib
+    cd, theta, kw = _cnn(shape, F, channels, (1,) * len(shape), act, True, False, 11)
+    N = int(np.prod(shape))
+    init = np.array(([1, 0] * N)[:N], np.int32)
+    res = []
+    for generic in (0, 1):
+        _lib.load().jvmc_cnn_set_generic(generic)
+        try:
+            states = torch.zeros((C, N), dtype=torch.int32, device=DEV)
+            states[:] = dev(init)
+            counters = torch.zeros(2, dtype=torch.int64, device=DEV)
+            cfg = host(K.cnn_mcmc(states, dev(theta), cd, seed, 5, 3, proposer, mu, N, 2 * N, sweeps, counters))
+            res.append((cfg, host(counters), host(states)))
+        finally:
+            _lib.load().jvmc_cnn_set_generic(0)
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    assert res[0][1][0] == C * (2 + sweeps) * N and 0 < res[0][1][1] <= res[0][1][0]
+    return res[0][1]
+
+
+def check_cnn_eloc(strings, shape=(4, 4), F=(3, 3), channels=(3, 2), act=("elu",), bias=True, B=41, seed=5, args=()):
+    """Fused incremental CNN local energy (jvmc_cnn_eloc_bfo) vs the reference's algorithm on the oracle
+    (s' -> psi(s'), operator/base.py:166-192) and vs the generic device route."""
+    from vmc_jax_b200 import _lib
+    cd, theta, kw = _cnn(shape, F, channels, (1,) * len(shape), act, bias, False, seed)
+    N = int(np.prod(shape))
+    tab = obfo.Tables(strings)
+    s = rand_configs(B, N, seed + 1)
+    f = lambda x: ocnn.cnn_logpsi(x.reshape((-1,) + tuple(shape)), theta, **kw).astype(np.complex128)
+    ref = obfo.get_O_loc(tab, s, f, *args)
+    ds, dth = dev(s), dev(theta)
+    dt = op_tables_to_device(tab)
+    pref = dev(tab.eval_prefactors(*args))
+    res = K.cnn_eloc(ds, dth, cd, dt, pref)
+    assert res is not None, "the net is inside the incremental kernel's scope"
+    e_fused, err = res
+    assert int(err.item()) == 0
+    sp, m, cnt = K.bfo_s_primes(ds, dt, pref)
+    e_gen = host(K.oloc_reduce(m, K.cnn_logpsi(ds, dth, cd), K.cnn_logpsi(sp, dth, cd).reshape(m.shape)))
+    r1, r2 = relerr(host(e_fused), ref), relerr(e_gen, ref)
+    assert r1 < RTOL and r2 < RTOL, (r1, r2)
+    _lib.load().jvmc_cnn_set_generic(1)
+    try:
+        assert K.cnn_eloc(ds, dth, cd, dt, pref) is None
+    finally:
+        _lib.load().jvmc_cnn_set_generic(0)
+    return r1
+
+
 def smoke_check():
     assert torch.cuda.is_available(), "smoke() needs a CUDA device"
     check_logpsi(N=8, M=16, B=64)

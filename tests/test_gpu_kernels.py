@@ -258,6 +258,45 @@ def test_cnn_sampler_chi2(shape, F, proposer, sector):
     G.check_cnn_sampler(shape=shape, F=F, proposer=proposer, sector=sector)
 
 
+@pytest.mark.parametrize("shape,F,channels,act,proposer", [
+    ((6, 6), (3, 3), (3, 2), ("elu",), "spin_flip_zeroMag"),
+    ((6, 6), (3, 3), (3, 2), ("elu",), "spin_flip"),
+    ((4, 6), (2, 3), (2, 3, 2), ("poly6", "tanh", "elu"), "spin_flip_Z2"),
+    ((10,), (4,), (5,), ("poly5",), "spin_flip_zeroMag"),
+    ((3, 4), (3, 3), (2, 2, 2), ("elu",), "spin_flip"),               # boxes wrap around the whole lattice
+    ((12, 12), (3, 3), (6, 4), ("elu",), "spin_flip_zeroMag")])        # BASELINE configs[3] net
+def test_cnn_incremental_sampler_equals_full_forward_sampler(shape, F, channels, act, proposer):
+    G.check_cnn_inc_sampler(shape, F, channels, act, proposer)
+
+
+def _heisenberg_strings(shape):
+    Lx, Ly = shape if len(shape) == 2 else (shape[0], 1)
+    out = []
+    for x in range(Lx):
+        for y in range(Ly):
+            i = x * Ly + y
+            nbrs = [x * Ly + (y + 1) % Ly] if Ly > 1 else []
+            nbrs.append(((x + 1) % Lx) * Ly + y)
+            for j in nbrs:
+                if j == i:
+                    continue
+                out += [(-0.25, [G.obfo.Sx(i), G.obfo.Sx(j)]), (-0.25, [G.obfo.Sy(i), G.obfo.Sy(j)]),
+                        (0.25, [G.obfo.Sz(i), G.obfo.Sz(j)])]
+    return out
+
+
+@pytest.mark.parametrize("shape,F,channels,act,kind", [
+    ((4, 4), (3, 3), (3, 2), ("elu",), "heisenberg"),
+    ((4, 4), (3, 3), (3, 2), ("elu",), "tfim"),
+    ((4, 6), (2, 3), (2, 3, 2), ("poly6", "tanh", "elu"), "heisenberg"),
+    ((10,), (4,), (5,), ("poly5",), "tfim"),
+    ((10,), (3,), (4, 3), ("elu",), "heisenberg"),
+    ((3, 4), (3, 3), (2, 2, 2), ("elu",), "heisenberg")])
+def test_cnn_fused_eloc(shape, F, channels, act, kind):
+    strings = _heisenberg_strings(shape) if kind == "heisenberg" else G.obfo.tfim_strings(shape, -0.8)
+    G.check_cnn_eloc(strings, shape, F, channels, act)
+
+
 @pytest.mark.parametrize("R,M", [(3, 5), (7, 24), (4, 64), (11, 33)])
 def test_hermitian_mirror_blocks(R, M):
     """rebuilds the part of a Hermitian matrix below the block diagonal from the part above (multi-GPU reduction)."""

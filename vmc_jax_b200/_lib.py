@@ -77,6 +77,11 @@ _SIGS = {
     "jvmc_cnn_grad": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ll, c_ptr, c_ptr]),
     "jvmc_cnn_mcmc": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ll, c_ull, c_ull, c_ll, c_int, c_dbl, c_int, c_ll, c_int,
                               c_ptr, c_ptr, c_ptr]),
+    "jvmc_cnn_mcmc_inc": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ll, c_ull, c_ull, c_ll, c_int, c_dbl, c_int, c_ll, c_int,
+                              c_ptr, c_ptr, c_ptr]),
+    "jvmc_cnn_eloc_bfo": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ll, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int,
+                                  c_ptr, c_ptr, c_ptr, c_ptr]),
+    "jvmc_cnn_set_generic": (c_int, [c_int]),
     "jvmc_symrbm_logpsi": (c_int, [c_ptr, c_ll, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "jvmc_symrbm_grad": (c_int, [c_ptr, c_ll, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr,
                                  c_ptr]),

@@ -12,46 +12,9 @@
 // (if the layer has one), then the kernel in C order [Fx, Fy, Cin, Cout].  One CTA per sample / chain; activations
 // live in shared memory.  Correctness-first kernels for the "next" row of the scope table (config 4).
 #include "common.cuh"
+#include "cnn_common.cuh"
 
 namespace {
-
-constexpr int CNN_MAXL = 8;
-
-struct CnnDesc {
-  int nl;                 // layers
-  int Lx, Ly;             // lattice (Ly = 1 for chains)
-  int Fx, Fy, sx, sy;     // filter diameter and stride per axis
-  int ch[CNN_MAXL + 1];   // channels, ch[0] = 1
-  int ox[CNN_MAXL + 1], oy[CNN_MAXL + 1];   // spatial size after layer l (index 0: input)
-  int act[CNN_MAXL];      // 0 elu, 1 relu, 2 tanh, 3 poly5, 4 poly6, 5 square
-  int hasBias[CNN_MAXL];
-  int offB[CNN_MAXL], offK[CNN_MAXL];       // offsets into theta
-  int offA[CNN_MAXL + 1]; // offsets of the layer outputs in the activation scratch (index 0: input)
-  int totA;               // total activation elements (input + all layers)
-  int P;                  // number of parameters
-  double nrm;             // sqrt(ox[nl] oy[nl] ch[nl])
-};
-
-__device__ __forceinline__ double actf(int a, double z) {
-  switch (a) {
-    case 0: return z > 0.0 ? z : expm1(z);
-    case 1: return z > 0.0 ? z : 0.0;
-    case 2: return tanh(z);
-    case 3: { const double q = z * z; return ((0.133333333 * q - 0.333333333) * q + 1.) * z; }
-    case 4: { const double q = z * z; return ((0.022222222 * q - 0.083333333) * q + 0.5) * q; }
-    default: return z * z;
-  }
-}
-__device__ __forceinline__ double dactf(int a, double z) {
-  switch (a) {
-    case 0: return z > 0.0 ? 1.0 : exp(z);
-    case 1: return z > 0.0 ? 1.0 : 0.0;
-    case 2: { const double t = tanh(z); return 1.0 - t * t; }
-    case 3: { const double q = z * z; return (5.0 * 0.133333333 * q - 3.0 * 0.333333333) * q + 1.; }
-    case 4: { const double q = z * z; return ((6.0 * 0.022222222 * q - 4.0 * 0.083333333) * q + 2.0 * 0.5) * z; }
-    default: return 2.0 * z;
-  }
-}
 
 // pre-activation of output element (px, py, co) of layer l from the previous layer's output `in`
 __device__ __forceinline__ double conv_at(const CnnDesc& d, int l, const double* __restrict__ theta,
@@ -296,37 +259,6 @@ __global__ void cnn_mcmc_kernel(CnnDesc d, const double* theta, CnnMcmcArgs a) {
   }
 }
 
-// desc: int array [nl, Lx, Ly, Fx, Fy, sx, sy, firstLayerBias, bias, ch_1..ch_nl, act_1..act_nl]
-int make_desc(const int* h, int n, CnnDesc& d) {
-  if (n < 9) return JVMC_ERR_ARG;
-  d.nl = h[0];
-  if (d.nl < 1 || d.nl > CNN_MAXL || n != 9 + 2 * d.nl) return JVMC_ERR_ARG;
-  d.Lx = h[1]; d.Ly = h[2]; d.Fx = h[3]; d.Fy = h[4]; d.sx = h[5]; d.sy = h[6];
-  if (d.Lx < 1 || d.Ly < 1 || d.Fx < 1 || d.Fy < 1 || d.sx < 1 || d.sy < 1) return JVMC_ERR_ARG;
-  d.ch[0] = 1; d.ox[0] = d.Lx; d.oy[0] = d.Ly;
-  int off = 0, offA = d.Lx * d.Ly;
-  d.offA[0] = 0;
-  for (int l = 0; l < d.nl; ++l) {
-    d.ch[l + 1] = h[9 + l];
-    d.act[l] = h[9 + d.nl + l];
-    if (d.ch[l + 1] < 1 || d.act[l] < 0 || d.act[l] > 5) return JVMC_ERR_ARG;
-    d.hasBias[l] = (l == 0) ? h[7] : h[8];
-    // wrap padding by F-1 then VALID convolution with stride s: floor((L - 1) / s) + 1 outputs
-    d.ox[l + 1] = (d.ox[l] - 1) / d.sx + 1;
-    d.oy[l + 1] = (d.oy[l] - 1) / d.sy + 1;
-    d.offB[l] = off;
-    if (d.hasBias[l]) off += d.ch[l + 1];
-    d.offK[l] = off;
-    off += d.Fx * d.Fy * d.ch[l] * d.ch[l + 1];
-    d.offA[l + 1] = offA;
-    offA += d.ox[l + 1] * d.oy[l + 1] * d.ch[l + 1];
-  }
-  d.P = off;
-  d.totA = offA;
-  d.nrm = sqrt((double)(d.ox[d.nl] * d.oy[d.nl] * d.ch[d.nl]));
-  return JVMC_OK;
-}
-
 // threads per CTA: enough to give every thread a few output elements of the widest layer
 int cnn_threads(const CnnDesc& d) {
   int widest = 0;
@@ -374,12 +306,21 @@ extern "C" int jvmc_cnn_grad(const int* desc, int ndesc, const double* theta, co
   return JVMC_OK;
 }
 
+extern "C" int jvmc_cnn_mcmc_inc(const int* desc, int ndesc, const double* theta, int32_t* states, long long C,
+                                 unsigned long long seed, unsigned long long step0, long long chain0, int proposer,
+                                 double mu, int sweepSteps, long long thermSteps, int numSamplesPerChain, int32_t* out,
+                                 unsigned long long* counters, void* stream);
+
 extern "C" int jvmc_cnn_mcmc(const int* desc, int ndesc, const double* theta, int32_t* states, long long C,
                              unsigned long long seed, unsigned long long step0, long long chain0, int proposer, double mu,
                              int sweepSteps, long long thermSteps, int numSamplesPerChain, int32_t* out,
                              unsigned long long* counters, void* stream) {
+  // stride-1 nets: one warp per chain with incremental updates of the cached activations (cnn_inc.cu)
+  int rc = jvmc_cnn_mcmc_inc(desc, ndesc, theta, states, C, seed, step0, chain0, proposer, mu, sweepSteps, thermSteps,
+                             numSamplesPerChain, out, counters, stream);
+  if (rc != JVMC_ERR_UNSUPPORTED) return rc;
   CnnDesc d;
-  int rc = make_desc(desc, ndesc, d);
+  rc = make_desc(desc, ndesc, d);
   if (rc != JVMC_OK) return rc;
   if (!theta || !states || !counters || C < 0) return JVMC_ERR_ARG;
   if (numSamplesPerChain > 0 && !out) return JVMC_ERR_ARG;

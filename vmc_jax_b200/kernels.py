@@ -157,6 +157,25 @@ def cnn_mcmc(states, theta, cd, seed, step0, chain0, proposer, mu, sweepSteps, t
     return out
 
 
+def cnn_eloc(s, theta, cd, tab, pref):
+    """Fused local energy of a stride-1 CNN (incremental psi(s')/psi(s), csrc/cnn_inc.cu); None when the net or the
+    operator is outside the kernel's scope (the caller then takes the generic s' route)."""
+    s = _c(s, I32)
+    theta = _c(theta, F64)
+    pref = _c(pref, CPX)
+    B = s.shape[0]
+    out = torch.empty(B, dtype=CPX, device=s.device)
+    err = torch.zeros(1, dtype=I32, device=s.device)
+    _lib.require_cuda()
+    rc = _lib.load().jvmc_cnn_eloc_bfo(cd.arr, cd.n, ptr(theta), ptr(s), B, *tab.args(), tab.numDiag, ptr(pref), ptr(out),
+                                       ptr(err), _lib.stream())
+    if rc == -3:      # JVMC_ERR_UNSUPPORTED
+        return None
+    _lib.check(rc, "jvmc_cnn_eloc_bfo")
+    _lib.LAUNCHES += 1
+    return out, err
+
+
 class SymTables:
     """Device copies of a LatticeSymmetry in index form (perm, sign, inverse map, factors)."""
 

@@ -96,6 +96,16 @@ class Operator(metaclass=abc.ABCMeta):
             if _CHECK_ELOC_FLAG and int(err.item()) != 0:
                 raise RuntimeError("fused E_loc kernel reported an unsupported operator string (flag %d)" % int(err.item()))
             return out.reshape(lead)
+        if tab.cnn_fused_ok(psi):
+            lead = tuple(samples.shape[:2])
+            flat = samples.reshape(lead[0] * lead[1], -1).contiguous()
+            res = K.cnn_eloc(flat, psi.get_parameters(), psi._cnnDesc, tab.device_tables(), tab.eval_prefactors(*args))
+            if res is not None:
+                out, err = res
+                self._last_err = err
+                if _CHECK_ELOC_FLAG and int(err.item()) != 0:
+                    raise RuntimeError("fused CNN E_loc kernel reported an unsupported operator string (flag %d)" % int(err.item()))
+                return out.reshape(lead)
         if self.ElocBatchSize > 0:
             return self.get_O_loc_batched(samples, psi, logPsiS, self.ElocBatchSize, *args)
         sampleOffdConfigs, _ = self.get_s_primes(samples, *args)

@@ -188,6 +188,12 @@ class CompiledTables:
                 and self.lDim == 2 and self.maxOpStrLength <= 16 and not self.fermionic.any()
                 and all(len(t) <= 2 for t in self.nondiag_sites))
 
+    def cnn_fused_ok(self, psi):
+        """The incremental CNN local-energy kernel covers lDim=2, non-fermionic strings changing <= 2 sites."""
+        return (getattr(psi, "kind", "") == "cnn" and getattr(psi, "logarithmic", False)
+                and self.lDim == 2 and self.maxOpStrLength <= 16 and not self.fermionic.any()
+                and all(len(t) <= 2 for t in self.nondiag_sites))
+
 
 class BranchFreeOperator(Operator):
     """Operators whose strings map every basis state to at most one basis state (reference :311-487)."""
