@@ -1022,7 +1022,8 @@ def aux_config5_minsr(jVMC, op, torch, K, L=20, alpha=4, nsamp=2 ** 14, chains=1
 
 def aux_config4_cnn(jVMC, op, torch, L=12, nsamp=2 ** 13, chains=1184):
     """BASELINE configs[3] on ONE GPU, bounded: 2D Heisenberg J1 12x12 (Marshall-rotated), real CNN, exchange proposer:
-    sample + E_loc (s' enumeration + forward passes) + dense gradients + S, F.  Correctness-level kernels."""
+    sample (incremental sampler, csrc/cnn_inc.cu) + E_loc (fused, incremental psi(s')/psi(s)) + dense gradients + S, F
+    (DESIGN 4.5).  Every phase runs once untimed first (module load, shared-memory attributes, cuBLAS handles)."""
     dev = jVMC.global_defs.myDevice
     H = op.BranchFreeOperator(ElocBatchSize=2048)
     for x in range(L):
@@ -1041,14 +1042,17 @@ def aux_config4_cnn(jVMC, op, torch, L=12, nsamp=2 ** 13, chains=1184):
         torch.cuda.synchronize()
         t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
         return r, (time.perf_counter() - t0) * 1e3
-    (s, logPsi, p), t_s = timed(lambda: smp.sample())
-    Eloc, t_e = timed(lambda: H.get_O_loc(s, psi, logPsi))
     from vmc_jax_b200.stats import SampledObs
+    s, logPsi, p = smp.sample()
+    Eloc = H.get_O_loc(s, psi, logPsi)
 
     def stats():
         E = SampledObs(Eloc, p)
         G = SampledObs(psi.gradients(s), p)
         return E.mean(), G.covar(E), G.covar()
+    stats()
+    (s, logPsi, p), t_s = timed(lambda: smp.sample())
+    Eloc, t_e = timed(lambda: H.get_O_loc(s, psi, logPsi))
     (Em, F, S), t_g = timed(stats)
     B = s.shape[1]
     return {"config": "2D Heisenberg %dx%d, CNN F=(3,3) channels=(6,4) (P=%d real), exchange proposer, %d chains, %d "

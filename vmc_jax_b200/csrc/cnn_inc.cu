@@ -170,9 +170,10 @@ __device__ __forceinline__ void tap4(const double* __restrict__ kr, int C4, cons
 }
 
 // Full evaluation into the state buffer (a_0 must hold the configuration as +-1) by the NT threads of the group.
-// Returns log psi in every thread.
+// Returns log psi in every thread.  Out of line: the sampler calls it from four places and its loop must stay inside
+// the instruction cache.
 template <int NT, class S>
-__device__ double inc_forward(const IncLayout& L, const double* __restrict__ w, double* st, double* red, int tid) {
+__device__ __noinline__ double inc_forward(const IncLayout& L, const double* __restrict__ w, double* st, double* red, int tid) {
   const int N = L.N;
   const float invLy = 1.0f / (float)L.Ly;
   double sum = 0.0;
@@ -412,7 +413,7 @@ __device__ __forceinline__ int nth_set_site(unsigned word, int r, int lane) {
 // when shared memory, not threads, limits the chains per SM: four times the warps to issue from)
 template <int NT, class S>
 __global__ void __launch_bounds__(NT == 32 ? 256 : 128, NT == 32 ? 1 : 8)
-cnn_inc_mcmc_kernel(IncLayout L, const double* __restrict__ theta, IncMcmcArgs a, int perChainBytes) {
+cnn_inc_mcmc_kernel(const __grid_constant__ IncLayout L, const double* __restrict__ theta, IncMcmcArgs a, int perChainBytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* w = reinterpret_cast<double*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -546,7 +547,7 @@ cnn_inc_mcmc_kernel(IncLayout L, const double* __restrict__ theta, IncMcmcArgs a
 // one CTA per sample: the four warps evaluate the net once together, then take the off-diagonal strings in turn
 template <class S>
 __global__ void __launch_bounds__(128)
-cnn_inc_eloc_kernel(IncLayout L, const double* __restrict__ theta, BfoTables t, const int32_t* __restrict__ s, long long B,
+cnn_inc_eloc_kernel(const __grid_constant__ IncLayout L, const double* __restrict__ theta, BfoTables t, const int32_t* __restrict__ s, long long B,
                     const cplx* __restrict__ pref, int numDiag, cplx* __restrict__ out, int* __restrict__ errFlag,
                     int perWarpBytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
