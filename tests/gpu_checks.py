@@ -585,7 +585,7 @@ def check_cnn_inc_sampler(shape=(6, 6), F=(3, 3), channels=(3, 2), act=("elu",),
     N = int(np.prod(shape))
     init = np.array(([1, 0] * N)[:N], np.int32)
     res = []
-    for generic in (0, 1):
+    for generic in (0, 1, 2):        # incremental (two warps per chain), generic, incremental with four warps per chain
         _lib.load().jvmc_cnn_set_generic(generic)
         try:
             states = torch.zeros((C, N), dtype=torch.int32, device=DEV)
@@ -595,8 +595,9 @@ def check_cnn_inc_sampler(shape=(6, 6), F=(3, 3), channels=(3, 2), act=("elu",),
             res.append((cfg, host(counters), host(states)))
         finally:
             _lib.load().jvmc_cnn_set_generic(0)
-    assert np.array_equal(res[0][0], res[1][0])
-    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    for other in res[1:]:
+        assert np.array_equal(res[0][0], other[0])
+        assert np.array_equal(res[0][1], other[1]) and np.array_equal(res[0][2], other[2])
     assert res[0][1][0] == C * (2 + sweeps) * N and 0 < res[0][1][1] <= res[0][1][0]
     return res[0][1]
 

@@ -49,7 +49,10 @@ __device__ __forceinline__ double expm1_neg(double z) {
 
 __device__ __forceinline__ double actf(int a, double z) {
   switch (a) {
-    case 0: return z > 0.0 ? z : expm1_neg(z);
+    case 0: {   // branch-free: the evaluations of neighbouring channels interleave instead of serialising on divergent branches
+      const double e = expm1_neg(fmin(z, 0.0));
+      return z > 0.0 ? z : e;
+    }
     case 1: return z > 0.0 ? z : 0.0;
     case 2: return tanh(z);
     case 3: { const double q = z * z; return ((0.133333333 * q - 0.333333333) * q + 1.) * z; }

@@ -409,10 +409,10 @@ __device__ __forceinline__ int nth_set_site(unsigned word, int r, int lane) {
   return 32 * src + __shfl_sync(0xffffffffu, bit, src);
 }
 
-// NT = 32: one warp per chain, several chains per CTA; NT = 128: the four warps of a CTA share one chain (the layout
-// when shared memory, not threads, limits the chains per SM: four times the warps to issue from)
+// NT = 32: one warp per chain, several chains per CTA; NT = 64 / 128: the two / four warps of a CTA share one chain (the
+// layout when shared memory, not threads, limits the chains per SM: more warps to issue from)
 template <int NT, class S>
-__global__ void __launch_bounds__(NT == 32 ? 256 : 128, NT == 32 ? 1 : 8)
+__global__ void __launch_bounds__(NT == 32 ? 256 : NT, NT == 32 ? 1 : 8)
 cnn_inc_mcmc_kernel(const __grid_constant__ IncLayout L, const double* __restrict__ theta, IncMcmcArgs a, int perChainBytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* w = reinterpret_cast<double*>(smem_raw);
@@ -440,11 +440,10 @@ cnn_inc_mcmc_kernel(const __grid_constant__ IncLayout L, const double* __restric
     }
   }
   auto load_input = [&](unsigned wbits) {
-    if (NT == 32 || warp == 0)
-      for (int k = 0; k < 32; ++k) {
-        const int i = 32 * lane + k;
-        if (i < N) st[i] = ((wbits >> k) & 1u) ? 1.0 : -1.0;
-      }
+    for (int w0 = 0; w0 < N; w0 += 32) {          // word by word: consecutive lanes write consecutive sites
+      const unsigned wb = __shfl_sync(0xffffffffu, wbits, w0 >> 5);
+      if ((NT == 32 || warp == 0) && w0 + lane < N) st[w0 + lane] = ((wb >> lane) & 1u) ? 1.0 : -1.0;
+    }
     group_sync<NT>();
   };
   load_input(bits);
@@ -629,6 +628,8 @@ cnn_inc_eloc_kernel(const __grid_constant__ IncLayout L, const double* __restric
   }
 }
 
+int g_inc_nt = 64;
+
 template <class S>
 int launch_inc_mcmc(const IncLayout& L, const double* theta, const IncMcmcArgs& a, long long C, size_t wBytes, size_t perChain,
                     void* stream) {
@@ -637,8 +638,14 @@ int launch_inc_mcmc(const IncLayout& L, const double* theta, const IncMcmcArgs& 
   if (smem1 > INC_SMEM_SM) return JVMC_ERR_UNSUPPORTED;
   int perSm1 = (int)(INC_SMEM_SM / (smem1 + 1024));
   if (perSm1 > 32) perSm1 = 32;
-  if (perSm1 <= 16) {
-    // shared memory limits the residency: four warps per chain
+  if (perSm1 <= 16 && g_inc_nt == 64) {
+    // shared memory limits the residency: two warps per chain (measured at config 4: 28.6 ms against 31.2 ms with four
+    // and 65 ms with one; jvmc_cnn_set_generic(2) selects four for A/B runs)
+    if (smem1 > 48 * 1024)
+      cudaFuncSetAttribute(cnn_inc_mcmc_kernel<64, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    cudaFuncSetAttribute(cnn_inc_mcmc_kernel<64, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cnn_inc_mcmc_kernel<64, S><<<(unsigned)C, 64, smem1, (cudaStream_t)stream>>>(L, theta, a, (int)perChain);
+  } else if (perSm1 <= 16) {
     if (smem1 > 48 * 1024)
       cudaFuncSetAttribute(cnn_inc_mcmc_kernel<128, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
     // the chains per SM follow from shared memory: ask for the largest carve-out
@@ -677,7 +684,11 @@ inline bool is_cfg4(const IncLayout& L) {
 
 static int g_cnn_generic = 0;
 // development knob: 1 makes jvmc_cnn_mcmc_inc / jvmc_cnn_eloc_bfo answer JVMC_ERR_UNSUPPORTED (A/B against the generic path)
-extern "C" int jvmc_cnn_set_generic(int on) { g_cnn_generic = on; return JVMC_OK; }
+extern "C" int jvmc_cnn_set_generic(int on) {
+  g_cnn_generic = (on == 1);
+  g_inc_nt = (on == 2) ? 128 : 64;      // 2: incremental sampler with four instead of two warps per chain (A/B)
+  return JVMC_OK;
+}
 
 extern "C" int jvmc_cnn_mcmc_inc(const int* desc, int ndesc, const double* theta, int32_t* states, long long C,
                                  unsigned long long seed, unsigned long long step0, long long chain0, int proposer,
