@@ -273,10 +273,14 @@ __device__ double inc_delta(const IncLayout& L, const double* __restrict__ w, co
     double* an = zn + L.maxAff[l] * C;
     double* da = an + L.maxAff[l] * C;
     const double* zo = st + L.offZ[l];
-    for (int i = tid; i < n; i += NT) {
+    // work items: (affected position, chunk of four output channels)
+    const int nch = (C + 3) >> 2;
+    const float invNch = 1.0f / (float)nch;
+    for (int it = tid; it < n * nch; it += NT) {
+      const int i = nch == 1 ? it : (nch == 2 ? (it >> 1) : fast_div(it, nch, invNch));
+      const int co0 = 4 * (it - i * nch);
       const int px = lx[i], py = ly[i], p = px * Ly + py;
-#pragma unroll
-      for (int co0 = 0; co0 < C; co0 += 4) {
+      {
         double z[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) z[j] = (co0 + j < C) ? zo[(co0 + j) * N + p] : 0.0;
