@@ -202,7 +202,8 @@ int jvmc_cnn_mcmc(const int* desc, int ndesc, const double* theta, int32_t* stat
  * (l (F-1) + 1)^d affected positions of layer l from activations cached in shared memory.  Both answer
  * JVMC_ERR_UNSUPPORTED for nets outside their scope (stride > 1, > 4 layers, state beyond shared memory); jvmc_cnn_mcmc
  * tries jvmc_cnn_mcmc_inc first.  jvmc_cnn_eloc_bfo: fused local energy for nets.CNN <- Operator.get_O_loc
- * (base.py:166-192); operator tables as for jvmc_rbm_eloc_bfo.  jvmc_cnn_set_generic(1) disables both (A/B knob). */
+ * (base.py:166-192); operator tables as for jvmc_rbm_eloc_bfo.  jvmc_cnn_set_generic(1) disables both, (2) runs the incremental sampler with four instead
+ * of two warps per chain (A/B knobs for the tests and tools/cnn_bench.py). */
 int jvmc_cnn_mcmc_inc(const int* desc, int ndesc, const double* theta, int32_t* states, long long C,
                   unsigned long long seed, unsigned long long step0, long long chain0, int proposer, double mu,
                   int sweepSteps, long long thermSteps, int numSamplesPerChain, int32_t* out,

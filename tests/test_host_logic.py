@@ -285,5 +285,9 @@ def test_bench_reference_arm_and_argument_handling():
     assert d["samples"] == 16 and d["gram_cols"] == 16 * 32 and t > 0
     t, d = bench.cpu_tdvp_step(L=6, alpha=1, nsamp=200, chains=50)
     assert d["samples"] == 200 and np.isfinite(d["update_norm"])
+    # the MinSR workload (BASELINE configs[4]) has its own CPU step and is a registered workload of both arms
+    t, d = bench.cpu_minsr_step((3, 3), 3.04, 2, 12, 4)
+    assert d["samples"] == 12 and np.isfinite(d["update_max_abs"]) and d["update_max_abs"] > 0
+    assert bench.MINSR_WORKLOAD in bench.WORKLOADS and bench.WORKLOADS[bench.MINSR_WORKLOAD][0] == (20, 20)
     src = open(bench.__file__).read()
     assert "args.steps + args.warmup + 8" not in src
