@@ -457,6 +457,8 @@ cnn_inc_mcmc_kernel(const __grid_constant__ IncLayout L, const double* __restric
   long long nextEmit = a.thermSteps + a.K;
   int emitted = 0;
   int cnt[INC_MAXL + 1];
+  uint4 qa = make_uint4(0, 0, 0, 0);
+  uint32_t qb = 0;
   for (long long stp = 0; stp < total; ++stp) {
     const unsigned long long gs = a.step0 + (unsigned long long)stp;
     IncChange c;
@@ -465,7 +467,17 @@ cnn_inc_mcmc_kernel(const __grid_constant__ IncLayout L, const double* __restric
     double u = 0.0;
     int* px = reinterpret_cast<int*>(red + 8);         // proposal exchange slots (behind the list counts)
     if (NT == 32 || warp == 0) {
-    const uint4 r = rng((uint32_t)gs, (uint32_t)(gs >> 32), (uint32_t)gchain, (uint32_t)(gchain >> 32) << 8);
+    // Philox once per 32 steps: lane l evaluates the counters of step (batch base + l), the step's values come by shuffle
+    const int bidx = (int)(stp & 31);
+    if (bidx == 0) {
+      const unsigned long long gl = gs + (unsigned long long)lane;
+      qa = rng((uint32_t)gl, (uint32_t)(gl >> 32), (uint32_t)gchain, (uint32_t)(gchain >> 32) << 8);
+      if (a.proposer == 2)
+        qb = rng((uint32_t)gl, (uint32_t)(gl >> 32), (uint32_t)gchain, ((uint32_t)(gchain >> 32) << 8) | 1u).x;
+    }
+    uint4 r;
+    r.x = __shfl_sync(0xffffffffu, qa.x, bidx); r.y = __shfl_sync(0xffffffffu, qa.y, bidx);
+    r.z = __shfl_sync(0xffffffffu, qa.z, bidx); r.w = __shfl_sync(0xffffffffu, qa.w, bidx);
     u = u01_from_bits(r.z, r.w);
     if (a.proposer == 2) {
       // exchange the ru-th up spin with the rd-th down spin (sampler.py:42-64)
@@ -477,8 +489,7 @@ cnn_inc_mcmc_kernel(const __grid_constant__ IncLayout L, const double* __restric
         if (c.n == 0) { c.site[0] = id; c.delta[0] = 2.0; } else { c.site[1] = id; c.delta[1] = 2.0; }
         ++c.n;
       }
-      const uint4 r2 = rng((uint32_t)gs, (uint32_t)(gs >> 32), (uint32_t)gchain, ((uint32_t)(gchain >> 32) << 8) | 1u);
-      g = __umulhi(r2.x, 5u) == 0u;
+      g = __umulhi(__shfl_sync(0xffffffffu, qb, bidx), 5u) == 0u;
     } else {
       const int k = (int)__umulhi(r.x, (uint32_t)N);
       const unsigned wk = __shfl_sync(0xffffffffu, bits, k >> 5);
