@@ -58,12 +58,12 @@ def sample():
 
 tab = H._ensure_compiled(0)
 dt, pref = tab.device_tables(), tab.eval_prefactors()
-for generic in ([0] if a.no_generic else [0, 1]):
+for generic in ([0, 2] if a.no_generic else [0, 1]):
     _lib.load().jvmc_cnn_set_generic(generic)
     (cfg, counters), t_s = timed(sample)
     steps = a.chains * (a.therm + a.sweeps) * N
     acc = float(counters[1]) / float(counters[0])
-    name = "generic (full forward per proposal)" if generic else "incremental"
+    name = {0: "incremental", 1: "generic (full forward per proposal)", 2: "incremental, wide variant"}[generic]
     print("%s: sampler %.2f ms for %d samples, %.3g proposals (acceptance %.3f): %.2f us per proposal and chain, %.1f M proposals/s"
           % (name, t_s, cfg.shape[0], steps, acc, t_s * 1e3 / ((a.therm + a.sweeps) * N), steps / t_s / 1e3))
     s = cfg.reshape(1, cfg.shape[0], L, L)

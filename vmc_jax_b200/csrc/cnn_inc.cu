@@ -559,8 +559,8 @@ cnn_inc_mcmc_kernel(const __grid_constant__ IncLayout L, const double* __restric
 }
 
 // one CTA per sample: the four warps evaluate the net once together, then take the off-diagonal strings in turn
-template <class S>
-__global__ void __launch_bounds__(128)
+template <class S, int NW>
+__global__ void __launch_bounds__(32 * NW)
 cnn_inc_eloc_kernel(const __grid_constant__ IncLayout L, const double* __restrict__ theta, BfoTables t, const int32_t* __restrict__ s, long long B,
                     const cplx* __restrict__ pref, int numDiag, cplx* __restrict__ out, int* __restrict__ errFlag,
                     int perWarpBytes) {
@@ -569,8 +569,8 @@ cnn_inc_eloc_kernel(const __grid_constant__ IncLayout L, const double* __restric
   const int N = L.N;
   double* w = reinterpret_cast<double*>(smem_raw);
   double* st = w + L.wSize;
-  double* red = st + L.stateSize;                                   // [8]
-  int32_t* cfg = reinterpret_cast<int32_t*>(red + 8);
+  double* red = st + L.stateSize;                                   // [16]
+  int32_t* cfg = reinterpret_cast<int32_t*>(red + 16);
   unsigned char* scratch = reinterpret_cast<unsigned char*>(cfg + ((N + 3) & ~3)) + (size_t)warp * perWarpBytes;
   double* val = reinterpret_cast<double*>(scratch);
   int16_t* sh = reinterpret_cast<int16_t*>(val + L.valSize);
@@ -582,7 +582,7 @@ cnn_inc_eloc_kernel(const __grid_constant__ IncLayout L, const double* __restric
   }
   inc_clear_maps<32>(L, sh, lane);
   inc_load_weights(L, theta, w);                                    // (block barriers inside)
-  (void)inc_forward<128, S>(L, w, st, red, (int)threadIdx.x);
+  (void)inc_forward<32 * NW, S>(L, w, st, red, (int)threadIdx.x);
   cplx eloc = cmk(0.0, 0.0), diagAcc = cmk(0.0, 0.0);
   int cnt[INC_MAXL + 1];
   int rank = 0;
@@ -680,11 +680,19 @@ int launch_inc_mcmc(const IncLayout& L, const double* theta, const IncMcmcArgs& 
 template <class S>
 int launch_inc_eloc(const IncLayout& L, const double* theta, const BfoTables& t, const int32_t* s, long long B,
                     const cplx* pref, int numDiag, cplx* out, int* errFlag, int nw, size_t smem, size_t perWarp, void* stream) {
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(cnn_inc_eloc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(cnn_inc_eloc_kernel<S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cnn_inc_eloc_kernel<S><<<(unsigned)B, 32 * nw, smem, (cudaStream_t)stream>>>(L, theta, t, s, B, pref, numDiag, out, errFlag,
-                                                                            (int)perWarp);
+  if (nw == 8) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(cnn_inc_eloc_kernel<S, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(cnn_inc_eloc_kernel<S, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cnn_inc_eloc_kernel<S, 8><<<(unsigned)B, 256, smem, (cudaStream_t)stream>>>(L, theta, t, s, B, pref, numDiag, out, errFlag,
+                                                                             (int)perWarp);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(cnn_inc_eloc_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(cnn_inc_eloc_kernel<S, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cnn_inc_eloc_kernel<S, 4><<<(unsigned)B, 128, smem, (cudaStream_t)stream>>>(L, theta, t, s, B, pref, numDiag, out, errFlag,
+                                                                             (int)perWarp);
+  }
   JVMC_CHECK_LAUNCH();
   return JVMC_OK;
 }
@@ -741,9 +749,9 @@ extern "C" int jvmc_cnn_eloc_bfo(const int* desc, int ndesc, const double* theta
   if (g_cnn_generic || len > BFO_MAXLEN || len <= 0 || numOps <= 0 || lDim != 2 || !make_inc_layout(d, L))
     return JVMC_ERR_UNSUPPORTED;
   BfoTables t = make_tables(numOps, len, lDim, idx, map, matEls, fermi, isDiag);
-  const int nw = 4;
+  const int nw = g_inc_nt == 128 ? 8 : 4;      // warps per sample (8: A/B knob jvmc_cnn_set_generic(2))
   const size_t perWarp = (inc_scratch_bytes(L) + 15) & ~(size_t)15;
-  const size_t smem = (size_t)L.wSize * sizeof(double) + (size_t)L.stateSize * sizeof(double) + 8 * sizeof(double) +
+  const size_t smem = (size_t)L.wSize * sizeof(double) + (size_t)L.stateSize * sizeof(double) + 16 * sizeof(double) +
                       (size_t)((L.N + 3) & ~3) * sizeof(int32_t) + nw * perWarp;
   if (smem > INC_SMEM_SM) return JVMC_ERR_UNSUPPORTED;
   return is_cfg4(L) ? launch_inc_eloc<SpecCfg4>(L, theta, t, s, B, (const cplx*)pref, numDiag, (cplx*)out, errFlag, nw, smem,
