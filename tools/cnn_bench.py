@@ -58,7 +58,7 @@ def sample():
 
 tab = H._ensure_compiled(0)
 dt, pref = tab.device_tables(), tab.eval_prefactors()
-for generic in ([0, 2] if a.no_generic else [0, 1]):
+for generic in ([0] if a.no_generic else [0, 1]):
     _lib.load().jvmc_cnn_set_generic(generic)
     (cfg, counters), t_s = timed(sample)
     steps = a.chains * (a.therm + a.sweeps) * N

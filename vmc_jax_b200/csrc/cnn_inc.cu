@@ -303,7 +303,7 @@ __device__ double inc_delta(const IncLayout& L, const double* __restrict__ w, co
           const int16_t* pmap = sh + L.offMap[l - 1];
           const double* pda = val + L.offV[l - 1] + 2 * L.maxAff[l - 1] * Cp;
           const double* Kp = w + L.wK[l - 1];
-#pragma unroll
+#pragma unroll 1
           for (int fx = 0; fx < S_FX; ++fx) {
             const int qx = wrap_up(px + fx, Lx);
 #pragma unroll
