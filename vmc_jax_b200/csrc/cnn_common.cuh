@@ -24,7 +24,7 @@ struct CnnDesc {
 // expm1(z) for z <= 0 (the negative branch of elu, evaluated for every affected entry of every proposal): argument
 // reduction z = k ln2 + r, |r| <= ln2 / 2, Taylor polynomial of expm1(r) to r^14 (truncation 3e-19 relative),
 // result 2^k expm1(r) + (2^k - 1) without cancellation; 2e-16 relative against libm, a quarter of its instructions.
-__device__ __forceinline__ double expm1_neg(double z) {
+__device__ __noinline__ double expm1_neg(double z) {
   z = fmax(z, -64.0);                                   // expm1 = -1 to the last bit below
   const double k = rint(z * 1.4426950408889634);
   double r = fma(-k, 6.93147180369123816490e-01, z);
