@@ -8,8 +8,8 @@
 //   log psi' = log psi + sum_{p affected} (act(z_L'(p)) - act(z_L(p))) / nrm
 // with the pre-activations z_l and activations a_l of the current configuration cached in shared memory.
 //
-//  jvmc_cnn_mcmc_inc  <- MCSampler._sweep for nets.CNN with stride 1: one WARP per Markov chain, cached state updated
-//                        in place on acceptance; global flips (Z2 / zero-magnetisation proposers, sampler.py:28-64) and
+//  jvmc_cnn_mcmc_inc  <- MCSampler._sweep for nets.CNN with stride 1: one or two warps per Markov chain (two when shared
+//                        memory limits the chains per SM), cached state updated in place on acceptance; global flips (Z2 / zero-magnetisation proposers, sampler.py:28-64) and
 //                        the end of every sweep re-evaluate the net in full (bounds the drift of the cached sums)
 //  jvmc_cnn_eloc_bfo  <- Operator.get_O_loc for nets.CNN: one CTA per sample, full forward once, then every warp takes
 //                        off-diagonal strings and evaluates psi(s')/psi(s) from the delta (strings changing <= 2 sites)
