@@ -231,17 +231,20 @@ __device__ double inc_delta(const IncLayout& L, const double* __restrict__ w, co
   const int sx0 = fast_div(c.site[0], Ly, invLy), sy0 = c.site[0] - sx0 * Ly;
   const int sx1 = fast_div(c.site[1], Ly, invLy), sy1 = c.site[1] - sx1 * Ly;
   double dsum = 0.0;
+  // ---- affected positions of every layer: union of the boxes of the changed sites (ballot compaction by one warp per
+  // layer; with several warps in the group the layers are built concurrently by different warps)
+  {
+    const int gw = tid >> 5;                      // warp within the group
 #pragma unroll
-  for (int l = 1; l <= S_NL; ++l) {
-    // ---- affected positions: union of the boxes of the changed sites (first warp of the group; ballot compaction)
-    const int Wx = L.Wx[l], Wy = L.Wy[l], per = Wx * Wy, ncand = c.n * per;
-    uint16_t* lx = reinterpret_cast<uint16_t*>(sh) + L.offLst[l];
-    uint16_t* ly = lx + L.maxAff[l];
-    int16_t* map = sh + L.offMap[l];
-    const bool last = (l == S_NL);
-    int n = 0;
-    if (NT == 32 || tid < 32) {
+    for (int l = 1; l <= S_NL; ++l) {
+      if ((l - 1) % (NT / 32) != gw) continue;
+      const int Wx = L.Wx[l], Wy = L.Wy[l], per = Wx * Wy, ncand = c.n * per;
+      uint16_t* lx = reinterpret_cast<uint16_t*>(sh) + L.offLst[l];
+      uint16_t* ly = lx + L.maxAff[l];
+      int16_t* map = sh + L.offMap[l];
+      const bool last = (l == S_NL);
       const float invWy = 1.0f / (float)Wy;
+      int n = 0;
       for (int base = 0; base < ncand; base += 32) {
         const int cand = base + lane;
         bool keep = false;
@@ -262,11 +265,21 @@ __device__ double inc_delta(const IncLayout& L, const double* __restrict__ w, co
         }
         n += __popc(m);
       }
-      if (NT > 32 && tid == 0) reinterpret_cast<int*>(val + L.valSize - 12)[8 + l] = n;   // behind the 4 reduction slots
+      if (NT == 32) cnt[l] = n;
+      else if (lane == 0) reinterpret_cast<int*>(val + L.valSize - 12)[8 + l] = n;   // behind the 4 reduction slots
     }
     group_sync<NT>();
-    if (NT > 32) n = reinterpret_cast<const int*>(val + L.valSize - 12)[8 + l];
-    cnt[l] = n;
+    if (NT > 32) {
+#pragma unroll
+      for (int l = 1; l <= S_NL; ++l) cnt[l] = reinterpret_cast<const int*>(val + L.valSize - 12)[8 + l];
+    }
+  }
+#pragma unroll
+  for (int l = 1; l <= S_NL; ++l) {
+    const uint16_t* lx = reinterpret_cast<const uint16_t*>(sh) + L.offLst[l];
+    const uint16_t* ly = lx + L.maxAff[l];
+    const bool last = (l == S_NL);
+    const int n = cnt[l];
     // ---- new values: one thread per affected position, output channels in chunks of four
     const int C = S_C(l), C4 = S_C4(l), a = S_ACT(l - 1);
     double* zn = val + L.offV[l];
@@ -618,6 +631,9 @@ cnn_inc_eloc_kernel(const __grid_constant__ IncLayout L, const double* __restric
         live &= live - 1;
         mm = cadd(mm, cmk(__shfl_sync(0xffffffffu, m.x, nx), __shfl_sync(0xffffffffu, m.y, nx)));
       }
+      // matrix elements that cancel exactly (S^xS^x + S^yS^y on a bond of parallel spins) need no amplitude ratio:
+      // the reference adds m r and -m r with the same r
+      if (mm.x == 0.0 && mm.y == 0.0) continue;
       if ((rank++ % nw) != warp) continue;       // the CTA's warps take the distinct s' in turn
       if (nfl > 2) { if (lane == 0) atomicExch(errFlag, 1); continue; }
       IncChange c;
