@@ -341,9 +341,21 @@ __device__ double inc_delta(const IncLayout& L, const double* __restrict__ w, co
           }
       }
     }
-    group_sync<NT>();
+    if (l < S_NL) group_sync<NT>();             // (the reduction below synchronises after the last layer)
   }
-  // ---- leave the maps clean
+  // ---- sum over the group; the maps are cleaned between the two barriers of the reduction (every thread is past its
+  // last map read at the first one)
+  dsum = warp_sum(dsum);
+  double* red = val + L.valSize - 12;
+  if (NT > 32) {
+    if (lane == 0) red[tid >> 5] = dsum;
+    __syncthreads();
+    dsum = 0.0;
+#pragma unroll
+    for (int k = 0; k < NT / 32; ++k) dsum += red[k];
+  } else {
+    __syncwarp();
+  }
   for (int l = 1; l < S_NL; ++l) {
     const uint16_t* lx = reinterpret_cast<const uint16_t*>(sh) + L.offLst[l];
     const uint16_t* ly = lx + L.maxAff[l];
@@ -351,7 +363,7 @@ __device__ double inc_delta(const IncLayout& L, const double* __restrict__ w, co
     for (int i = tid; i < cnt[l]; i += NT) map[lx[i] * Ly + ly[i]] = -1;
   }
   group_sync<NT>();
-  return group_sum<NT>(dsum, val + L.valSize - 12) / L.nrm;
+  return dsum / L.nrm;
 }
 
 // Make the change of the last inc_delta the cached state.
