@@ -200,11 +200,13 @@ __device__ __noinline__ double inc_forward(const IncLayout& L, const double* __r
             tap4(Kp + ((fx * S_FY + fy) * ci_n) * C4 + co0, C4, in + q, N, ci_n, acc);
           }
         }
+        double av4[4];
+        actf4(a, acc, av4);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (co0 + j < co_n) {
             z[(co0 + j) * N + p] = acc[j];
-            const double av = actf(a, acc[j]);
+            const double av = av4[j];
             if (last) sum += av; else ao[(co0 + j) * N + p] = av;
           }
       }
@@ -326,14 +328,22 @@ __device__ double inc_delta(const IncLayout& L, const double* __restrict__ w, co
             }
           }
         }
+        double av4[4], ao4[4] = {0.0, 0.0, 0.0, 0.0};
+        actf4(a, z, av4);
+        if (last) {
+          double zo4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) zo4[j] = (co0 + j < C) ? zo[(co0 + j) * N + p] : 0.0;
+          actf4(a, zo4, ao4);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (co0 + j < C) {
             const int e = i * C + co0 + j;
             zn[e] = z[j];
-            const double av = actf(a, z[j]);
+            const double av = av4[j];
             if (last) {
-              dsum += av - actf(a, zo[(co0 + j) * N + p]);
+              dsum += av - ao4[j];
             } else {
               an[e] = av;
               da[e] = av - st[L.offA[l] + (co0 + j) * N + p];
