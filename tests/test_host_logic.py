@@ -88,12 +88,27 @@ def test_compile_tables_match_oracle():
     assert np.array_equal(tab.diag, T.diag)
     assert tab.maxOpStrLength == 3
     assert not tab.fused_ok(object())
+    # the fused local-energy kernels are chosen by the kind of net and the shape of the strings (<= 2 changed sites)
+
+    class _Psi:
+        def __init__(self, kind, kr):
+            self.kind, self.khatri_rao, self.logarithmic = kind, kr, True
+
+        def flip_tables(self):
+            return None
+    assert tab.fused_ok(_Psi("rbm", True)) and not tab.cnn_fused_ok(_Psi("rbm", True))
+    assert tab.cnn_fused_ok(_Psi("cnn", False)) and not tab.fused_ok(_Psi("cnn", False))
+    H3 = op.BranchFreeOperator()
+    H3.add(op.scal_opstr(1., (op.Sx(0), op.Sx(1), op.Sx(2))))       # three flipped sites: generic s' route
+    t3 = H3.compile()
+    assert not t3.cnn_fused_ok(_Psi("cnn", False)) and not t3.fused_ok(_Psi("rbm", True))
     # fermionic flags
     F = op.BranchFreeOperator()
     F.add(op.scal_opstr(1., (op.creation(1), op.annihilation(0))))
     F.add(op.scal_opstr(2., (op.number(0),)))
     ft = F.compile()
     assert ft.fermionic.tolist() == [[1, 1], [0, 0]] and ft.isDiag.tolist() == [0, 1]
+    assert not ft.cnn_fused_ok(_Psi("cnn", False))                  # Jordan-Wigner strings: generic route
 
 
 def test_td_prefactor_compiles():
